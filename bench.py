@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py -- attacker+defender env-steps/sec of the batched step, against the HBM roofline.
+
+    python bench.py --gpus 1 --steps 50 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the CPU arm (oracle port of the reference step on the host cores)
+
+Workload (BASELINE.json configs[2]): CyberBattleToyCtf-v0 with MARLon bounds (N=12, C=10), the
+MARLon attacker+defender pair step (AttackerEnvWrapper.step + DefenderEnvWrapper.step, reference_stale binding, SB3
+auto-reset), dense int8 action masks, 65536 envs per GPU; random VALID attacker actions and uniform defender actions
+(recorded once with the on-device sampler, then replayed: the env dynamics are deterministic so the replay is valid).
+One "step" = one launch of the fused step kernel over all envs of the rank.  Env instances shard across ranks with
+no data-path collective ("weak" scaling: fixed envs per GPU); the only collective is the per-rollout all-reduce of
+the 16-slot episode-statistics vector.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def workload_config(mask_mode=0):
+    from marlon_b200 import _abi, config, scenario, scenarios
+
+    comp = scenario.compile_scenario(scenarios.toyctf_environment())
+    # MultiAgentUniverse.build defaults (multiagent_universe.py:78-95) with ppo/train_marl.py:12-14 bounds
+    cfg = config.make_config(
+        _abi.MODE_MARLON, maximum_node_count=12, maximum_total_credentials=10, maximum_discoverable_credentials_per_action=5,
+        throws_on_invalid_actions=False, attacker_goal=config.AttackerGoal(own_atleast=6),
+        defender_constraint=config.DefenderConstraint(0.60), losing_reward=-5000.0,
+        attacker_max_timesteps=2000, attacker_invalid_action_reward_modifier=-1.0,
+        defender_enabled=True, defender_max_timesteps=2000, defender_invalid_action_reward=-1,
+        defender_reset_on_constraint_broken=True, defender_loss_reward=-5000.0, mask_mode=mask_mode)
+    return comp, cfg
+
+
+def algorithmic_bytes_per_env_step(comp, cfg, S_words):
+    """reference dtypes (int8 masks, int32 other observation fields), each state byte read once and
+    written once, actions read, rewards/flags written, no re-reads."""
+    n, N, C, LEAK = comp.n_nodes, cfg.maximum_node_count, cfg.maximum_total_credentials, cfg.maximum_discoverable_credentials_per_action
+    ident = comp.identifiers
+    P, L, R, props = len(ident.ports), len(ident.local_vulnerabilities), len(ident.remote_vulnerabilities), len(ident.properties)
+    att_small = 4 * (7 + 4 * LEAK + 2 * C + N * props + N)
+    masks = (N * L + N * N * R + N * N * P * C) if cfg.mask_mode == 0 else 4 * ((N + 31) // 32)
+    defender = (n + 12 * n + comp.n_services) if cfg.def_enabled else 0
+    state = 2 * 4 * S_words
+    io = 40 + (48 if cfg.def_enabled else 0) + 4 + 4 + 4
+    return dict(attacker_obs=att_small, masks=masks, defender_obs=defender, state_rw=state, actions_rewards_flags=io,
+                total=att_small + masks + defender + state + io)
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference step on the host cores (one process per core, numpy valid-action sampler)
+# ------------------------------------------------------------------------------------------------------------------
+def numpy_valid_actions(arrays, cfg, rng, n_nodes):
+    """Uniform valid attacker actions + uniform defender actions from the observation arrays (host side)."""
+    from marlon_b200 import _abi, config
+
+    sc = arrays["scalars"]
+    n = sc.shape[0]
+    nd, nc = sc[:, 6], sc[:, 5]
+    owned = arrays["owned_bits"][:, 0]
+    N, L = arrays["local_vulnerability"].shape[1:]
+    R, P = arrays["remote_vulnerability"].shape[3], arrays["connect"].shape[3]
+    lay = config.attacker_action_layout(cfg)
+    idx_of_kind = {cfg.kind_of_index[i]: i for i in range(3)}
+    att = np.zeros((n, 10), dtype=np.int32)
+    kind = (rng.random(n) * np.where(nc > 0, 3, 2)).astype(np.int64)
+    bits = ((owned[:, None] >> np.arange(N)[None, :]) & 1).astype(bool)
+    pick = rng.random((n, N)) * bits
+    src = pick.argmax(1)
+    loc = arrays["local_vulnerability"][np.arange(n), src]  # [n, L]
+    lv = (rng.random((n, L)) * (loc > 0)).argmax(1)
+    kind = np.where((kind == 0) & (loc.sum(1) == 0), 1, kind)
+    tgt = (rng.random(n) * np.maximum(nd, 1)).astype(np.int64)
+    for k in (0, 1, 2):
+        m = kind == k
+        a0 = lay[k][0]
+        att[m, 0] = idx_of_kind[k]
+        att[m, a0] = src[m]
+        if k == _abi.KIND_LOCAL:
+            att[m, a0 + 1] = lv[m]
+        elif k == _abi.KIND_REMOTE:
+            att[m, a0 + 1] = tgt[m]
+            att[m, a0 + 2] = (rng.random(m.sum()) * R).astype(np.int64)
+        else:
+            att[m, a0 + 1] = tgt[m]
+            att[m, a0 + 2] = (rng.random(m.sum()) * P).astype(np.int64)
+            att[m, a0 + 3] = (rng.random(m.sum()) * np.maximum(nc[m], 1)).astype(np.int64)
+    nvec = np.array([5, n_nodes, n_nodes, 6, 2, n_nodes, 6, 2, n_nodes, 3, n_nodes, 3])
+    dfn = (rng.random((n, 12)) * nvec).astype(np.int32)
+    return att, dfn
+
+
+def _cpu_worker(args):
+    seed, n_envs, seconds = args
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from oracle import OracleBatch
+
+    comp, cfg = workload_config()
+    o = OracleBatch(comp, cfg, n_envs)
+    o.reset()
+    rng = np.random.default_rng(seed)
+    steps, spent = 0, 0.0
+    t_end = time.perf_counter() + seconds
+    while time.perf_counter() < t_end:
+        att, dfn = numpy_valid_actions(o.arrays, cfg, rng, comp.n_nodes)
+        t0 = time.perf_counter()
+        o.step(att, dfn)
+        spent += time.perf_counter() - t0
+        steps += 1
+    return steps * n_envs, spent
+
+
+def cpu_baseline(seconds=12.0, n_envs=256, cores=None):
+    """Oracle (C port of the reference step) on every host core at once; only the step call is timed."""
+    import multiprocessing as mp
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle
+
+    oracle.build()
+    cores = cores or len(os.sched_getaffinity(0))
+    with mp.get_context("fork").Pool(cores) as pool:
+        res = pool.map(_cpu_worker, [(1000 + i, n_envs, seconds) for i in range(cores)])
+    value = sum(s / t for s, t in res if t > 0)
+    return {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
+            "sample": f"{cores} processes x {n_envs} envs, ToyCtf(12,10) MARLon attacker+defender pair step, random valid actions, "
+                      f"{seconds:.0f} s wall each, only oracle step() timed ({sum(s for s, _ in res)} env-steps)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t0 = time.time()
+    per = max(2.0, min(20.0, 1.5 * (args.steps + args.warmup) / 10.0))
+    cb = cpu_baseline(seconds=per)
+    comp, cfg = workload_config()
+    line = {
+        "impl": "reference", "metric": "attacker+defender env-steps/sec", "value": cb["value"], "unit": "env-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "CyberBattleToyCtf-v0 (N=12,C=10) MARLon attacker+defender pair step, dense masks, random valid actions",
+                   "note": "reference arm = CPU oracle port of the reference step (the reference is pure Python and does not travel); "
+                           "one process per host core, bounded sample"},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.time() - t0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from marlon_b200 import _abi
+    from marlon_b200.batch import Batch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    comp, cfg = workload_config(mask_mode=1 if args.factored else 0)
+    n = args.envs_per_gpu
+    K, W = args.steps, args.warmup
+
+    # ---- record the synthetic action tape (valid attacker actions for the evolving state), untimed ----
+    rec = Batch(comp, cfg, n, device=local)
+    rec.reset()
+    tape_a = torch.empty((W + K, n, 10), dtype=torch.int32, device=dev)
+    tape_d = torch.empty((W + K, n, 12), dtype=torch.int32, device=dev)
+    for s in range(W + K):
+        rec.sample_actions(seed=args.seed + rank, attacker_out=tape_a[s], defender_out=tape_d[s])
+        rec.step(tape_a[s], tape_d[s])
+    torch.cuda.synchronize()
+    S_words = None
+    rec.close()
+    del rec
+
+    b = Batch(comp, cfg, n, device=local)
+    b.reset()
+    S_words = b.export_state(0, 1).shape[1]  # canonical words (not the packed layout); packed size comes from the library
+    packed_state_words = int(os.environ.get("CBX_STATE_WORDS", "0")) or None
+    for s in range(W):
+        b.step(tape_a[s], tape_d[s])
+    b.stats_reset()
+    b.enable_timing(True)
+    launches0 = b.launch_count
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for s in range(W, W + K):
+        b.step(tape_a[s], tape_d[s])
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    stats = b.stats_tensor.clone()
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)  # the only collective of the path: per-rollout episode statistics
+    clk = clocks.stop() if rank == 0 else None
+    total_ms = float(ms.item())
+    launches = b.launch_count - launches0
+    kernel_ms, kernel_n = b.step_kernel_ms()
+    b.enable_timing(False)
+
+    # ---- e2e: the same step through the public API with HOST action buffers and host-side results ----
+    h_a = tape_a[W:W + K].cpu().numpy()
+    h_d = tape_d[W:W + K].cpu().numpy()
+    b2 = Batch(comp, cfg, n, device=local)
+    b2.reset()
+    for s in range(W):
+        b2.step(tape_a[s], tape_d[s])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for s in range(K):
+        out = b2.step_host(h_a[s], h_d[s])
+    e2e_s = time.perf_counter() - t0
+    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_s = float(e2e_t.item())
+    assert out["att_reward"].shape[0] == n
+
+    if rank == 0:
+        from marlon_b200 import _lib  # noqa: F401
+
+        peak, peak_kind = measured_peak_gbs()
+        # packed per-env state words: ask the library through the export of the layout (S) -- state array bytes / n_pad
+        S_packed = packed_state_words or _packed_state_words(comp, cfg)
+        ab = algorithmic_bytes_per_env_step(comp, cfg, S_packed)
+        achieved = ab["total"] * n / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else None
+        total_envs = n * world
+        line = {
+            "metric": "attacker+defender env-steps/sec", "value": total_envs * K / (total_ms * 1e-3), "unit": "env-steps/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "CyberBattleToyCtf-v0 (N=12,C=10) MARLon attacker+defender pair step (AttackerEnvWrapper + "
+                                   "DefenderEnvWrapper, reference_stale defender, SB3 auto-reset), "
+                                   + ("factored" if args.factored else "dense int8") + " action masks, random valid actions",
+                       "envs_per_gpu": n, "total_envs": total_envs, "parallelism": f"env-sharded x{world}, no data-path collective",
+                       "l2": "per-step output (%.0f MB/GPU) larger than the 126 MB L2; no flush needed" % (ab["total"] * n / 1e6),
+                       "algorithmic_bytes_per_env_step": ab},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                         "traffic": None, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
+                         "kernel": "cbx_step_kernel", "kernel_ms": kernel_ms, "kernel_launches_timed": kernel_n},
+            "e2e": {"value": total_envs * K / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": n * (10 + 12) * 4,
+                    "d2h_bytes_per_step": n * 12,
+                    "note": "cbx_batch_step_host: pinned H2D of actions, step, D2H of rewards + done flags; observations stay in HBM as torch tensors"},
+            "gpu_launches": launches,
+            "clocks": clk,
+            "episode_stats": {k: float(v) for k, v in zip(_abi.STAT_NAMES, stats.cpu().numpy())},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(seconds=args.cpu_seconds)
+        print(json.dumps(line))
+    b.close()
+    b2.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _packed_state_words(comp, cfg):
+    """Words of the packed per-env state (mirrors compute_layout in csrc/cbx_api.cu)."""
+    n = comp.n_nodes
+    ident = comp.identifiers
+    L, R, props = len(ident.local_vulnerabilities), len(ident.remote_vulnerabilities), len(ident.properties)
+    Wn, PW, AW = (n + 31) // 32, (props + 31) // 32, (2 * (L + R) + 31) // 32
+    nsec, ntr = max(1, len(comp.secrets)), len(comp.triples)
+    has_tags = int(comp.blob[12]) & 1
+    return (13 + (n + 3) // 4 + 2 + 3 * Wn + (n + 15) // 16 + (((n + 7) // 8) if has_tags else 0) + 3 * ((n + 3) // 4)
+            + n * PW + n * AW + (nsec + 31) // 32 + max(1, (ntr + 31) // 32) + (ntr + 2) // 2)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=65536)
+    ap.add_argument("--seed", type=int, default=2026)
+    ap.add_argument("--factored", action="store_true", help="factored masks instead of dense int8 masks")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -347,6 +347,9 @@ int64_t cbx_batch_launch_count(const cbx_batch* b);
 int cbx_batch_enable_timing(cbx_batch* b, int enabled);
 int cbx_batch_step_kernel_ms(cbx_batch* b, double* mean_ms, int64_t* launches);
 
+/* sizeof(cbx_config) (0), sizeof(cbx_views) (1), sizeof(cbx_tape) (2): lets a binding check its struct mirrors. */
+size_t cbx_abi_sizeof(int which);
+
 #ifdef __cplusplus
 }
 #endif

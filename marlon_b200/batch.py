@@ -1,0 +1,180 @@
+"""``Batch``: n independent environments resident in HBM, stepped by one fused kernel launch.
+
+Every observation / reward / flag array is a zero-copy ``torch.Tensor`` view of library-owned device memory
+(``__cuda_array_interface__``; the tensors export DLPack like any torch tensor).  Work is enqueued on torch's
+current stream of the batch's device, so it orders with the caller's torch ops without extra synchronisation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import numpy as np
+
+from . import _abi, _lib
+from .scenario import CompiledScenario
+
+_TYPESTR = {"int32": "<i4", "int8": "|i1", "uint8": "|u1", "uint32": "<u4", "float32": "<f4", "float64": "<f8"}
+
+
+class _DevArray:
+    def __init__(self, ptr, shape, dtype):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": _TYPESTR[dtype], "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+class Batch:
+    def __init__(self, compiled: CompiledScenario, cfg: _abi.Config, n_envs: int, device: int = 0):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("marlon_b200.Batch needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self._torch = torch
+        self._L = _lib.load()
+        self.compiled, self.cfg, self.n_envs, self.device = compiled, cfg, int(n_envs), int(device)
+        self.torch_device = torch.device("cuda", self.device)
+        blob = compiled.tobytes()
+        self._scn = C.c_void_p()
+        _lib.check(self._L.cbx_scenario_create(blob, len(blob), C.byref(self._scn)))
+        self._h = C.c_void_p()
+        try:
+            with torch.cuda.device(self.device):
+                torch.cuda.init()
+                _lib.check(self._L.cbx_batch_create(self._scn, self.n_envs, C.byref(cfg), self.device, C.byref(self._h)))
+        except Exception:
+            self._L.cbx_scenario_destroy(self._scn)
+            self._scn = None
+            raise
+        v = _abi.Views()
+        _lib.check(self._L.cbx_batch_views(self._h, C.byref(v)))
+        self.views = v
+        self.tensors: Dict[str, "torch.Tensor"] = {}
+        for name, (shape, dt) in _abi.view_specs(v, cfg).items():
+            ptr = C.cast(getattr(v, name), C.c_void_p).value
+            if not ptr:
+                continue
+            full = (self.n_envs,) + tuple(shape)
+            if int(np.prod(full)) == 0:
+                self.tensors[name] = torch.zeros(full, dtype=getattr(torch, dt), device=self.torch_device)
+            else:
+                self.tensors[name] = torch.as_tensor(_DevArray(ptr, full, dt), device=self.torch_device)
+        self.stats_tensor = torch.as_tensor(
+            _DevArray(C.cast(v.episode_stats, C.c_void_p).value, (_abi.STAT_COUNT,), "float64"), device=self.torch_device)
+        self.att_width = 10 if cfg.mode == _abi.MODE_MARLON else 5
+        self._keep = []
+
+    # ------------------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._torch.cuda.synchronize(self.device)
+            self.tensors.clear()
+            self._L.cbx_batch_destroy(self._h)
+            self._h = None
+        if getattr(self, "_scn", None):
+            self._L.cbx_scenario_destroy(self._scn)
+            self._scn = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(self._torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _dev(self, a, dtype, width=None):
+        """-> contiguous device tensor of `dtype` (accepts numpy / lists / torch tensors)."""
+        torch = self._torch
+        if a is None:
+            return None
+        if not isinstance(a, torch.Tensor):
+            a = torch.as_tensor(np.ascontiguousarray(a))
+        a = a.to(device=self.torch_device, dtype=dtype, non_blocking=True).contiguous()
+        if width is not None and tuple(a.shape) != (self.n_envs, width):
+            raise ValueError(f"expected shape {(self.n_envs, width)}, got {tuple(a.shape)}")
+        return a
+
+    # ------------------------------------------------------------------------------------------------
+    def reset(self, mask=None):
+        """Reset the envs selected by `mask` (all when None) and write their reset observations."""
+        torch = self._torch
+        m = self._dev(mask, torch.uint8) if mask is not None else None
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.cbx_batch_reset(self._h, C.c_void_p(m.data_ptr()) if m is not None else None, self._stream()))
+        self._keep = [m]
+
+    def step(self, attacker_actions, defender_actions=None, scan_u=None, detect_u=None):
+        """One env-step for every env. Actions: int32 [n,10] (MARLon) or [n,5] (CyberBattleEnv), defender [n,12]."""
+        torch = self._torch
+        a = self._dev(attacker_actions, torch.int32, self.att_width)
+        d = self._dev(defender_actions, torch.int32, 12) if defender_actions is not None else None
+        tape = None
+        su = du = None
+        if scan_u is not None:
+            su, du = self._dev(scan_u, torch.float64), self._dev(detect_u, torch.float64)
+            tape = _abi.Tape(C.cast(C.c_void_p(su.data_ptr()), C.POINTER(C.c_double)),
+                             C.cast(C.c_void_p(du.data_ptr()), C.POINTER(C.c_double)))
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.cbx_batch_step(self._h, C.c_void_p(a.data_ptr()), C.c_void_p(d.data_ptr()) if d is not None else None,
+                                              C.byref(tape) if tape is not None else None, self._stream()))
+        self._keep = [a, d, su, du]  # keep inputs alive until the next call (stream-ordered use)
+
+    def step_host(self, attacker_actions: np.ndarray, defender_actions: Optional[np.ndarray] = None):
+        """The same step through HOST buffers (pinned staging + H2D of actions, D2H of rewards/flags); synchronous."""
+        a = np.ascontiguousarray(attacker_actions, dtype=np.int32)
+        d = None if defender_actions is None else np.ascontiguousarray(defender_actions, dtype=np.int32)
+        n = self.n_envs
+        out = np.empty(n * 12, dtype=np.uint8)
+        with self._torch.cuda.device(self.device):
+            _lib.check(self._L.cbx_batch_step_host(self._h, a.ctypes.data, None if d is None else d.ctypes.data,
+                                                   out.ctypes.data, out.nbytes, self._stream()))
+        return {
+            "att_reward": out[: 4 * n].view(np.float32), "def_reward": out[4 * n: 8 * n].view(np.float32),
+            "att_terminated": out[8 * n: 9 * n], "att_truncated": out[9 * n: 10 * n],
+            "def_terminated": out[10 * n: 11 * n], "def_truncated": out[11 * n: 12 * n],
+        }
+
+    def sample_actions(self, seed: int = 0, attacker_out=None, defender_out=None):
+        """Uniformly sampled VALID attacker actions (and uniform defender actions) for the current state, on device."""
+        torch = self._torch
+        if attacker_out is None:
+            attacker_out = torch.empty((self.n_envs, self.att_width), dtype=torch.int32, device=self.torch_device)
+        need_def = self.cfg.mode == _abi.MODE_MARLON and self.cfg.def_enabled
+        if need_def and defender_out is None:
+            defender_out = torch.empty((self.n_envs, 12), dtype=torch.int32, device=self.torch_device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.cbx_batch_sample_actions(self._h, C.c_void_p(attacker_out.data_ptr()),
+                                                        C.c_void_p(defender_out.data_ptr()) if need_def else None,
+                                                        int(seed) & 0xFFFFFFFFFFFFFFFF, self._stream()))
+        return attacker_out, (defender_out if need_def else None)
+
+    def export_state(self, begin: int = 0, end: Optional[int] = None) -> np.ndarray:
+        end = self.n_envs if end is None else end
+        w = self._L.cbx_export_words(self._scn, C.byref(self.cfg))
+        out = np.zeros((end - begin, w), dtype=np.int32)
+        with self._torch.cuda.device(self.device):
+            _lib.check(self._L.cbx_batch_export_state(self._h, begin, end, out.ctypes.data, self._stream()))
+        return out
+
+    def stats(self) -> np.ndarray:
+        return self.stats_tensor.cpu().numpy().copy()
+
+    def stats_reset(self):
+        with self._torch.cuda.device(self.device):
+            _lib.check(self._L.cbx_batch_stats_reset(self._h, self._stream()))
+
+    def enable_timing(self, on: bool = True):
+        _lib.check(self._L.cbx_batch_enable_timing(self._h, int(on)))
+
+    def step_kernel_ms(self):
+        ms, n = C.c_double(0), C.c_int64(0)
+        _lib.check(self._L.cbx_batch_step_kernel_ms(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.cbx_batch_launch_count(self._h))
+
+    def numpy(self, name: str) -> np.ndarray:
+        return self.tensors[name].cpu().numpy()

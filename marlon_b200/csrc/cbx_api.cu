@@ -1,0 +1,589 @@
+// cbx_api.cu -- host side of the C ABI declared in include/cbx.h: scenario upload, HBM layout, launches.
+// No simulation logic lives here and there is no CPU path: every entry point that computes launches a kernel.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "cbx_layout.h"
+
+extern "C" {
+cudaError_t cbx_launch_step(const cbx_params* p, int reset_only, int grid, int smem_bytes, int use_tma, cudaStream_t stream);
+cudaError_t cbx_launch_sample(const cbx_params* p, int32_t* att, int32_t* def, uint64_t seed, uint32_t step, cudaStream_t stream);
+cudaError_t cbx_kernel_attrs(int smem_bytes, int use_tma, int* blocks_per_sm);
+}
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                                        \
+  do {                                                                                                        \
+    cudaError_t _e = (expr);                                                                                  \
+    if (_e != cudaSuccess) return fail(CBX_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                                       __FILE__, __LINE__);                                                   \
+  } while (0)
+
+cbx_fastdiv make_fastdiv(uint32_t d) {
+  cbx_fastdiv f = {0, 0};
+  if (d == 0) d = 1;
+  uint32_t s = 0;
+  while ((1u << (s + 1)) <= d && s < 31) ++s;  // s = floor(log2 d)
+  if ((d & (d - 1)) == 0) { f.m = 0; f.s = s; return f; }
+  unsigned __int128 num = ((unsigned __int128)1) << (32 + s);
+  f.m = (uint32_t)((num + d - 1) / d);
+  f.s = s;
+  return f;
+}
+
+int align_up(int x, int a) { return (x + a - 1) / a * a; }
+
+}  // namespace
+
+struct cbx_scenario {
+  std::vector<uint32_t> blob;
+  int n, P, nprops, L, R, nsecrets, ntriples, nservices, max_leak, flags;
+};
+
+struct cbx_batch {
+  cbx_params p;
+  int device, grid, smem_bytes, use_tma;
+  std::vector<void*> allocs;
+  uint32_t* d_tables;
+  int64_t launches;
+  uint32_t sample_step;
+  // pinned staging for the host-buffer entry point
+  int32_t *h_att, *h_def, *d_att, *d_def;
+  uint8_t *h_out, *d_out_unused;
+  // kernel timing
+  int timing;
+  std::vector<cudaEvent_t> ev;
+  size_t ev_used;
+  double ms_sum;
+  int64_t ms_count;
+  const cbx_scenario* scn;
+  std::vector<uint32_t> init_state;
+};
+
+extern "C" {
+
+const char* cbx_last_error(void) { return g_err.c_str(); }
+int cbx_abi_version(void) { return CBX_ABI_VERSION; }
+
+int cbx_scenario_create(const void* tables, size_t nbytes, cbx_scenario** out) {
+  if (!tables || !out || nbytes < CBX_H_WORDS * 4 || nbytes % 4) return fail(CBX_ERR_INVALID, "scenario blob too small or misaligned");
+  const uint32_t* w = (const uint32_t*)tables;
+  if (w[CBX_H_MAGIC] != CBX_SCN_MAGIC) return fail(CBX_ERR_INVALID, "bad scenario magic");
+  if (w[CBX_H_VERSION] != CBX_SCN_VERSION) return fail(CBX_ERR_INVALID, "scenario version %u, library expects %u", w[CBX_H_VERSION], CBX_SCN_VERSION);
+  if ((size_t)w[CBX_H_TOTAL_WORDS] * 4 != nbytes || w[CBX_H_TOTAL_WORDS] % 4) return fail(CBX_ERR_INVALID, "scenario blob size mismatch");
+  cbx_scenario* s = new cbx_scenario();
+  s->blob.assign(w, w + nbytes / 4);
+  s->n = (int)w[CBX_H_N_NODES]; s->P = (int)w[CBX_H_N_PORTS]; s->nprops = (int)w[CBX_H_N_PROPS];
+  s->L = (int)w[CBX_H_N_LOCAL]; s->R = (int)w[CBX_H_N_REMOTE]; s->nsecrets = (int)w[CBX_H_N_SECRETS];
+  s->ntriples = (int)w[CBX_H_N_TRIPLES]; s->nservices = (int)w[CBX_H_N_SERVICES]; s->max_leak = (int)w[CBX_H_MAX_LEAK];
+  s->flags = (int)w[CBX_H_FLAGS];
+  const size_t tot = w[CBX_H_TOTAL_WORDS];
+  const int V = s->L + s->R, Ws = (s->nsecrets + 31) / 32;
+  bool ok = s->n >= 1 && s->n <= 255 && s->P >= 1 && s->P <= 32 && s->nprops >= 1 && s->nprops <= 64 && s->L >= 1 && s->R >= 1 &&
+            s->ntriples <= 65535 && (size_t)w[CBX_H_OFF_NODE] + (size_t)s->n * CBX_NODE_WORDS <= tot &&
+            (size_t)w[CBX_H_OFF_AUTH] + (size_t)s->n * s->P * Ws <= tot &&
+            (size_t)w[CBX_H_OFF_VULN] + (size_t)s->n * V * CBX_VULN_WORDS <= tot &&
+            (size_t)w[CBX_H_OFF_PAYLOAD] + w[CBX_H_N_PAYLOAD] <= tot && (size_t)w[CBX_H_OFF_TRIPLE] + 3 * (size_t)s->ntriples <= tot;
+  if (!ok) { delete s; return fail(CBX_ERR_INVALID, "scenario header out of range"); }
+  *out = s;
+  return CBX_OK;
+}
+
+int cbx_scenario_destroy(cbx_scenario* s) {
+  delete s;
+  return CBX_OK;
+}
+
+int cbx_config_default(cbx_config* c) {
+  if (!c) return fail(CBX_ERR_INVALID, "null config");
+  memset(c, 0, sizeof(*c));
+  c->abi_version = CBX_ABI_VERSION;
+  c->mode = CBX_MODE_CYBERBATTLE;
+  c->maximum_node_count = 100;
+  c->maximum_total_credentials = 1000;
+  c->maximum_discoverable_credentials_per_action = 5;
+  c->throws_on_invalid_actions = 1;
+  c->has_attacker_goal = 1;
+  c->goal_low_availability = 1.0;
+  c->goal_own_atleast_percent = 1.0;
+  c->defender_goal_eviction = 1;
+  c->winning_reward = 5000.0;
+  c->scan_frequency = 1;
+  c->kind_of_index[0] = CBX_KIND_CONNECT; c->kind_of_index[1] = CBX_KIND_LOCAL; c->kind_of_index[2] = CBX_KIND_REMOTE;
+  c->att_max_timesteps = 2000;
+  c->att_invalid_action_reward_modifier = -1.0;
+  c->def_max_timesteps = 100;
+  c->def_reset_on_constraint_broken = 1;
+  c->auto_reset = 1;
+  c->def_loss_reward = -5000.0;
+  c->def_sla_worsening_penalty_scale = 200.0;
+  return CBX_OK;
+}
+
+static int compute_layout(const cbx_scenario* s, const cbx_config* cfg, int64_t n_envs, cbx_layout* L) {
+  memset(L, 0, sizeof(*L));
+  L->n = s->n; L->N = cfg->maximum_node_count; L->C = cfg->maximum_total_credentials;
+  L->LEAK = cfg->maximum_discoverable_credentials_per_action;
+  L->P = s->P; L->L = s->L; L->R = s->R; L->nprops = s->nprops; L->nsecrets = s->nsecrets; L->ntriples = s->ntriples;
+  L->nservices = s->nservices;
+  if (L->n > L->N) return fail(CBX_ERR_INVALID, "Network node count (%d) exceeds the specified limit of %d.", L->n, L->N);  // ENV:416-418
+  if (s->max_leak > L->LEAK)
+    return fail(CBX_ERR_INVALID, "Some action in the environment returns %d credentials which exceeds the maximum number of discoverable credentials of %d",
+                s->max_leak, L->LEAK);  // ENV:430-435
+  if (L->N > 255) return fail(CBX_ERR_UNSUPPORTED, "maximum_node_count %d > 255", L->N);
+  if (L->C > 65535) return fail(CBX_ERR_UNSUPPORTED, "maximum_total_credentials %d > 65535", L->C);
+  if (L->LEAK > CBX_MAX_LEAK) L->LEAK = L->LEAK;  // staging grows with LEAK; checked against shared memory below
+  if (s->ntriples > L->C)
+    return fail(CBX_ERR_UNSUPPORTED, "scenario has %d distinct credentials but maximum_total_credentials is %d (the reference would emit out-of-space observations)",
+                s->ntriples, L->C);
+  L->Wn = (L->n + 31) / 32;
+  L->PW = (L->nprops + 31) / 32;
+  L->AW = (2 * (L->L + L->R) + 31) / 32;
+  L->OW = (L->N + 31) / 32;
+  int o = 0;
+  L->o_hdr = o++;
+  L->o_att_ts = o++; L->o_def_ts = o++;
+  L->o_att_valid = o++; L->o_att_invalid = o++; L->o_def_valid = o++; L->o_def_invalid = o++;
+  L->o_last_cyber = o++; L->o_last_reward = o++; L->o_last_att = o++; L->o_att_return = o++; L->o_def_return = o++;
+  L->o_avail = o++;
+  L->o_cd_shadow = o; o += (L->n + 3) / 4;
+  L->o_cyber_begin = o;
+  L->o_stepcount = o++;
+  L->o_ep_sum = o++;
+  L->o_installed = o; o += L->Wn;
+  L->o_everowned = o; o += L->Wn;
+  L->o_notrunning = o; o += L->Wn;
+  L->o_priv = o; o += (L->n + 15) / 16;
+  if (s->flags & 1) { L->o_tags = o; o += (L->n + 7) / 8; } else L->o_tags = -1;
+  L->o_cd_live = o; o += (L->n + 3) / 4;
+  L->o_disc_order = o; o += (L->n + 3) / 4;
+  L->o_disc_idx = o; o += (L->n + 3) / 4;
+  L->o_props = o; o += L->n * L->PW;
+  L->o_attacked = o; o += L->n * L->AW;
+  L->o_gathered = o; o += (L->nsecrets + 31) / 32;
+  L->o_cached = o; o += (L->ntriples + 31) / 32 > 0 ? (L->ntriples + 31) / 32 : 1;
+  L->o_cache = o; o += (L->ntriples + 1 + 1) / 2;
+  L->S = o;
+  int g = 11 + L->Wn;
+  L->g_leaked = g; g += 4 * L->LEAK;
+  L->g_inst = g; g += L->Wn;
+  L->g_priv = g; g += (L->n + 15) / 16;
+  L->G = g;
+  const int dense = cfg->mask_mode == CBX_MASK_DENSE;
+  int64_t szc = (int64_t)L->N * L->N * L->P * L->C;
+  if (dense && szc * (n_envs < CBX_TILE ? n_envs : CBX_TILE) >= (1ll << 31)) return fail(CBX_ERR_UNSUPPORTED, "dense connect mask of %lld bytes per env is too large; use factored masks", (long long)szc);
+  L->sz_local = dense ? L->N * L->L : 0;
+  L->sz_remote = dense ? L->N * L->N * L->R : 0;
+  L->sz_connect = dense ? (int)szc : 0;
+  return CBX_OK;
+}
+
+static void build_init_state(const cbx_scenario* s, const cbx_layout& L, std::vector<uint32_t>& st) {
+  st.assign((size_t)((L.S + 3) & ~3), 0u);
+  const uint32_t* w = s->blob.data();
+  const uint32_t* node = w + w[CBX_H_OFF_NODE];
+  auto setbyte = [&](int off, int i, uint32_t v) { st[off + i / 4] = (st[off + i / 4] & ~(0xFFu << ((i & 3) * 8))) | (v << ((i & 3) * 8)); };
+  for (int i = 0; i < ((L.n + 3) / 4) * 4; ++i) setbyte(L.o_disc_idx, i, 0xFFu);
+  int nd = 0;
+  for (int i = 0; i < L.n; ++i) {
+    const uint32_t* r = node + (size_t)i * CBX_NODE_WORDS;
+    uint32_t f = r[CBX_N_FLAGS];
+    int priv = (f >> 2) & 3;
+    if (f & 2u) {  // agent_installed: AgentActions.__init__ marks it owned at LocalUser and discovers its properties (ACT:149-152)
+      st[L.o_installed + i / 32] |= 1u << (i % 32);
+      st[L.o_everowned + i / 32] |= 1u << (i % 32);
+      if (priv < 1) priv = 1;
+      st[L.o_props + i * L.PW] = r[CBX_N_PROPS_LO];
+      if (L.PW > 1) st[L.o_props + i * L.PW + 1] = r[CBX_N_PROPS_HI];
+      setbyte(L.o_disc_order, nd, (uint32_t)i);  // ENV:392-394
+      setbyte(L.o_disc_idx, i, (uint32_t)nd);
+      nd++;
+    }
+    st[L.o_priv + i / 16] |= (uint32_t)priv << ((i % 16) * 2);
+  }
+  st[L.o_hdr] = (uint32_t)nd;
+}
+
+int cbx_batch_create(const cbx_scenario* s, int64_t n_envs, const cbx_config* cfg, int device, cbx_batch** out) {
+  if (!s || !cfg || !out) return fail(CBX_ERR_INVALID, "null argument");
+  if (cfg->abi_version != CBX_ABI_VERSION) return fail(CBX_ERR_INVALID, "config abi_version %d, library %d", cfg->abi_version, CBX_ABI_VERSION);
+  if (n_envs <= 0) return fail(CBX_ERR_INVALID, "n_envs must be positive");
+  if (device < 0) return fail(CBX_ERR_NODEVICE, "device %d: this library has no CPU path", device);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(CBX_ERR_NODEVICE, "no CUDA device available (there is no CPU fallback)");
+  if (device >= ndev) return fail(CBX_ERR_NODEVICE, "device %d out of range (%d devices)", device, ndev);
+  if (cfg->mode != CBX_MODE_CYBERBATTLE && cfg->mode != CBX_MODE_MARLON) return fail(CBX_ERR_INVALID, "bad mode");
+  if (cfg->builtin_defender == CBX_BUILTIN_SCAN_AND_REIMAGE && (cfg->scan_frequency <= 0 || cfg->scan_capacity < 0))
+    return fail(CBX_ERR_INVALID, "scan_frequency must be positive");
+  { int seen = 0; for (int k = 0; k < 3; ++k) { if (cfg->kind_of_index[k] < 0 || cfg->kind_of_index[k] > 2) return fail(CBX_ERR_INVALID, "kind_of_index"); seen |= 1 << cfg->kind_of_index[k]; }
+    if (seen != 7) return fail(CBX_ERR_INVALID, "kind_of_index must be a permutation"); }
+  CUDA_TRY(cudaSetDevice(device));
+  cbx_batch* b = new cbx_batch();
+  memset(&b->p, 0, sizeof(b->p));
+  b->device = device; b->launches = 0; b->sample_step = 0; b->timing = 0; b->ev_used = 0; b->ms_sum = 0; b->ms_count = 0;
+  b->h_att = b->h_def = b->d_att = b->d_def = nullptr; b->h_out = nullptr; b->scn = s;
+  int rc = compute_layout(s, cfg, n_envs, &b->p.lay);
+  if (rc) { delete b; return rc; }
+  cbx_layout& L = b->p.lay;
+  b->p.cfg = *cfg;
+  b->p.n_envs = n_envs;
+  b->p.n_pad = (n_envs + CBX_TILE - 1) / CBX_TILE * CBX_TILE;
+  b->p.n_tiles = (int)(b->p.n_pad / CBX_TILE);
+  b->p.table_words = (int)s->blob.size();
+  int col = 1;
+  for (int k = 0; k < 3; ++k) {
+    int kind = cfg->kind_of_index[k];
+    b->p.slice_of_kind[kind] = col;
+    col += kind == CBX_KIND_LOCAL ? 2 : kind == CBX_KIND_REMOTE ? 3 : 4;
+  }
+  // encoder constants
+  cbx_enc_consts& K = b->p.enc;
+  K.d_leaked = make_fastdiv(4 * L.LEAK); K.d_cachem = make_fastdiv(2 * L.C); K.d_props = make_fastdiv(L.N * L.nprops);
+  K.d_priv = make_fastdiv(L.N); K.d_nprops = make_fastdiv(L.nprops); K.d_L = make_fastdiv(L.L);
+  K.d_local = make_fastdiv(L.N * L.L); K.d_remote = make_fastdiv(L.N * L.N * L.R);
+  K.d_connect = make_fastdiv((uint32_t)((int64_t)L.N * L.N * L.P * L.C)); K.d_rowr = make_fastdiv(L.N * L.R);
+  K.d_rowc = make_fastdiv(L.N * L.P * L.C); K.d_C = make_fastdiv(L.C); K.d_n = make_fastdiv(L.n);
+  K.d_6n = make_fastdiv(6 * L.n); K.d_svc = make_fastdiv(L.nservices > 0 ? L.nservices : 1);
+  K.desc_words = 8 + L.OW + L.Wn;
+  // shared-memory plan
+  cbx_smem_plan& pl = b->p.plan;
+  int o = 0;
+  pl.tables = o; o = align_up(o + b->p.table_words + ((L.S + 3) & ~3), 32);
+  pl.state = o; o = align_up(o + L.S * CBX_TILE, 32);
+  pl.stage = o; o = align_up(o + L.G * CBX_TILE, 32);
+  pl.desc = o; o = align_up(o + K.desc_words * CBX_TILE, 32);
+  pl.lut = o; o = align_up(o + 512, 32);
+  pl.bars = o; o += 8;
+  pl.total_bytes = o * 4;
+  b->smem_bytes = pl.total_bytes;
+  if (b->smem_bytes > 227 * 1024) {
+    delete b;
+    return fail(CBX_ERR_UNSUPPORTED, "scenario needs %d bytes of shared memory per CTA (> 227 KiB)", pl.total_bytes);
+  }
+  const char* no_tma = getenv("CBX_NO_TMA");
+  b->use_tma = !(no_tma && no_tma[0] == '1');
+  int bps = 0;
+  { cudaError_t e = cbx_kernel_attrs(b->smem_bytes, b->use_tma, &bps);
+    if (e != cudaSuccess) { delete b; return fail(CBX_ERR_CUDA, "kernel attributes: %s", cudaGetErrorString(e)); } }
+  if (bps < 1) { delete b; return fail(CBX_ERR_CUDA, "step kernel does not fit on an SM"); }
+  int sms = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  b->grid = sms * bps;
+  if (b->grid > b->p.n_tiles) b->grid = b->p.n_tiles;
+  const char* gridenv = getenv("CBX_GRID");
+  if (gridenv && atoi(gridenv) > 0) b->grid = atoi(gridenv) < b->p.n_tiles ? atoi(gridenv) : b->p.n_tiles;
+
+  auto dalloc = [&](void** ptr, size_t bytes) -> cudaError_t {
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMalloc(ptr, bytes);
+    if (e == cudaSuccess) { b->allocs.push_back(*ptr); e = cudaMemset(*ptr, 0, bytes); }
+    return e;
+  };
+#define ALLOC(field, type, per_env)                                                                                \
+  do {                                                                                                             \
+    void* _p = nullptr;                                                                                            \
+    cudaError_t _e = dalloc(&_p, (size_t)b->p.n_pad * (size_t)(per_env) * sizeof(type));                          \
+    if (_e != cudaSuccess) { int _rc = fail(CBX_ERR_CUDA, "cudaMalloc(%s): %s", #field, cudaGetErrorString(_e)); \
+      cbx_batch_destroy(b); return _rc; }                                                                          \
+    field = (type*)_p;                                                                                             \
+  } while (0)
+  build_init_state(s, L, b->init_state);
+  {
+    std::vector<uint32_t> tab(s->blob);
+    tab.insert(tab.end(), b->init_state.begin(), b->init_state.end());
+    void* pt = nullptr;
+    cudaError_t e = dalloc(&pt, tab.size() * 4);
+    if (e != cudaSuccess) { int rc2 = fail(CBX_ERR_CUDA, "cudaMalloc(tables): %s", cudaGetErrorString(e)); cbx_batch_destroy(b); return rc2; }
+    b->d_tables = (uint32_t*)pt;
+    e = cudaMemcpy(pt, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { int rc2 = fail(CBX_ERR_CUDA, "upload tables: %s", cudaGetErrorString(e)); cbx_batch_destroy(b); return rc2; }
+    b->p.tables = b->d_tables;
+  }
+  cbx_views& v = b->p.v;
+  v.n_envs = n_envs; v.N = L.N; v.L = L.L; v.R = L.R; v.P = L.P; v.C = L.C; v.LEAK = L.LEAK; v.n_props = L.nprops;
+  v.n_nodes = L.n; v.n_services = L.nservices; v.owned_words = L.OW;
+  ALLOC(b->p.state, uint32_t, L.S);
+  ALLOC(v.scalars, int32_t, 8);
+  ALLOC(v.leaked_credentials, int32_t, 4 * L.LEAK);
+  ALLOC(v.credential_cache_matrix, int32_t, 2 * L.C);
+  ALLOC(v.discovered_nodes_properties, int32_t, L.N * L.nprops);
+  ALLOC(v.nodes_privilegelevel, int32_t, L.N);
+  const bool dense = cfg->mask_mode == CBX_MASK_DENSE;
+  if (dense) {
+    ALLOC(v.local_vulnerability, int8_t, L.sz_local);
+    ALLOC(v.remote_vulnerability, int8_t, L.sz_remote);
+    ALLOC(v.connect, int8_t, L.sz_connect);
+  }
+  ALLOC(v.owned_bits, uint32_t, L.OW);
+  const bool defobs = cfg->mode == CBX_MODE_MARLON && cfg->def_enabled;
+  if (defobs) {
+    ALLOC(v.def_infected_nodes, int8_t, L.n);
+    ALLOC(v.def_incoming_firewall, int8_t, 6 * L.n);
+    ALLOC(v.def_outgoing_firewall, int8_t, 6 * L.n);
+    ALLOC(v.def_services_status, int8_t, L.nservices);
+  }
+  ALLOC(v.att_reward, float, 1); ALLOC(v.def_reward, float, 1);
+  ALLOC(v.att_terminated, uint8_t, 1); ALLOC(v.att_truncated, uint8_t, 1);
+  ALLOC(v.def_terminated, uint8_t, 1); ALLOC(v.def_truncated, uint8_t, 1);
+  ALLOC(v.att_info, int32_t, 8);
+  ALLOC(v.network_availability, double, 1);
+  { void* ps = nullptr; cudaError_t e = dalloc(&ps, CBX_STAT_COUNT * sizeof(double));
+    if (e != cudaSuccess) { int rc2 = fail(CBX_ERR_CUDA, "cudaMalloc(stats): %s", cudaGetErrorString(e)); cbx_batch_destroy(b); return rc2; }
+    v.episode_stats = (double*)ps; }
+  if (cfg->emit_terminal_obs) {
+    ALLOC(v.term_scalars, int32_t, 8);
+    ALLOC(v.term_leaked_credentials, int32_t, 4 * L.LEAK);
+    ALLOC(v.term_credential_cache_matrix, int32_t, 2 * L.C);
+    ALLOC(v.term_discovered_nodes_properties, int32_t, L.N * L.nprops);
+    ALLOC(v.term_nodes_privilegelevel, int32_t, L.N);
+    if (dense) {
+      ALLOC(v.term_local_vulnerability, int8_t, L.sz_local);
+      ALLOC(v.term_remote_vulnerability, int8_t, L.sz_remote);
+      ALLOC(v.term_connect, int8_t, L.sz_connect);
+    }
+    if (defobs) ALLOC(v.term_def_infected_nodes, int8_t, L.n);
+  }
+#undef ALLOC
+  // bring every env to its initial state (the reference resets before the first step as well)
+  {
+    b->p.reset_mask = nullptr;
+    cudaError_t e = cbx_launch_step(&b->p, 1, b->grid, b->smem_bytes, b->use_tma, 0);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { int rc2 = fail(CBX_ERR_CUDA, "initial reset: %s", cudaGetErrorString(e)); cbx_batch_destroy(b); return rc2; }
+    b->launches++;
+  }
+  *out = b;
+  return CBX_OK;
+}
+
+int cbx_batch_destroy(cbx_batch* b) {
+  if (!b) return CBX_OK;
+  cudaSetDevice(b->device);
+  for (void* p : b->allocs) cudaFree(p);
+  if (b->h_att) cudaFreeHost(b->h_att);
+  if (b->h_def) cudaFreeHost(b->h_def);
+  if (b->h_out) cudaFreeHost(b->h_out);
+  if (b->d_att) cudaFree(b->d_att);
+  if (b->d_def) cudaFree(b->d_def);
+  for (cudaEvent_t e : b->ev) cudaEventDestroy(e);
+  delete b;
+  return CBX_OK;
+}
+
+static int timed_launch(cbx_batch* b, int reset_only, cudaStream_t st) {
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  const bool t = b->timing && !reset_only;
+  if (t) {
+    if (b->ev_used + 2 > b->ev.size()) {
+      for (int k = 0; k < 2; ++k) { cudaEvent_t e; CUDA_TRY(cudaEventCreate(&e)); b->ev.push_back(e); }
+    }
+    e0 = b->ev[b->ev_used]; e1 = b->ev[b->ev_used + 1];
+    b->ev_used += 2;
+    CUDA_TRY(cudaEventRecord(e0, st));
+  }
+  CUDA_TRY(cbx_launch_step(&b->p, reset_only, b->grid, b->smem_bytes, b->use_tma, st));
+  if (t) CUDA_TRY(cudaEventRecord(e1, st));
+  b->launches++;
+  return CBX_OK;
+}
+
+int cbx_batch_reset(cbx_batch* b, const uint8_t* mask_or_null, void* cuda_stream) {
+  if (!b) return fail(CBX_ERR_INVALID, "null batch");
+  CUDA_TRY(cudaSetDevice(b->device));
+  b->p.reset_mask = mask_or_null;
+  b->p.att_actions = nullptr; b->p.def_actions = nullptr; b->p.scan_u = nullptr; b->p.detect_u = nullptr;
+  return timed_launch(b, 1, (cudaStream_t)cuda_stream);
+}
+
+int cbx_batch_step(cbx_batch* b, const int32_t* att, const int32_t* def, const cbx_tape* tape, void* cuda_stream) {
+  if (!b || !att) return fail(CBX_ERR_INVALID, "null batch or attacker actions");
+  const cbx_config& c = b->p.cfg;
+  if (c.mode == CBX_MODE_MARLON && c.def_enabled && !def) return fail(CBX_ERR_INVALID, "defender actions required (def_enabled)");
+  CUDA_TRY(cudaSetDevice(b->device));
+  b->p.reset_mask = nullptr;
+  b->p.att_actions = att; b->p.def_actions = def;
+  b->p.scan_u = tape ? tape->scan_u : nullptr;
+  b->p.detect_u = tape ? tape->detect_u : nullptr;
+  if (tape && (!tape->scan_u || !tape->detect_u)) return fail(CBX_ERR_INVALID, "tape needs both scan_u and detect_u");
+  return timed_launch(b, 0, (cudaStream_t)cuda_stream);
+}
+
+int cbx_batch_step_host(cbx_batch* b, const int32_t* h_att, const int32_t* h_def, void* host_out, size_t host_out_bytes, void* cuda_stream) {
+  if (!b || !h_att || !host_out) return fail(CBX_ERR_INVALID, "null argument");
+  const cbx_config& c = b->p.cfg;
+  const int64_t n = b->p.n_envs;
+  const int aw = c.mode == CBX_MODE_MARLON ? 10 : 5;
+  const bool need_def = c.mode == CBX_MODE_MARLON && c.def_enabled;
+  if (need_def && !h_def) return fail(CBX_ERR_INVALID, "defender actions required");
+  const size_t out_bytes = (size_t)n * (4 + 4 + 4);
+  if (host_out_bytes < out_bytes) return fail(CBX_ERR_INVALID, "host_out needs %zu bytes", out_bytes);
+  CUDA_TRY(cudaSetDevice(b->device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  if (!b->h_att) {
+    CUDA_TRY(cudaMallocHost((void**)&b->h_att, (size_t)n * 10 * 4));
+    CUDA_TRY(cudaMallocHost((void**)&b->h_def, (size_t)n * 12 * 4));
+    CUDA_TRY(cudaMallocHost((void**)&b->h_out, out_bytes));
+    CUDA_TRY(cudaMalloc((void**)&b->d_att, (size_t)n * 10 * 4));
+    CUDA_TRY(cudaMalloc((void**)&b->d_def, (size_t)n * 12 * 4));
+  }
+  memcpy(b->h_att, h_att, (size_t)n * aw * 4);
+  CUDA_TRY(cudaMemcpyAsync(b->d_att, b->h_att, (size_t)n * aw * 4, cudaMemcpyHostToDevice, st));
+  if (need_def) {
+    memcpy(b->h_def, h_def, (size_t)n * 12 * 4);
+    CUDA_TRY(cudaMemcpyAsync(b->d_def, b->h_def, (size_t)n * 12 * 4, cudaMemcpyHostToDevice, st));
+  }
+  int rc = cbx_batch_step(b, b->d_att, need_def ? b->d_def : nullptr, nullptr, cuda_stream);
+  if (rc) return rc;
+  const cbx_views& v = b->p.v;
+  uint8_t* o = b->h_out;
+  CUDA_TRY(cudaMemcpyAsync(o, v.att_reward, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(o + (size_t)n * 4, v.def_reward, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(o + (size_t)n * 8, v.att_terminated, (size_t)n, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(o + (size_t)n * 9, v.att_truncated, (size_t)n, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(o + (size_t)n * 10, v.def_terminated, (size_t)n, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(o + (size_t)n * 11, v.def_truncated, (size_t)n, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  memcpy(host_out, o, out_bytes);
+  return CBX_OK;
+}
+
+int cbx_batch_sample_actions(cbx_batch* b, int32_t* att, int32_t* def, uint64_t seed, void* cuda_stream) {
+  if (!b || !att) return fail(CBX_ERR_INVALID, "null argument");
+  CUDA_TRY(cudaSetDevice(b->device));
+  CUDA_TRY(cbx_launch_sample(&b->p, att, def, seed, b->sample_step++, (cudaStream_t)cuda_stream));
+  b->launches++;
+  return CBX_OK;
+}
+
+int cbx_batch_views(cbx_batch* b, cbx_views* out) {
+  if (!b || !out) return fail(CBX_ERR_INVALID, "null argument");
+  *out = b->p.v;
+  return CBX_OK;
+}
+
+int cbx_batch_stats_reset(cbx_batch* b, void* cuda_stream) {
+  if (!b) return fail(CBX_ERR_INVALID, "null batch");
+  CUDA_TRY(cudaSetDevice(b->device));
+  CUDA_TRY(cudaMemsetAsync(b->p.v.episode_stats, 0, CBX_STAT_COUNT * sizeof(double), (cudaStream_t)cuda_stream));
+  return CBX_OK;
+}
+
+int64_t cbx_export_words(const cbx_scenario* s, const cbx_config* cfg) {
+  if (!s || !cfg) return -1;
+  return CBX_X_HEADER_WORDS + 10 * (int64_t)s->n + cfg->maximum_total_credentials + (s->nsecrets + 31) / 32;
+}
+
+int cbx_batch_export_state(cbx_batch* b, int64_t begin, int64_t end, int32_t* out, void* cuda_stream) {
+  if (!b || !out || begin < 0 || end > b->p.n_envs || begin >= end) return fail(CBX_ERR_INVALID, "bad export range");
+  CUDA_TRY(cudaSetDevice(b->device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const cbx_layout& L = b->p.lay;
+  const int64_t m = end - begin;
+  std::vector<uint32_t> raw((size_t)L.S * m);
+  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(cudaMemcpy2D(raw.data(), (size_t)m * 4, b->p.state + begin, (size_t)b->p.n_pad * 4, (size_t)m * 4, (size_t)L.S, cudaMemcpyDeviceToHost));
+  const int n = L.n;
+  const int64_t W = cbx_export_words(b->scn, &b->p.cfg);
+  const bool def = b->p.cfg.mode == CBX_MODE_MARLON && b->p.cfg.def_enabled;
+  for (int64_t i = 0; i < m; ++i) {
+    auto w = [&](int off) { return raw[(size_t)off * m + i]; };
+    auto byte = [&](int off, int k) { return (w(off + k / 4) >> ((k & 3) * 8)) & 0xFFu; };
+    auto bit = [&](int off, int k) { return (w(off + k / 32) >> (k & 31)) & 1u; };
+    int32_t* x = out + i * W;
+    memset(x, 0, (size_t)W * 4);
+    const uint32_t hdr = w(L.o_hdr), av = w(L.o_avail);
+    x[CBX_X_STEPCOUNT] = (int32_t)w(L.o_stepcount);
+    x[CBX_X_DONE] = (hdr >> 24) & 1;
+    x[CBX_X_N_DISCOVERED] = hdr & 0xFF;
+    x[CBX_X_N_CACHED] = (hdr >> 8) & 0xFFFF;
+    x[CBX_X_ATT_TIMESTEPS] = (int32_t)w(L.o_att_ts);
+    x[CBX_X_DEF_TIMESTEPS] = (int32_t)w(L.o_def_ts);
+    x[CBX_X_ATT_RESET_REQUEST] = (hdr >> 25) & 1;
+    x[CBX_X_DEF_RESET_REQUEST] = def ? (hdr >> 26) & 1 : 0;
+    x[CBX_X_HAS_BREACHED_SLA] = (hdr >> 27) & 1;
+    x[CBX_X_ATT_VALID] = (int32_t)w(L.o_att_valid); x[CBX_X_ATT_INVALID] = (int32_t)w(L.o_att_invalid);
+    x[CBX_X_DEF_VALID] = (int32_t)w(L.o_def_valid); x[CBX_X_DEF_INVALID] = (int32_t)w(L.o_def_invalid);
+    int live = 0;
+    for (int k = 0; k < n; ++k) live += bit(L.o_notrunning, k);
+    x[CBX_X_LIVE_IMAGING_COUNT] = live;
+    x[CBX_X_SHADOW_IMAGING_COUNT] = (av >> 8) & 0xFF;
+    x[CBX_X_PREV_SHADOW_IMAGING_COUNT] = (av >> 16) & 0xFF;
+    int32_t* p = x + CBX_X_HEADER_WORDS;
+    const int nd = hdr & 0xFF, nc = (hdr >> 8) & 0xFFFF;
+    for (int k = 0; k < n; ++k) p[k] = k < nd ? (int32_t)byte(L.o_disc_order, k) : -1;
+    p += n;
+    for (int k = 0; k < n; ++k) p[k] = bit(L.o_installed, k);
+    p += n;
+    for (int k = 0; k < n; ++k) p[k] = (w(L.o_priv + k / 16) >> ((k % 16) * 2)) & 3;
+    p += n;
+    for (int k = 0; k < n; ++k) p[k] = byte(L.o_cd_live, k);
+    p += n;
+    for (int k = 0; k < n; ++k) p[k] = byte(L.o_cd_shadow, k);
+    p += n;
+    for (int k = 0; k < n; ++k) p[k] = bit(L.o_everowned, k);
+    p += n;
+    for (int k = 0; k < n; ++k) p[k] = (int32_t)w(L.o_props + k * L.PW);
+    p += n;
+    for (int k = 0; k < n; ++k) p[k] = L.PW > 1 ? (int32_t)w(L.o_props + k * L.PW + 1) : 0;
+    p += n;
+    for (int k = 0; k < n; ++k) p[k] = (int32_t)w(L.o_attacked + k * L.AW);
+    p += n;
+    for (int k = 0; k < n; ++k) p[k] = L.o_tags < 0 ? 0 : (int32_t)((w(L.o_tags + k / 8) >> ((k % 8) * 4)) & 15u);
+    p += n;
+    for (int k = 0; k < L.C; ++k) p[k] = k < nc ? (int32_t)((w(L.o_cache + k / 2) >> ((k & 1) * 16)) & 0xFFFFu) : -1;
+    p += L.C;
+    for (int k = 0; k < (L.nsecrets + 31) / 32; ++k) p[k] = (int32_t)w(L.o_gathered + k);
+  }
+  return CBX_OK;
+}
+
+int64_t cbx_batch_launch_count(const cbx_batch* b) { return b ? b->launches : -1; }
+
+int cbx_batch_enable_timing(cbx_batch* b, int enabled) {
+  if (!b) return fail(CBX_ERR_INVALID, "null batch");
+  b->timing = enabled;
+  return CBX_OK;
+}
+
+int cbx_batch_step_kernel_ms(cbx_batch* b, double* mean_ms, int64_t* launches) {
+  if (!b || !mean_ms || !launches) return fail(CBX_ERR_INVALID, "null argument");
+  CUDA_TRY(cudaSetDevice(b->device));
+  for (size_t k = 0; k + 1 < b->ev_used; k += 2) {
+    CUDA_TRY(cudaEventSynchronize(b->ev[k + 1]));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, b->ev[k], b->ev[k + 1]));
+    b->ms_sum += ms;
+    b->ms_count++;
+  }
+  b->ev_used = 0;
+  *mean_ms = b->ms_count ? b->ms_sum / (double)b->ms_count : 0.0;
+  *launches = b->ms_count;
+  b->ms_sum = 0; b->ms_count = 0;
+  return CBX_OK;
+}
+
+// sizes of the ABI structs, so the Python mirror can be checked without a GPU
+size_t cbx_abi_sizeof(int which) { return which == 0 ? sizeof(cbx_config) : which == 1 ? sizeof(cbx_views) : sizeof(cbx_tape); }
+
+}  // extern "C"

@@ -1,0 +1,783 @@
+// cbx_kernels.cu -- fused env-step kernel (game logic + observation / action-mask encoder) for sm_100a.
+//
+// One persistent CTA per resident slot loops over tiles of 32 envs:
+//   (0) TMA bulk copies stage the scenario tables (once per CTA) and the tile's S x 32 state words into shared memory;
+//   (1) warp 0 plays the step, one thread per env, on the shared-memory tile (cbx_device.cuh);
+//   (2) all 128 threads encode the tile's observations and action masks straight into the output tensors with
+//       16-byte streaming stores -- the dense masks are >90 % of the bytes of a step, so this is the part that runs
+//       against the HBM roofline;
+//   (3) the state tile is streamed back with TMA bulk stores.
+// Algorithmic bytes per env-step and the roofline are stated in DESIGN.md.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "cbx_device.cuh"
+
+namespace cbx {
+
+struct FastDiv {  // x / d for x < 2^31 (d fixed per batch; cbx_fastdiv computed on the host)
+  uint32_t m, s;
+  __device__ __forceinline__ FastDiv(uint32_t m_, uint32_t s_) : m(m_), s(s_) {}
+  __device__ __forceinline__ FastDiv(const cbx_fastdiv& f) : m(f.m), s(f.s) {}
+  __device__ __forceinline__ uint32_t div(uint32_t x) const { return (m ? __umulhi(x, m) : x) >> s; }
+};
+
+// desc (env-major): 0 nd | 1 nc | 2 obs kind | 3 lim_remote | 4 lim_connect | 5 base_lo | 6 base_hi | 7 enc flags |
+//                   [8, 8+OW) owned-by-discovery-index bits | [8+OW, 8+OW+Wn) installed bits for the defender observation
+enum { D_ND = 0, D_NC, D_KIND, D_LIMR, D_LIMC, D_BLO, D_BHI, D_FLAGS, D_OWNED };
+
+// ---- TMA / mbarrier helpers (PTX) -------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_1d(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void st_stream(void* p, uint4 v) { __stcs(reinterpret_cast<uint4*>(p), v); }
+
+// ---- encoder -----------------------------------------------------------------------------------------------------------
+struct Target {  // output pointers already offset to the tile's first env
+  int32_t *scalars, *leaked, *cachem, *props, *priv;
+  int8_t *local, *remote, *connect;
+  int8_t *infected, *fw_in, *fw_out, *services;
+  uint32_t* owned_bits;
+};
+
+struct Tile {
+  const cbx_layout* L;
+  const uint32_t* tb;
+  const uint32_t* st;    // state tile
+  const uint32_t* sg;    // staging
+  const uint32_t* desc;  // env-major
+  const uint2* lut;
+  const cbx_enc_consts* K;
+  int DW;
+  __device__ __forceinline__ uint32_t w(int e, int off) const { return st[off * CBX_TILE + e]; }
+  __device__ __forceinline__ uint32_t g(int e, int off) const { return sg[off * CBX_TILE + e]; }
+  __device__ __forceinline__ uint32_t d(int e, int k) const { return desc[e * DW + k]; }
+  __device__ __forceinline__ uint32_t byte(int e, int off, int i) const { return (w(e, off + (i >> 2)) >> ((i & 3) * 8)) & 0xFFu; }
+  __device__ __forceinline__ bool owned(int e, int s) const { return (d(e, D_OWNED + (s >> 5)) >> (s & 31)) & 1u; }
+};
+
+// generic writer for int32 fields: `wpe` words per env, f(e, wi) -> value
+template <class F>
+__device__ __forceinline__ void write_i32(int32_t* dst, int wpe, FastDiv dv, int n_valid, uint32_t enc_mask, F f) {
+  if (!dst || wpe == 0) return;
+  const uint32_t total = (uint32_t)wpe * n_valid;
+  for (uint32_t v = threadIdx.x * 4; v < total; v += CBX_THREADS * 4) {
+    uint32_t vals[4];
+    uint32_t keep = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t idx = v + q;
+      vals[q] = 0;
+      if (idx < total) {
+        uint32_t e = dv.div(idx);
+        if ((enc_mask >> e) & 1u) { vals[q] = (uint32_t)f((int)e, (int)(idx - e * wpe)); keep |= 1u << q; }
+      }
+    }
+    if (keep == 15u) st_stream(dst + v, make_uint4(vals[0], vals[1], vals[2], vals[3]));
+    else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if ((keep >> q) & 1u) dst[v + q] = (int32_t)vals[q];
+    }
+  }
+}
+
+// generic (slow) writer for int8 fields: f(e, i) -> 0/1
+template <class F>
+__device__ __forceinline__ void write_i8(int8_t* dst, int bpe, FastDiv dv, int n_valid, uint32_t enc_mask, F f) {
+  if (!dst || bpe == 0) return;
+  const uint32_t total = (uint32_t)bpe * n_valid;
+  for (uint32_t v = threadIdx.x * 16; v < total; v += CBX_THREADS * 16) {
+    uint32_t words[4] = {0, 0, 0, 0};
+    uint32_t keep = 0;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      uint32_t idx = v + q;
+      if (idx < total) {
+        uint32_t e = dv.div(idx);
+        if ((enc_mask >> e) & 1u) {
+          words[q >> 2] |= (uint32_t)(f((int)e, (int)(idx - e * bpe)) & 0xFF) << ((q & 3) * 8);
+          keep |= 1u << q;
+        }
+      }
+    }
+    if (keep == 0xFFFFu) st_stream(dst + v, make_uint4(words[0], words[1], words[2], words[3]));
+    else {
+#pragma unroll
+      for (int q = 0; q < 16; ++q)
+        if ((keep >> q) & 1u) dst[v + q] = (int8_t)((words[q >> 2] >> ((q & 3) * 8)) & 0xFF);
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t lowmask(int k) { return k <= 0 ? 0u : (k >= 32 ? 0xFFFFFFFFu : ((1u << k) - 1u)); }
+
+// 16 pattern bits of the connect mask starting at credential phase k: bit j <=> ((k + j) mod C) < nc
+__device__ __forceinline__ uint32_t pat16(const Tile& t, int e, int k, int C) {
+  if (C <= 48) {
+    uint64_t base = ((uint64_t)t.d(e, D_BHI) << 32) | t.d(e, D_BLO);
+    return (uint32_t)(base >> k) & 0xFFFFu;
+  }
+  const int nc = (int)t.d(e, D_NC);
+  uint32_t m = lowmask(min(max(nc - k, 0), 16));
+  m |= lowmask(min(max(C - k + nc, 0), 16)) & ~lowmask(min(max(C - k, 0), 16));
+  return m;
+}
+
+// Row-structured dense masks: byte (s, w) of an env = owned[s] & (w < lim) & pattern(w mod C).
+//   remote  [N][N*R]:   lim = n_discovered * R,     no pattern
+//   connect [N][N*P*C]: lim = n_discovered * P * C, pattern = (credential index < n_cached)
+template <bool CONNECT>
+__device__ __forceinline__ uint32_t rowmask_byte(const Tile& t, int e, uint32_t i, int row_len, FastDiv drow, int C, FastDiv dC) {
+  uint32_t s = drow.div(i), w = i - s * row_len;
+  uint32_t lim = CONNECT ? t.d(e, D_LIMC) : t.d(e, D_LIMR);
+  bool on = t.owned(e, (int)s) && w < lim;
+  if (CONNECT && on) on = (w - dC.div(w) * C) < t.d(e, D_NC);
+  return on ? 1u : 0u;
+}
+
+template <bool CONNECT>
+__device__ __forceinline__ void write_rowmask(int8_t* dst, int bpe, FastDiv denv, int row_len, FastDiv drow, int C, FastDiv dC,
+                                              int n_valid, uint32_t enc_mask, const Tile& t) {
+  if (!dst || bpe == 0) return;
+  const uint32_t total = (uint32_t)bpe * n_valid;
+  const bool fast = (bpe % 16 == 0) && row_len >= 16;
+  for (uint32_t v = threadIdx.x * 16; v < total; v += CBX_THREADS * 16) {
+    if (fast) {
+      uint32_t e = denv.div(v);
+      if (!((enc_mask >> e) & 1u)) continue;
+      uint32_t i = v - e * bpe;
+      uint32_t s = drow.div(i), w0 = i - s * row_len;
+      int lim = (int)(CONNECT ? t.d(e, D_LIMC) : t.d(e, D_LIMR));
+      int a = min(16, row_len - (int)w0);
+      uint32_t m = t.owned(e, (int)s) ? lowmask(min(max(lim - (int)w0, 0), a)) : 0u;
+      if (a < 16 && t.owned(e, (int)s + 1)) m |= lowmask(min(lim, 16 - a)) << a;
+      if (CONNECT) m &= pat16(t, (int)e, (int)(i - dC.div(i) * C), C);
+      uint2 lo = t.lut[m & 0xFFu], hi = t.lut[(m >> 8) & 0xFFu];
+      st_stream(dst + v, make_uint4(lo.x, lo.y, hi.x, hi.y));
+    } else {
+      uint32_t words[4] = {0, 0, 0, 0};
+      uint32_t keep = 0;
+      for (int q = 0; q < 16; ++q) {
+        uint32_t idx = v + q;
+        if (idx < total) {
+          uint32_t e = denv.div(idx);
+          if ((enc_mask >> e) & 1u) {
+            words[q >> 2] |= rowmask_byte<CONNECT>(t, (int)e, idx - e * bpe, row_len, drow, C, dC) << ((q & 3) * 8);
+            keep |= 1u << q;
+          }
+        }
+      }
+      if (keep == 0xFFFFu) st_stream(dst + v, make_uint4(words[0], words[1], words[2], words[3]));
+      else
+        for (int q = 0; q < 16; ++q)
+          if ((keep >> q) & 1u) dst[v + q] = (int8_t)((words[q >> 2] >> ((q & 3) * 8)) & 0xFF);
+    }
+  }
+}
+
+// Encode the attacker observation of the envs selected by enc_mask (bit e = env e of the tile).
+__device__ void encode_attacker(const Tile& t, const Target& o, int n_valid, uint32_t enc_mask) {
+  const cbx_layout* L = t.L;
+  const cbx_enc_consts& K = *t.K;
+  write_i32(o.scalars, 8, FastDiv(0u, 3u), n_valid, enc_mask, [&](int e, int wi) { return t.g(e, STG_SCALARS + wi); });
+  write_i32(o.leaked, 4 * L->LEAK, K.d_leaked, n_valid, enc_mask, [&](int e, int wi) { return t.g(e, L->g_leaked + wi); });
+  write_i32(o.cachem, 2 * L->C, K.d_cachem, n_valid, enc_mask, [&](int e, int wi) -> uint32_t {
+    int c = wi >> 1;
+    if (t.d(e, D_KIND) == OBS_BLANK || c >= (int)t.d(e, D_NC)) return 0u;
+    uint32_t tr = (t.w(e, L->o_cache + (c >> 1)) >> ((c & 1) * 16)) & 0xFFFFu;
+    const uint32_t* rec = t.tb + t.tb[CBX_H_OFF_TRIPLE] + 3 * tr;
+    return (wi & 1) ? rec[1] : t.byte(e, L->o_disc_idx, (int)rec[0]);
+  });
+  write_i32(o.props, L->N * L->nprops, K.d_props, n_valid, enc_mask, [&](int e, int wi) -> uint32_t {
+    if (t.d(e, D_KIND) == OBS_BLANK) return 2u;
+    uint32_t k = FastDiv(K.d_nprops).div((uint32_t)wi), p = wi - k * L->nprops;
+    if (k >= t.d(e, D_ND)) return 0u;
+    uint32_t node = t.byte(e, L->o_disc_order, (int)k);
+    return (t.w(e, L->o_props + node * L->PW + (p >> 5)) >> (p & 31)) & 1u;
+  });
+  write_i32(o.priv, L->N, K.d_priv, n_valid, enc_mask, [&](int e, int wi) -> uint32_t {
+    if (t.d(e, D_KIND) == OBS_BLANK || wi >= (int)t.d(e, D_ND)) return 0u;
+    uint32_t node = t.byte(e, L->o_disc_order, wi);
+    return (t.g(e, L->g_priv + (node >> 4)) >> ((node & 15) * 2)) & 3u;
+  });
+  write_i8(o.local, L->sz_local, K.d_local, n_valid, enc_mask, [&](int e, int i) -> uint32_t {
+    uint32_t s = FastDiv(K.d_L).div((uint32_t)i), v = i - s * L->L;
+    if (!t.owned(e, (int)s)) return 0u;
+    uint32_t node = t.byte(e, L->o_disc_order, (int)s);
+    return t.tb[t.tb[CBX_H_OFF_VULN] + (node * (L->L + L->R) + v) * CBX_VULN_WORDS] & 1u;
+  });
+  write_rowmask<false>(o.remote, L->sz_remote, K.d_remote, L->N * L->R, K.d_rowr, 1, FastDiv(0u, 0u), n_valid, enc_mask, t);
+  write_rowmask<true>(o.connect, L->sz_connect, K.d_connect, L->N * L->P * L->C, K.d_rowc, L->C, K.d_C, n_valid, enc_mask, t);
+}
+
+__device__ void encode_defender(const Tile& t, const Target& o, int n_valid, uint32_t enc_mask, bool static_too) {
+  const cbx_layout* L = t.L;
+  const cbx_enc_consts& K = *t.K;
+  write_i8(o.infected, L->n, K.d_n, n_valid, enc_mask,
+           [&](int e, int i) -> uint32_t { return (t.d(e, D_OWNED + L->OW + (i >> 5)) >> (i & 31)) & 1u; });
+  if (!static_too) return;
+  write_i8(o.fw_in, 6 * L->n, K.d_6n, n_valid, enc_mask, [&](int, int i) -> uint32_t {
+    int node = i / 6, r = i - node * 6;
+    return (t.tb[t.tb[CBX_H_OFF_NODE] + node * CBX_NODE_WORDS + CBX_N_DEFOBS] >> r) & 1u;
+  });
+  write_i8(o.fw_out, 6 * L->n, K.d_6n, n_valid, enc_mask, [&](int, int i) -> uint32_t {
+    int node = i / 6, r = i - node * 6;
+    return (t.tb[t.tb[CBX_H_OFF_NODE] + node * CBX_NODE_WORDS + CBX_N_DEFOBS] >> (8 + r)) & 1u;
+  });
+  write_i8(o.services, L->nservices, K.d_svc, n_valid, enc_mask, [&](int, int) -> uint32_t { return 1u; });
+}
+
+// copy env rows main -> terminal buffers (terminal observation of an intercepted-and-truncated step is the previous one)
+__device__ void copy_rows(void* dst, const void* src, int bpe, int n_valid, uint32_t mask) {
+  if (!dst || !src || bpe == 0) return;
+  for (int e = 0; e < n_valid; ++e) {
+    if (!((mask >> e) & 1u)) continue;
+    const uint8_t* s = (const uint8_t*)src + (size_t)e * bpe;
+    uint8_t* d = (uint8_t*)dst + (size_t)e * bpe;
+    for (int k = threadIdx.x; k < bpe; k += CBX_THREADS) d[k] = s[k];
+  }
+}
+
+__device__ Target make_target(const cbx_views& v, const cbx_layout& L, int64_t e0, bool term) {
+  Target o;
+  const int64_t N = L.N;
+  if (!term) {
+    o.scalars = v.scalars + e0 * 8;
+    o.leaked = v.leaked_credentials + e0 * 4 * L.LEAK;
+    o.cachem = v.credential_cache_matrix + e0 * 2 * L.C;
+    o.props = v.discovered_nodes_properties + e0 * N * L.nprops;
+    o.priv = v.nodes_privilegelevel + e0 * N;
+    o.local = v.local_vulnerability ? v.local_vulnerability + e0 * L.sz_local : nullptr;
+    o.remote = v.remote_vulnerability ? v.remote_vulnerability + e0 * L.sz_remote : nullptr;
+    o.connect = v.connect ? v.connect + e0 * (int64_t)L.sz_connect : nullptr;
+    o.infected = v.def_infected_nodes ? v.def_infected_nodes + e0 * L.n : nullptr;
+    o.fw_in = v.def_incoming_firewall ? v.def_incoming_firewall + e0 * 6 * L.n : nullptr;
+    o.fw_out = v.def_outgoing_firewall ? v.def_outgoing_firewall + e0 * 6 * L.n : nullptr;
+    o.services = v.def_services_status ? v.def_services_status + e0 * L.nservices : nullptr;
+    o.owned_bits = v.owned_bits + e0 * L.OW;
+  } else {
+    o.scalars = v.term_scalars ? v.term_scalars + e0 * 8 : nullptr;
+    o.leaked = v.term_leaked_credentials ? v.term_leaked_credentials + e0 * 4 * L.LEAK : nullptr;
+    o.cachem = v.term_credential_cache_matrix ? v.term_credential_cache_matrix + e0 * 2 * L.C : nullptr;
+    o.props = v.term_discovered_nodes_properties ? v.term_discovered_nodes_properties + e0 * N * L.nprops : nullptr;
+    o.priv = v.term_nodes_privilegelevel ? v.term_nodes_privilegelevel + e0 * N : nullptr;
+    o.local = v.term_local_vulnerability ? v.term_local_vulnerability + e0 * L.sz_local : nullptr;
+    o.remote = v.term_remote_vulnerability ? v.term_remote_vulnerability + e0 * L.sz_remote : nullptr;
+    o.connect = v.term_connect ? v.term_connect + e0 * (int64_t)L.sz_connect : nullptr;
+    o.infected = v.term_def_infected_nodes ? v.term_def_infected_nodes + e0 * L.n : nullptr;
+    o.fw_in = o.fw_out = o.services = nullptr;
+    o.owned_bits = nullptr;
+  }
+  return o;
+}
+
+// env-major descriptor for the encoder, built by the env's logic thread
+__device__ void build_desc(const Ctx& c, uint32_t* d, int DW, const uint32_t* def_inst_override) {
+  const cbx_layout* L = c.L;
+  const uint32_t kind = c.g(STG_OBS_KIND);
+  const int nd = c.nd(), nc = c.nc();
+  d[D_ND] = (uint32_t)nd;
+  d[D_NC] = (uint32_t)nc;
+  d[D_KIND] = kind;
+  d[D_LIMR] = (uint32_t)(nd * L->R);
+  d[D_LIMC] = (uint32_t)(nd * L->P * L->C);
+  uint64_t base = 0;
+  if (L->C <= 48) {
+    int ph = 0;
+    for (int b = 0; b < 64; ++b) {
+      if (ph < nc) base |= 1ull << b;
+      if (++ph == L->C) ph = 0;
+    }
+  }
+  d[D_BLO] = (uint32_t)base;
+  d[D_BHI] = (uint32_t)(base >> 32);
+  d[D_FLAGS] = 0;
+  for (int k = 0; k < L->OW; ++k) d[D_OWNED + k] = 0;
+  if (kind != OBS_BLANK) {
+    for (int s = 0; s < nd; ++s) {
+      uint32_t node = c.byte(L->o_disc_order, s);
+      if ((c.g(L->g_inst + (node >> 5)) >> (node & 31)) & 1u) d[D_OWNED + (s >> 5)] |= 1u << (s & 31);
+    }
+  }
+  for (int k = 0; k < L->Wn; ++k) d[D_OWNED + L->OW + k] = def_inst_override ? def_inst_override[k] : c.w(L->o_installed + k);
+  (void)DW;
+}
+
+struct Acc {  // per-thread episode statistics, reduced once per CTA
+  double v[CBX_STAT_COUNT];
+};
+
+// AttackerEnvWrapper.step (ATT:255-398) for one env; the VecEnv auto-reset is applied later by the caller
+__device__ void attacker_wrapper_step(const Ctx& c, const cbx_params& p, const int32_t* aa, int slice_of_kind[3], Acc& acc) {
+  const cbx_layout* L = c.L;
+  const cbx_config* cfg = c.cfg;
+  int32_t info[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int kind = cfg->kind_of_index[aa[0]];
+  const int32_t* coords = aa + slice_of_kind[kind];
+  const int ndisc = c.nd();
+  bool in_range = kind == CBX_KIND_LOCAL ? coords[0] < ndisc : (coords[0] < ndisc && coords[1] < ndisc);  // ATT:233-253
+  double reward_modifier = 0.0, reward = 0.0, cyber_reward = 0.0;
+  int terminated = 0, truncated = 0;
+  if (!in_range) {
+    c.w(L->o_att_invalid) += 1;
+    reward_modifier += cfg->att_invalid_action_reward_modifier;
+    info[5] = 1;
+    c.g(STG_OBS_KIND) = OBS_KEEP;
+  } else {
+    c.w(L->o_att_valid) += 1;
+    StepOut so = c.cyber_step(kind, coords, p.scan_u, p.detect_u);
+    reward = cyber_reward = so.reward;
+    terminated = so.terminated;
+    info[0] = (int32_t)__float_as_uint((float)so.reward);
+    info[1] = (int32_t)__float_as_uint((float)so.raw);
+    info[2] = so.outcome;
+    info[3] = so.error;
+  }
+  c.setflag(HDR_HAS_CYBER, true);
+  c.setf32(L->o_last_cyber, (float)reward);
+  c.w(L->o_att_ts) += 1;
+  if (c.flag(HDR_ATT_RR)) truncated = 1;
+  if ((int)c.w(L->o_att_ts) >= cfg->att_max_timesteps) truncated = 1;
+  reward = reward + reward_modifier;
+  c.setflag(HDR_HAS_REWARD, true);
+  c.setf32(L->o_last_reward, (float)reward);
+  c.setf32(L->o_att_return, c.f32(L->o_att_return) + (float)reward);
+  info[4] = (int32_t)c.w(L->o_stepcount);
+  p.v.att_reward[c.env] = (float)reward;
+  p.v.att_terminated[c.env] = (uint8_t)terminated;
+  p.v.att_truncated[c.env] = (uint8_t)truncated;
+  p.v.network_availability[c.env] = c.live_availability();
+  acc.v[CBX_STAT_ENV_STEPS] += 1;
+  const int done = terminated || truncated;
+  c.g(STG_ATT_DONE) = (uint32_t)done;
+  if (done) {
+    info[6] = (int32_t)c.w(L->o_att_ts);
+    double ret = (double)c.f32(L->o_att_return);
+    int len = (int)c.w(L->o_att_ts);
+    acc.v[CBX_STAT_EPISODES] += 1;
+    acc.v[CBX_STAT_ATT_RETURN] += ret;
+    acc.v[CBX_STAT_ATT_RETURN_SQ] += ret * ret;
+    acc.v[CBX_STAT_EP_LEN] += len;
+    acc.v[CBX_STAT_EP_LEN_SQ] += (double)len * len;
+    acc.v[CBX_STAT_ATT_VALID] += c.w(L->o_att_valid);
+    acc.v[CBX_STAT_ATT_INVALID] += c.w(L->o_att_invalid);
+    if (terminated && cyber_reward == cfg->winning_reward) acc.v[CBX_STAT_ATT_WINS] += 1;
+    if (!terminated && (int)c.w(L->o_att_ts) >= cfg->att_max_timesteps) acc.v[CBX_STAT_TIMEOUTS] += 1;
+  }
+  int4* ip = reinterpret_cast<int4*>(p.v.att_info + c.env * 8);
+  ip[0] = make_int4(info[0], info[1], info[2], info[3]);
+  ip[1] = make_int4(info[4], info[5], info[6], info[7]);
+}
+
+// DefenderEnvWrapper.step (DWR:197-327) with LearningDefender.executeAction on the stale copy (LDF:31-107)
+__device__ void defender_wrapper_step(const Ctx& c, const cbx_params& p, const int32_t* da, Acc& acc) {
+  const cbx_layout* L = c.L;
+  const cbx_config* cfg = c.cfg;
+  double reward = 0.0;
+  int term = 0, trunc = 0;
+  const bool empty = da[0] < 0;
+  const bool valid = empty ? true : c.defender_action_valid(da);
+  if (!valid) { c.w(L->o_def_invalid) += 1; reward += cfg->def_invalid_action_reward; }
+  else c.w(L->o_def_valid) += 1;
+  int down = c.tick(L->o_cd_shadow, -1);  // on_attacker_step_taken() of the stale actuator: availability BEFORE the action
+  if (valid && !empty && da[0] == 0) c.setbyte(L->o_cd_shadow, da[1], 16);
+  uint32_t a = c.w(L->o_avail);
+  const int prev_down = (int)((a >> 16) & 0xFFu);
+  const double cur = c.availability(down), prev = c.availability(prev_down);
+  const double worsening = prev - cur;
+  if (c.flag(HDR_HAS_CYBER)) reward += -1.0 * (double)c.f32(L->o_last_cyber);
+  if (cur < cfg->maintain_sla) {
+    if (!c.flag(HDR_BREACHED)) {
+      reward += cfg->def_loss_reward;
+      if (cfg->def_reset_on_constraint_broken) term = 1;
+      c.setflag(HDR_BREACHED, true);
+      acc.v[CBX_STAT_SLA_BREACHES] += 1;
+    } else if (worsening > 0) reward += -cfg->def_sla_worsening_penalty_scale * worsening;
+  } else c.setflag(HDR_BREACHED, false);
+  c.w(L->o_avail) = (a & 0xFFu) | ((uint32_t)down << 8) | ((uint32_t)down << 16);
+  if (c.defender_goal_reached()) { reward = cfg->winning_reward; term = 1; }
+  c.w(L->o_def_ts) += 1;
+  if (c.flag(HDR_DEF_RR)) { trunc = 1; reward = -1.0 * (double)c.f32(L->o_last_att); }
+  else if ((int)c.w(L->o_def_ts) >= cfg->def_max_timesteps) trunc = 1;
+  c.setf32(L->o_def_return, c.f32(L->o_def_return) + (float)reward);
+  p.v.def_reward[c.env] = (float)reward;
+  p.v.def_terminated[c.env] = (uint8_t)term;
+  p.v.def_truncated[c.env] = (uint8_t)trunc;
+  const int done = term || trunc;
+  c.g(STG_DEF_DONE) = (uint32_t)done;
+  if (done) {
+    double ret = (double)c.f32(L->o_def_return);
+    acc.v[CBX_STAT_DEF_RETURN] += ret;
+    acc.v[CBX_STAT_DEF_RETURN_SQ] += ret * ret;
+    acc.v[CBX_STAT_DEF_VALID] += c.w(L->o_def_valid);
+    acc.v[CBX_STAT_DEF_INVALID] += c.w(L->o_def_invalid);
+    for (int k = 0; k < L->Wn; ++k) c.g(STG_DEF_TERM_INST + k) = c.w(L->o_installed + k);
+  }
+}
+
+__device__ void cyber_only_step(const Ctx& c, const cbx_params& p, const int32_t* a, Acc& acc) {
+  const cbx_layout* L = c.L;
+  StepOut so = c.cyber_step(a[0], a + 1, p.scan_u, p.detect_u);
+  int4* ip = reinterpret_cast<int4*>(p.v.att_info + c.env * 8);
+  int done = so.terminated && so.error != CBX_E_STEP_AFTER_DONE;
+  ip[0] = make_int4((int)__float_as_uint((float)so.reward), (int)__float_as_uint((float)so.raw), so.outcome, so.error);
+  ip[1] = make_int4((int)c.w(L->o_stepcount), 0, done ? (int)c.w(L->o_stepcount) : 0, 0);
+  p.v.att_reward[c.env] = (float)so.reward;
+  p.v.att_terminated[c.env] = (uint8_t)so.terminated;
+  p.v.att_truncated[c.env] = 0;
+  p.v.network_availability[c.env] = c.live_availability();
+  c.g(STG_ATT_DONE) = (uint32_t)done;
+  if (so.error == CBX_E_STEP_AFTER_DONE) return;
+  acc.v[CBX_STAT_ENV_STEPS] += 1;
+  c.setf32(L->o_att_return, c.f32(L->o_att_return) + (float)so.reward);
+  if (done) {
+    double ret = (double)c.f32(L->o_att_return);
+    int len = (int)c.w(L->o_stepcount);
+    acc.v[CBX_STAT_EPISODES] += 1;
+    acc.v[CBX_STAT_ATT_RETURN] += ret;
+    acc.v[CBX_STAT_ATT_RETURN_SQ] += ret * ret;
+    acc.v[CBX_STAT_EP_LEN] += len;
+    acc.v[CBX_STAT_EP_LEN_SQ] += (double)len * len;
+    if (so.reward == c.cfg->winning_reward) acc.v[CBX_STAT_ATT_WINS] += 1;
+  }
+}
+
+// ---- the kernel ----------------------------------------------------------------------------------------------------------
+template <bool USE_TMA>
+__global__ void __launch_bounds__(CBX_THREADS) cbx_step_kernel(const __grid_constant__ cbx_params p, const int reset_only) {
+  extern __shared__ __align__(128) uint32_t smem[];
+  const cbx_layout& L = p.lay;
+  const cbx_config& cfg = p.cfg;
+  uint32_t* s_tb = smem + p.plan.tables;
+  uint32_t* s_st = smem + p.plan.state;
+  uint32_t* s_sg = smem + p.plan.stage;
+  uint32_t* s_desc = smem + p.plan.desc;
+  uint2* s_lut = reinterpret_cast<uint2*>(smem + p.plan.lut);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.plan.bars);
+  __shared__ int s_tile;
+  __shared__ uint32_t s_masks[4];
+  const int tid = threadIdx.x;
+  const int DW = p.enc.desc_words;
+  const uint32_t* s_init = s_tb + p.table_words;  // initial per-env state follows the scenario blob
+  const uint32_t table_bytes = (uint32_t)(p.table_words + ((L.S + 3) & ~3)) * 4u;
+
+  // bits -> bytes expansion table: 8 mask bits to 8 bytes of 0/1
+  for (int k = tid; k < 256; k += CBX_THREADS) {
+    uint32_t lo = ((k & 0xF) * 0x00204081u) & 0x01010101u, hi = (((k >> 4) & 0xF) * 0x00204081u) & 0x01010101u;
+    s_lut[k] = make_uint2(lo, hi);
+  }
+  if (USE_TMA) {
+    if (tid == 0) {
+      mbar_init(&bars[0], 1);
+      mbar_init(&bars[1], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+      mbar_expect_tx(&bars[0], table_bytes);
+      tma_load_1d(s_tb, p.tables, table_bytes, &bars[0]);
+    }
+    mbar_wait(&bars[0], 0);
+  } else {
+    for (uint32_t k = tid; k < table_bytes / 4; k += CBX_THREADS) s_tb[k] = p.tables[k];
+    __syncthreads();
+  }
+
+  Acc acc;
+#pragma unroll
+  for (int k = 0; k < CBX_STAT_COUNT; ++k) acc.v[k] = 0.0;
+  uint32_t st_phase = 0;
+  int slice_of_kind[3] = {p.slice_of_kind[0], p.slice_of_kind[1], p.slice_of_kind[2]};
+
+  for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    const int64_t e0 = (int64_t)tile * CBX_TILE;
+    const int n_valid = (int)min((int64_t)CBX_TILE, p.n_envs - e0);
+    // ---- (0) stage the state tile: S rows of 128 B ----
+    if (USE_TMA) {
+      if (tid < 32) {
+        if (tid == 0) mbar_expect_tx(&bars[1], (uint32_t)L.S * 128u);
+        __syncwarp();
+        for (int r = tid; r < L.S; r += 32) tma_load_1d(s_st + r * CBX_TILE, p.state + (int64_t)r * p.n_pad + e0, 128u, &bars[1]);
+      }
+      mbar_wait(&bars[1], st_phase);
+      st_phase ^= 1;
+    } else {
+      for (int k = tid; k < L.S * CBX_TILE; k += CBX_THREADS)
+        s_st[k] = p.state[(int64_t)(k / CBX_TILE) * p.n_pad + e0 + (k % CBX_TILE)];
+      __syncthreads();
+    }
+
+    const bool active = tid < n_valid;
+    Ctx c;
+    c.st = s_st + tid; c.sg = s_sg + tid; c.tb = s_tb; c.L = &L; c.cfg = &cfg; c.env = e0 + tid;
+
+    // ---- (1) game logic, phase 1: attacker move (or reset) ----
+    if (tid < CBX_TILE) {
+      uint32_t att_done = 0, keep = 1;
+      if (active) {
+        c.g(STG_ATT_DONE) = 0; c.g(STG_DEF_DONE) = 0;
+        if (reset_only) {
+          if (!p.reset_mask || p.reset_mask[c.env]) {
+            if (cfg.mode == CBX_MODE_MARLON) {
+              c.attacker_reset(s_init);
+              if (cfg.def_enabled) c.defender_reset(s_init);
+            } else {
+              c.cyber_reset(s_init);
+              c.setf32(L.o_att_return, 0.f);
+            }
+            c.stage_reset_obs();
+            p.v.att_reward[c.env] = 0.f; p.v.att_terminated[c.env] = 0; p.v.att_truncated[c.env] = 0;
+            p.v.def_reward[c.env] = 0.f; p.v.def_terminated[c.env] = 0; p.v.def_truncated[c.env] = 0;
+            p.v.network_availability[c.env] = 1.0;
+            int4* ip = reinterpret_cast<int4*>(p.v.att_info + c.env * 8);
+            ip[0] = make_int4(0, 0, 0, 0); ip[1] = make_int4(0, 0, 0, 0);
+          } else c.g(STG_OBS_KIND) = OBS_KEEP;
+        } else if (cfg.mode == CBX_MODE_MARLON) {
+          attacker_wrapper_step(c, p, p.att_actions + c.env * 10, slice_of_kind, acc);
+        } else {
+          cyber_only_step(c, p, p.att_actions + c.env * 5, acc);
+        }
+        att_done = c.g(STG_ATT_DONE);
+        keep = c.g(STG_OBS_KIND) == OBS_KEEP;
+      }
+      uint32_t done_mask = __ballot_sync(0xFFFFFFFFu, att_done != 0);
+      uint32_t keep_mask = __ballot_sync(0xFFFFFFFFu, keep != 0);
+      if (tid == 0) { s_masks[0] = done_mask; s_masks[1] = keep_mask; }
+    }
+    __syncthreads();
+    const uint32_t att_done_mask = s_masks[0];
+    Tile t;
+    t.L = &L; t.tb = s_tb; t.st = s_st; t.sg = s_sg; t.desc = s_desc; t.lut = s_lut; t.K = &p.enc; t.DW = DW;
+
+    // ---- (1b) terminal observations of the envs that finished (rare): encode BEFORE the auto-reset ----
+    if (att_done_mask && cfg.auto_reset && cfg.emit_terminal_obs && !reset_only) {
+      const uint32_t keep_mask = s_masks[1];
+      if (tid < CBX_TILE && active && ((att_done_mask >> tid) & 1u)) build_desc(c, s_desc + tid * DW, DW, nullptr);
+      __syncthreads();
+      Target tt = make_target(p.v, L, e0, true);
+      encode_attacker(t, tt, n_valid, att_done_mask & ~keep_mask);
+      const uint32_t cp = att_done_mask & keep_mask;
+      if (cp) {
+        Target tm = make_target(p.v, L, e0, false);
+        copy_rows(tt.scalars, tm.scalars, 32, n_valid, cp);
+        copy_rows(tt.leaked, tm.leaked, 16 * L.LEAK, n_valid, cp);
+        copy_rows(tt.cachem, tm.cachem, 8 * L.C, n_valid, cp);
+        copy_rows(tt.props, tm.props, 4 * L.N * L.nprops, n_valid, cp);
+        copy_rows(tt.priv, tm.priv, 4 * L.N, n_valid, cp);
+        copy_rows(tt.local, tm.local, L.sz_local, n_valid, cp);
+        copy_rows(tt.remote, tm.remote, L.sz_remote, n_valid, cp);
+        copy_rows(tt.connect, tm.connect, L.sz_connect, n_valid, cp);
+      }
+      __syncthreads();
+    }
+
+    // ---- (2) game logic, phase 2: attacker auto-reset, defender move ----
+    if (tid < CBX_TILE) {
+      uint32_t def_done = 0, keep = 1;
+      if (active) {
+        if (!reset_only) {
+          if (c.g(STG_ATT_DONE) && cfg.auto_reset) {
+            if (cfg.mode == CBX_MODE_MARLON) c.attacker_reset(s_init);
+            else { c.cyber_reset(s_init); c.setf32(L.o_att_return, 0.f); }
+            c.stage_reset_obs();
+          }
+          if (cfg.mode == CBX_MODE_MARLON && cfg.def_enabled) defender_wrapper_step(c, p, p.def_actions + c.env * 12, acc);
+        }
+        def_done = c.g(STG_DEF_DONE) && cfg.auto_reset;
+        keep = c.g(STG_OBS_KIND) == OBS_KEEP;
+        // main defender observation: after an auto-reset it shows the fresh environment (DWR:477)
+        build_desc(c, s_desc + tid * DW, DW, def_done ? s_init + L.o_installed : nullptr);
+        if (!keep) {
+          uint32_t* ob = p.v.owned_bits + c.env * L.OW;
+          for (int k = 0; k < L.OW; ++k) ob[k] = s_desc[tid * DW + D_OWNED + k];
+        }
+      }
+      uint32_t dmask = __ballot_sync(0xFFFFFFFFu, def_done != 0);
+      uint32_t kmask = __ballot_sync(0xFFFFFFFFu, keep != 0);
+      if (tid == 0) { s_masks[2] = dmask; s_masks[3] = kmask; }
+    }
+    __syncthreads();
+    const uint32_t def_done_mask = s_masks[2];
+    const uint32_t enc_mask = ~s_masks[3];
+
+    // ---- (3) encode ----
+    {
+      Target tm = make_target(p.v, L, e0, false);
+      encode_attacker(t, tm, n_valid, enc_mask);
+      if (cfg.mode == CBX_MODE_MARLON && cfg.def_enabled) {
+        encode_defender(t, tm, n_valid, 0xFFFFFFFFu, true);
+        if (def_done_mask && cfg.emit_terminal_obs) {
+          // terminal defender observation = infected nodes seen by the step that ended the episode
+          __syncthreads();
+          if (tid < CBX_TILE && active && ((def_done_mask >> tid) & 1u))
+            for (int k = 0; k < L.Wn; ++k) s_desc[tid * DW + D_OWNED + L.OW + k] = c.g(STG_DEF_TERM_INST + k);
+          __syncthreads();
+          Target tt = make_target(p.v, L, e0, true);
+          encode_defender(t, tt, n_valid, def_done_mask, false);
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- (4) deferred defender auto-reset (DummyVecEnv resets after the step; the attacker's observation of this
+    //          step was taken before it), then stream the state tile back ----
+    if (tid < CBX_TILE && active && ((def_done_mask >> tid) & 1u)) c.defender_reset(s_init);
+    if (USE_TMA) {
+      fence_async_smem();
+      __syncthreads();
+      if (tid < 32) {
+        for (int r = tid; r < L.S; r += 32) tma_store_1d(p.state + (int64_t)r * p.n_pad + e0, s_st + r * CBX_TILE, 128u);
+        tma_store_commit();
+        tma_store_wait_read();  // the tile buffer is reused by the next iteration
+      }
+      __syncthreads();
+    } else {
+      __syncthreads();
+      for (int k = tid; k < L.S * CBX_TILE; k += CBX_THREADS)
+        p.state[(int64_t)(k / CBX_TILE) * p.n_pad + e0 + (k % CBX_TILE)] = s_st[k];
+      __syncthreads();
+    }
+  }
+  if (USE_TMA && tid < 32) tma_store_wait_all();
+
+  // ---- episode statistics: warp shuffle reduce, one atomic per slot per CTA ----
+  if (tid < 32) {
+#pragma unroll
+    for (int k = 0; k < CBX_STAT_COUNT; ++k) {
+      double x = acc.v[k];
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xFFFFFFFFu, x, o);
+      if (tid == 0 && x != 0.0) atomicAdd(p.v.episode_stats + k, x);
+    }
+  }
+}
+
+
+// ---- uniformly sampled valid actions (benchmark load; ENV:959-1047 semantics) -------------------------------------------
+// One thread per env reads its state words straight from HBM (column access is coalesced across the warp).
+__global__ void cbx_sample_kernel(const __grid_constant__ cbx_params p, int32_t* att, int32_t* def, uint64_t seed, uint32_t step) {
+  const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= p.n_envs) return;
+  const cbx_layout& L = p.lay;
+  auto W = [&](int off) { return p.state[(int64_t)off * p.n_pad + env]; };
+  uint32_t r[4];
+  philox4x32_10((uint32_t)env, (uint32_t)(env >> 32), step, 0x5A17u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+  uint32_t r2[4];
+  philox4x32_10((uint32_t)env, (uint32_t)(env >> 32), step, 0x5A18u, (uint32_t)seed, (uint32_t)(seed >> 32), r2);
+  const uint32_t hdr = W(L.o_hdr);
+  const int nd = hdr & 0xFF, nc = (hdr >> 8) & 0xFFFF;
+  // owned discovery indices
+  int owned[256];
+  int n_owned = 0;
+  for (int s = 0; s < nd; ++s) {
+    uint32_t node = (W(L.o_disc_order + (s >> 2)) >> ((s & 3) * 8)) & 0xFFu;
+    if ((W(L.o_installed + (node >> 5)) >> (node & 31)) & 1u) owned[n_owned++] = s;
+  }
+  int kind = (int)(__umulhi(r[0], nc > 0 ? 3u : 2u));  // 0 local, 1 remote, 2 connect (connect needs a cached credential)
+  int src = n_owned ? owned[__umulhi(r[1], (uint32_t)n_owned)] : 0;
+  int a[4] = {src, 0, 0, 0};
+  if (kind == CBX_KIND_LOCAL) {
+    // resample until the mask admits the action: pick uniformly among the vulnerabilities present on the node
+    uint32_t node = (W(L.o_disc_order + (src >> 2)) >> ((src & 3) * 8)) & 0xFFu;
+    int present[64];
+    int np = 0;
+    for (int v = 0; v < L.L && v < 64; ++v)
+      if (p.tables[p.tables[CBX_H_OFF_VULN] + (node * (L.L + L.R) + v) * CBX_VULN_WORDS] & 1u) present[np++] = v;
+    if (np) a[1] = present[__umulhi(r[2], (uint32_t)np)];
+    else { kind = CBX_KIND_REMOTE; }
+  }
+  if (kind == CBX_KIND_REMOTE) {
+    a[1] = (int)__umulhi(r[2], (uint32_t)max(nd, 1));
+    a[2] = (int)__umulhi(r[3], (uint32_t)L.R);
+  } else if (kind == CBX_KIND_CONNECT) {
+    a[1] = (int)__umulhi(r[2], (uint32_t)max(nd, 1));
+    a[2] = (int)__umulhi(r[3], (uint32_t)L.P);
+    a[3] = (int)__umulhi(r2[0], (uint32_t)max(nc, 1));
+  }
+  if (p.cfg.mode == CBX_MODE_MARLON) {
+    int32_t* o = att + env * 10;
+    for (int k = 0; k < 10; ++k) o[k] = 0;
+    int idx = 0;
+    for (int k = 0; k < 3; ++k)
+      if (p.cfg.kind_of_index[k] == kind) idx = k;
+    o[0] = idx;
+    const int width = kind == CBX_KIND_LOCAL ? 2 : kind == CBX_KIND_REMOTE ? 3 : 4;
+    for (int k = 0; k < width; ++k) o[p.slice_of_kind[kind] + k] = a[k];
+    if (def) {
+      int32_t* d = def + env * 12;
+      const uint32_t n = (uint32_t)L.n;
+      d[0] = (int)__umulhi(r2[1], 5u);
+      uint32_t x = r2[2], y = r2[3];
+      d[1] = (int)__umulhi(x, n); x = x * 1664525u + 1013904223u;
+      d[2] = (int)__umulhi(x, n); x = x * 1664525u + 1013904223u;
+      d[3] = (int)__umulhi(x, 6u); x = x * 1664525u + 1013904223u;
+      d[4] = (int)__umulhi(x, 2u); x = x * 1664525u + 1013904223u;
+      d[5] = (int)__umulhi(x, n); x = x * 1664525u + 1013904223u;
+      d[6] = (int)__umulhi(y, 6u); y = y * 1664525u + 1013904223u;
+      d[7] = (int)__umulhi(y, 2u); y = y * 1664525u + 1013904223u;
+      d[8] = (int)__umulhi(y, n); y = y * 1664525u + 1013904223u;
+      d[9] = (int)__umulhi(y, 3u); y = y * 1664525u + 1013904223u;
+      d[10] = (int)__umulhi(y, n); y = y * 1664525u + 1013904223u;
+      d[11] = (int)__umulhi(y, 3u);
+    }
+  } else {
+    int32_t* o = att + env * 5;
+    o[0] = kind; o[1] = a[0]; o[2] = a[1]; o[3] = a[2]; o[4] = a[3];
+  }
+}
+
+}  // namespace cbx
+
+// ---- launch helpers used by cbx_api.cu ------------------------------------------------------------------------------------
+extern "C" {
+cudaError_t cbx_launch_step(const cbx_params* p, int reset_only, int grid, int smem_bytes, int use_tma, cudaStream_t stream) {
+  if (use_tma) cbx::cbx_step_kernel<true><<<grid, CBX_THREADS, smem_bytes, stream>>>(*p, reset_only);
+  else cbx::cbx_step_kernel<false><<<grid, CBX_THREADS, smem_bytes, stream>>>(*p, reset_only);
+  return cudaGetLastError();
+}
+cudaError_t cbx_launch_sample(const cbx_params* p, int32_t* att, int32_t* def, uint64_t seed, uint32_t step, cudaStream_t stream) {
+  const int threads = 128;
+  const int grid = (int)((p->n_envs + threads - 1) / threads);
+  cbx::cbx_sample_kernel<<<grid, threads, 0, stream>>>(*p, att, def, seed, step);
+  return cudaGetLastError();
+}
+cudaError_t cbx_kernel_attrs(int smem_bytes, int use_tma, int* blocks_per_sm) {
+  cudaError_t e;
+  if (use_tma) {
+    e = cudaFuncSetAttribute(cbx::cbx_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, cbx::cbx_step_kernel<true>, CBX_THREADS, smem_bytes);
+  }
+  e = cudaFuncSetAttribute(cbx::cbx_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  if (e != cudaSuccess) return e;
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, cbx::cbx_step_kernel<false>, CBX_THREADS, smem_bytes);
+}
+}

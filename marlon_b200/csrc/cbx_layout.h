@@ -1,0 +1,102 @@
+// cbx_layout.h -- HBM data layout of a batch and the parameter block of the kernels (host + device).
+//
+// Per-env dynamic state is a structure of arrays of 32-bit words: word w of env e lives at
+// state[w * n_pad + e], so a tile of 32 consecutive envs is S rows of 128 contiguous bytes (one row per
+// state word).  A CTA stages the S x 32 tile in shared memory (row-major, i.e. word-major / env-minor: thread
+// e touching word w hits bank e -- conflict-free for the one-thread-per-env game logic), plays the step on it
+// and streams it back.  What replaces the reference's Python objects:
+//   discovered order + inverse map, agent_installed / ever_owned / not-running bitsets, 2-bit privilege levels,
+//   reimaging countdowns (live env and the MARLon defender's stale copy), discovered-property bitsets,
+//   2 bits per (node, vulnerability) replacing the last_attack timestamps, gathered-secret and cached-triple
+//   bitsets, the ordered credential cache, and the wrappers' counters.
+#ifndef CBX_LAYOUT_H_
+#define CBX_LAYOUT_H_
+
+#include <stdint.h>
+
+#include "../../include/cbx.h"
+
+#define CBX_TILE 32          // envs per tile (= one warp of game-logic threads)
+#define CBX_THREADS 128      // threads per CTA
+#define CBX_MAX_LEAK 64
+
+struct cbx_layout {
+  // dimensions
+  int n, N, C, LEAK, P, L, R, nprops, nsecrets, ntriples, nservices;
+  int Wn;      // words of a node bitset
+  int PW;      // words of a property bitset (1 or 2)
+  int AW;      // words of the attacked bits of one node: 2 bits per vulnerability
+  int OW;      // words of the owned-by-discovery-index bitset (over N)
+  // word offsets inside the per-env state
+  int o_hdr;          // bits 0-7 n_discovered | 8-23 n_cached | 24 done | 25 att_reset_request | 26 def_reset_request |
+                      //      27 has_breached_sla | 28 cyber_rewards non-empty | 29 rewards non-empty
+  int o_stepcount;
+  int o_att_ts, o_def_ts;
+  int o_att_valid, o_att_invalid, o_def_valid, o_def_invalid;
+  int o_last_cyber;   // f32: AttackerEnvWrapper.cyber_rewards[-1]
+  int o_last_reward;  // f32: AttackerEnvWrapper.rewards[-1]
+  int o_last_att;     // f32: DefenderEnvWrapper.__last_attacker_reward
+  int o_att_return, o_def_return;  // f32 running episode returns (Monitor)
+  int o_ep_sum;       // f32 sum of CyberBattleEnv.__episode_rewards
+  int o_avail;        // bits 0-7 live not-running count at last tick | 8-15 shadow count at last tick | 16-23 previous shadow count
+  int o_installed, o_everowned, o_notrunning;  // Wn words each
+  int o_priv;         // 2 bits per node
+  int o_tags;         // 4 bits per node (dynamic privilege_N tags)
+  int o_cd_live;      // 8 bits per node: 0 = Running, k = Imaging with k ticks left
+  int o_cd_shadow;
+  int o_disc_order;   // 8 bits per discovery index: node
+  int o_disc_idx;     // 8 bits per node: discovery index, 0xFF = undiscovered
+  int o_props;        // n * PW
+  int o_attacked;     // n * AW
+  int o_gathered;     // ceil(nsecrets/32)
+  int o_cached;       // ceil(ntriples/32): triple already in the cache
+  int o_cache;        // 16 bits per cache slot: triple id
+  int o_cyber_begin;  // words [o_cyber_begin, S) (+ parts of hdr / avail) belong to the CyberBattleEnv and are re-initialised
+                      // by CyberBattleEnv.reset(); the words before it belong to the MARLon wrappers and the stale copy
+  int S;              // words per env
+  // per-env staging words written by the game-logic thread for the encoder (word-major like the state tile):
+  //   [0,8) scalars | 8 obs kind | 9 attacker done | 10 defender done | [11, 11+Wn) installed bits at defender done
+  int g_leaked;       // 4*LEAK leaked-credential slots
+  int g_inst;         // Wn: agent_installed bits as the observation sees them (before the built-in defender moves)
+  int g_priv;         // ceil(n/16): privilege levels as the observation sees them
+  int G;              // staging words per env
+  // byte sizes per env of the dense masks
+  int sz_local, sz_remote, sz_connect;
+};
+
+struct cbx_fastdiv {  // x / d for x < 2^31: (m ? umulhi(x, m) : x) >> s
+  uint32_t m, s;
+};
+
+struct cbx_enc_consts {  // divisors of the encoder, fixed per batch
+  cbx_fastdiv d_leaked, d_cachem, d_props, d_priv, d_nprops, d_L, d_local, d_remote, d_connect, d_rowr, d_rowc, d_C, d_n,
+      d_6n, d_svc;
+  int desc_words;
+};
+
+struct cbx_smem_plan {  // shared-memory carve-up in 32-bit words
+  int tables, state, stage, desc, lut, bars, total_bytes;
+};
+
+struct cbx_params {
+  cbx_layout lay;
+  cbx_enc_consts enc;
+  cbx_smem_plan plan;
+  cbx_config cfg;
+  int64_t n_envs;
+  int64_t n_pad;          // n_envs rounded up to CBX_TILE
+  int n_tiles;
+  int table_words;        // scenario blob words (multiple of 4)
+  int slice_of_kind[3];
+  const uint32_t* tables; // scenario blob followed by the S-word initial state
+  uint32_t* state;
+  const int32_t* att_actions;
+  const int32_t* def_actions;
+  const double* scan_u;
+  const double* detect_u;
+  const uint8_t* reset_mask;  // reset kernel only
+  cbx_views v;
+  int* tile_counter;      // dynamic tile scheduler
+};
+
+#endif  // CBX_LAYOUT_H_

@@ -1,0 +1,175 @@
+"""GPU parity: the CUDA library (through the C ABI) against (a) the golden tapes recorded from the reference and
+(b) the C oracle on seeded inputs at the configs' sizes.  Integer / byte / index work bit-exact; rewards within
+1e-6 relative (BASELINE.json north_star), they are in fact exact."""
+import numpy as np
+import pytest
+
+import helpers
+from marlon_b200 import _abi, config, scenario, scenarios
+
+pytestmark = pytest.mark.gpu
+
+
+def _batch(comp, cfg, n):
+    from marlon_b200.batch import Batch
+
+    return Batch(comp, cfg, n)
+
+
+@pytest.mark.parametrize("name", helpers.golden_tapes())
+def test_cuda_matches_reference_tape(name):
+    meta, z = helpers.load_tape(name)
+    comp, cfg = helpers.config_from_meta(meta)
+    b = _batch(comp, cfg, meta["n_tapes"])
+    steps = helpers.replay(meta, z, b, b.numpy, b.export_state)
+    assert steps == meta["steps"]
+    b.close()
+
+
+def _compare_all(b, o, step, names=None):
+    for k, t in b.tensors.items():
+        if names and k not in names:
+            continue
+        if k.startswith("term_"):
+            continue
+        got, want = t.cpu().numpy(), o.arrays[k]
+        assert got.shape == want.shape, k
+        if got.dtype.kind == "f":
+            assert np.allclose(got, want, rtol=helpers.REWARD_RTOL, atol=helpers.REWARD_RTOL), (step, k)
+        else:
+            assert np.array_equal(got, want), (step, k, np.argwhere(got != want)[:4])
+    assert np.array_equal(b.export_state(), o.export_state()), (step, "state")
+
+
+def _run_against_oracle(comp, cfg, n, steps, seed, uniform_every=3, check_every=8, tape_rng=None):
+    from oracle import OracleBatch
+
+    b = _batch(comp, cfg, n)
+    o = OracleBatch(comp, cfg, n)
+    b.reset()
+    o.reset()
+    _compare_all(b, o, -1)
+    rng = np.random.default_rng(seed)
+    marlon = cfg.mode == _abi.MODE_MARLON
+    cap = max(cfg.scan_capacity, 1)
+    for s in range(steps):
+        att, dfn = b.sample_actions(seed=seed)
+        att = att.cpu().numpy()
+        dfn = dfn.cpu().numpy() if dfn is not None else None
+        if uniform_every and s % uniform_every == 0:  # sprinkle uniform (mostly invalid) actions: penalty / intercept branches
+            pick = rng.random(n) < 0.5
+            if marlon:
+                nvec = np.array([3] + [cfg.maximum_node_count] * 9)
+                lay = config.attacker_action_layout(cfg)
+                for kind, (a0, a1) in lay.items():
+                    dims = {0: [b.views.N, b.views.L], 1: [b.views.N, b.views.N, b.views.R],
+                            2: [b.views.N, b.views.N, b.views.P, b.views.C]}[kind]
+                    nvec[a0:a1] = dims
+                uni = (rng.random((n, 10)) * nvec).astype(np.int32)
+            else:
+                kind = rng.integers(0, 3, n)
+                uni = np.zeros((n, 5), dtype=np.int32)
+                uni[:, 0] = kind
+                uni[:, 1] = rng.integers(0, b.views.N, n)
+                uni[:, 2] = np.where(kind == 0, rng.integers(0, b.views.L, n), rng.integers(0, b.views.N, n))
+                uni[:, 3] = np.where(kind == 1, rng.integers(0, b.views.R, n), rng.integers(0, b.views.P, n))
+                uni[:, 4] = rng.integers(0, b.views.C, n)
+            att = np.where(pick[:, None], uni, att)
+            if dfn is not None:
+                dfn[rng.random(n) < 0.3, 0] = -1  # empty defender action
+        su = du = None
+        if tape_rng is not None and cfg.builtin_defender:
+            su, du = tape_rng.random((n, cap)), tape_rng.random((n, cap))
+        b.step(att, dfn, su, du)
+        o.step(att, dfn, su, du)
+        if s % check_every == 0 or s == steps - 1:
+            _compare_all(b, o, s)
+    assert np.allclose(b.stats(), o.stats, rtol=1e-9, atol=1e-6), (b.stats(), o.stats)
+    assert b.stats()[_abi.STAT_ENV_STEPS] == n * steps
+    b.close()
+
+
+def test_chain10_attacker_only_4096_envs_vs_oracle():
+    """BASELINE.json configs[1]: CyberBattleChain-10 attacker-only, 4096 batched envs, bit-exact."""
+    comp = scenario.compile_scenario(scenarios.chain_environment(10))
+    cfg = config.make_config(_abi.MODE_CYBERBATTLE, maximum_node_count=12, maximum_total_credentials=12,
+                             throws_on_invalid_actions=False, attacker_goal=config.AttackerGoal(own_atleast_percent=1.0),
+                             auto_reset=True, emit_terminal_obs=True)
+    _run_against_oracle(comp, cfg, 4096, 160, seed=7)
+
+
+def test_toyctf_scan_and_reimage_philox_vs_oracle():
+    """configs[2] parity leg: ToyCtf + ScanAndReimage(0.6, 2, 5), SLA 0.80, Philox draws on both sides."""
+    comp = scenario.compile_scenario(scenarios.toyctf_environment())
+    cfg = config.make_config(_abi.MODE_CYBERBATTLE, maximum_node_count=12, maximum_total_credentials=10,
+                             throws_on_invalid_actions=False, attacker_goal=config.AttackerGoal(own_atleast=6),
+                             defender_agent=config.ScanAndReimageCompromisedMachines(0.6, 2, 5),
+                             defender_constraint=config.DefenderConstraint(0.80), seed=1234, auto_reset=True, emit_terminal_obs=True)
+    _run_against_oracle(comp, cfg, 2048, 200, seed=11)
+
+
+def test_chain10_scan_tape_draws_vs_oracle():
+    comp = scenario.compile_scenario(scenarios.chain_environment(10))
+    cfg = config.make_config(_abi.MODE_CYBERBATTLE, maximum_node_count=12, maximum_total_credentials=12,
+                             throws_on_invalid_actions=False, defender_agent=config.ScanAndReimageCompromisedMachines(0.9, 3, 2),
+                             defender_constraint=config.DefenderConstraint(0.5), auto_reset=True, emit_terminal_obs=True)
+    _run_against_oracle(comp, cfg, 1000, 200, seed=13, tape_rng=np.random.default_rng(99))
+
+
+def test_toyctf_marlon_pair_vs_oracle():
+    """The bench workload: ToyCtf (12,10) MARLon attacker+defender pair step, dense masks."""
+    comp = scenario.compile_scenario(scenarios.toyctf_environment())
+    cfg = config.make_config(_abi.MODE_MARLON, maximum_node_count=12, maximum_total_credentials=10,
+                             maximum_discoverable_credentials_per_action=5, throws_on_invalid_actions=False,
+                             attacker_goal=config.AttackerGoal(own_atleast=6), defender_constraint=config.DefenderConstraint(0.60),
+                             losing_reward=-5000.0, defender_enabled=True, defender_max_timesteps=2000,
+                             defender_invalid_action_reward=-1, attacker_max_timesteps=2000, emit_terminal_obs=True)
+    _run_against_oracle(comp, cfg, 4099, 300, seed=17)  # 4099: a ragged last tile
+
+
+def test_chain100_factored_masks_vs_oracle():
+    """configs[3] shape: Chain-100 (102,102) attacker+defender, factored masks (dense would be 8.5 MB/env)."""
+    comp = scenario.compile_scenario(scenarios.chain_environment(100))
+    cfg = config.make_config(_abi.MODE_MARLON, maximum_node_count=102, maximum_total_credentials=102,
+                             throws_on_invalid_actions=False, defender_constraint=config.DefenderConstraint(0.60),
+                             losing_reward=-5000.0, defender_enabled=True, defender_max_timesteps=500,
+                             attacker_max_timesteps=500, mask_mode=_abi.MASK_FACTORED)
+    _run_against_oracle(comp, cfg, 1024, 200, seed=19)
+
+
+def test_chain100_dense_small_batch_vs_oracle():
+    comp = scenario.compile_scenario(scenarios.chain_environment(100))
+    cfg = config.make_config(_abi.MODE_CYBERBATTLE, maximum_node_count=102, maximum_total_credentials=102,
+                             throws_on_invalid_actions=False, auto_reset=True)
+    _run_against_oracle(comp, cfg, 3, 40, seed=23, check_every=4)
+
+
+def test_odd_bounds_take_the_generic_encoder_path():
+    """Bounds whose mask sizes are not multiples of 16 bytes (ragged vectors straddle envs)."""
+    comp = scenario.compile_scenario(scenarios.chain_environment(4))
+    cfg = config.make_config(_abi.MODE_CYBERBATTLE, maximum_node_count=7, maximum_total_credentials=5,
+                             throws_on_invalid_actions=False, auto_reset=True, emit_terminal_obs=True)
+    _run_against_oracle(comp, cfg, 77, 120, seed=29, check_every=2)
+
+
+def test_default_bounds_single_env():
+    """CyberBattleEnv defaults N=100, C=1000 (70 MB connect mask): one env, a few steps."""
+    comp = scenario.compile_scenario(scenarios.toyctf_environment())
+    cfg = config.make_config(_abi.MODE_CYBERBATTLE, throws_on_invalid_actions=False, auto_reset=False)
+    _run_against_oracle(comp, cfg, 1, 12, seed=31, check_every=3)
+
+
+def test_step_host_roundtrip():
+    """The HOST-buffer entry point (what bench.py's e2e leg times) returns the same rewards/flags as the device views."""
+    comp = scenario.compile_scenario(scenarios.toyctf_environment())
+    cfg = config.make_config(_abi.MODE_MARLON, maximum_node_count=12, maximum_total_credentials=10, throws_on_invalid_actions=False,
+                             attacker_goal=config.AttackerGoal(own_atleast=6), defender_constraint=config.DefenderConstraint(0.60),
+                             losing_reward=-5000.0, defender_enabled=True)
+    b = _batch(comp, cfg, 513)
+    b.reset()
+    for s in range(5):
+        att, dfn = b.sample_actions(seed=3)
+        out = b.step_host(att.cpu().numpy(), dfn.cpu().numpy())
+        for k in ("att_reward", "def_reward", "att_terminated", "att_truncated", "def_terminated", "def_truncated"):
+            assert np.array_equal(out[k], b.numpy(k)), k
+    b.close()

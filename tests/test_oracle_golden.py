@@ -61,3 +61,14 @@ def test_toyctf_commandcontrol_kat():
         assert r == want, (kind, a0, a1, a2, a3, r, want)
         total += r
     assert total == 389.0 == float(z["total"])
+
+
+def test_philox_known_answers():
+    """Philox4x32-10 known-answer vectors (Random123 kat_vectors): device stream == oracle stream is covered by the
+    ScanAndReimage test; here the oracle's generator is pinned to the published vectors."""
+    from oracle import philox4x32_10
+
+    assert philox4x32_10([0, 0, 0, 0], [0, 0]).tolist() == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    assert philox4x32_10([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2).tolist() == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    assert philox4x32_10([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0]).tolist() == \
+        [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
