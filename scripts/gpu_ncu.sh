@@ -1,0 +1,12 @@
+#!/bin/bash
+# ncu evidence for the step kernel (B200_PROFILING.md recipe): launch list, then one full capture of the top kernel.
+mkdir -p gpurun_out
+CMD="python bench.py --steps 5 --warmup 3 --no-cpu-baseline"
+$CMD > gpurun_out/plain.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
+echo "launch list rc=$?"
+$CMD > gpurun_out/plain2.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:cbx_step_kernel -s 16 -c 2 -f -o gpurun_out/prof $CMD > gpurun_out/ncu_full.log 2>&1
+echo "full capture rc=$?"
+tail -3 gpurun_out/ncu_full.log
+ls -la gpurun_out/
