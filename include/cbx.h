@@ -323,6 +323,14 @@ int cbx_batch_reset(cbx_batch* b, const uint8_t* mask_or_null, void* cuda_stream
 int cbx_batch_step(cbx_batch* b, const int32_t* attacker_actions, const int32_t* defender_actions,
                    const cbx_tape* tape_or_null, void* cuda_stream);
 
+/* The two halves of the MARLon pair step as separate calls, for callers that drive the two wrappers one after the
+ * other like the reference does (marl_algorithm.py:43-49): who = CBX_WHO_ATTACKER, CBX_WHO_DEFENDER or both.
+ * cbx_batch_reset_ex(.., CBX_WHO_ATTACKER) is AttackerEnvWrapper.reset(), (.., CBX_WHO_DEFENDER) DefenderEnvWrapper.reset(). */
+enum { CBX_WHO_ATTACKER = 1, CBX_WHO_DEFENDER = 2 };
+int cbx_batch_step_ex(cbx_batch* b, const int32_t* attacker_actions, const int32_t* defender_actions,
+                      const cbx_tape* tape_or_null, int who, void* cuda_stream);
+int cbx_batch_reset_ex(cbx_batch* b, const uint8_t* mask_or_null, int who, void* cuda_stream);
+
 /* Same step on HOST buffers: pinned staging + H2D of the actions, the step, D2H of rewards and done flags
  * (att_reward, def_reward, 4 flag arrays -> host_out, layout: float[n], float[n], uint8[4][n]); synchronises. */
 int cbx_batch_step_host(cbx_batch* b, const int32_t* host_attacker_actions, const int32_t* host_defender_actions,
@@ -346,6 +354,11 @@ int64_t cbx_batch_launch_count(const cbx_batch* b);
  * on the launch stream when timing is enabled. */
 int cbx_batch_enable_timing(cbx_batch* b, int enabled);
 int cbx_batch_step_kernel_ms(cbx_batch* b, double* mean_ms, int64_t* launches);
+
+/* Instrumentation: per-phase SM cycle counters of the step kernel, summed over CTAs (thread 0 of each CTA):
+ * [0] prologue [1] state-tile load [2] attacker logic [3] terminal observations [4] reset/defender logic + descriptors
+ * [5] observation/mask encode [6] state write-back.  enable!=0 switches counting on; out16 (may be NULL) receives and clears. */
+int cbx_batch_phase_cycles(cbx_batch* b, int enable, uint64_t* out16);
 
 /* sizeof(cbx_config) (0), sizeof(cbx_views) (1), sizeof(cbx_tape) (2): lets a binding check its struct mirrors. */
 size_t cbx_abi_sizeof(int which);

@@ -172,6 +172,14 @@ class Batch:
         _lib.check(self._L.cbx_batch_step_kernel_ms(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    PHASES = ["prologue", "state_load", "attacker_logic", "terminal_obs", "defender_logic_desc", "encode", "state_store"]
+
+    def phase_cycles(self, enable: bool = True):
+        """Per-phase SM cycles of the step kernel since the last call (summed over CTAs); switches counting on/off."""
+        out = (C.c_uint64 * 16)()
+        _lib.check(self._L.cbx_batch_phase_cycles(self._h, int(enable), out))
+        return {k: int(out[i]) for i, k in enumerate(self.PHASES)}
+
     @property
     def launch_count(self) -> int:
         return int(self._L.cbx_batch_launch_count(self._h))

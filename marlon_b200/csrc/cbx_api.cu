@@ -14,7 +14,7 @@
 #include "cbx_layout.h"
 
 extern "C" {
-cudaError_t cbx_launch_step(const cbx_params* p, int reset_only, int grid, int smem_bytes, int use_tma, cudaStream_t stream);
+cudaError_t cbx_launch_step(const cbx_params* p, int op, int grid, int smem_bytes, int use_tma, cudaStream_t stream);
 cudaError_t cbx_launch_sample(const cbx_params* p, int32_t* att, int32_t* def, uint64_t seed, uint32_t step, cudaStream_t stream);
 cudaError_t cbx_kernel_attrs(int smem_bytes, int use_tma, int* blocks_per_sm);
 }
@@ -266,6 +266,20 @@ int cbx_batch_create(const cbx_scenario* s, int64_t n_envs, const cbx_config* cf
   K.d_rowc = make_fastdiv(L.N * L.P * L.C); K.d_C = make_fastdiv(L.C); K.d_n = make_fastdiv(L.n);
   K.d_6n = make_fastdiv(6 * L.n); K.d_svc = make_fastdiv(L.nservices > 0 ? L.nservices : 1);
   K.desc_words = 8 + L.OW + L.Wn;
+  auto gcd16 = [](int x) { int g = 16; while (x % g) g >>= 1; return g; };
+  {
+    const int row_r = L.N * L.R, row_c = L.N * L.P * L.C;
+    K.tmpl_unit_r = gcd16(row_r);
+    K.tmpl_unit_c = gcd16(row_c);
+    const char* slow = getenv("CBX_GENERIC_ENCODER");
+    bool ok = !(slow && slow[0] == '1');
+    if (cfg->mask_mode == CBX_MASK_DENSE) {
+      // 4-byte store granules at least, rows short enough for CBX_MAXG (4) granules per lane, word-sized local mask
+      ok = ok && K.tmpl_unit_r >= 4 && K.tmpl_unit_c >= 4 && row_r / K.tmpl_unit_r <= 128 && row_c / K.tmpl_unit_c <= 128 &&
+           L.sz_local % 4 == 0;
+    }
+    K.warp_env = ok ? 1 : 0;
+  }
   // shared-memory plan
   cbx_smem_plan& pl = b->p.plan;
   int o = 0;
@@ -368,7 +382,7 @@ int cbx_batch_create(const cbx_scenario* s, int64_t n_envs, const cbx_config* cf
   // bring every env to its initial state (the reference resets before the first step as well)
   {
     b->p.reset_mask = nullptr;
-    cudaError_t e = cbx_launch_step(&b->p, 1, b->grid, b->smem_bytes, b->use_tma, 0);
+    cudaError_t e = cbx_launch_step(&b->p, CBX_OP_RESET | CBX_OP_ATTACKER | CBX_OP_DEFENDER, b->grid, b->smem_bytes, b->use_tma, 0);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { int rc2 = fail(CBX_ERR_CUDA, "initial reset: %s", cudaGetErrorString(e)); cbx_batch_destroy(b); return rc2; }
     b->launches++;
@@ -391,9 +405,9 @@ int cbx_batch_destroy(cbx_batch* b) {
   return CBX_OK;
 }
 
-static int timed_launch(cbx_batch* b, int reset_only, cudaStream_t st) {
+static int timed_launch(cbx_batch* b, int op, cudaStream_t st) {
   cudaEvent_t e0 = nullptr, e1 = nullptr;
-  const bool t = b->timing && !reset_only;
+  const bool t = b->timing && !(op & CBX_OP_RESET);
   if (t) {
     if (b->ev_used + 2 > b->ev.size()) {
       for (int k = 0; k < 2; ++k) { cudaEvent_t e; CUDA_TRY(cudaEventCreate(&e)); b->ev.push_back(e); }
@@ -402,31 +416,46 @@ static int timed_launch(cbx_batch* b, int reset_only, cudaStream_t st) {
     b->ev_used += 2;
     CUDA_TRY(cudaEventRecord(e0, st));
   }
-  CUDA_TRY(cbx_launch_step(&b->p, reset_only, b->grid, b->smem_bytes, b->use_tma, st));
+  CUDA_TRY(cbx_launch_step(&b->p, op, b->grid, b->smem_bytes, b->use_tma, st));
   if (t) CUDA_TRY(cudaEventRecord(e1, st));
   b->launches++;
   return CBX_OK;
 }
 
-int cbx_batch_reset(cbx_batch* b, const uint8_t* mask_or_null, void* cuda_stream) {
+int cbx_batch_reset_ex(cbx_batch* b, const uint8_t* mask_or_null, int who, void* cuda_stream) {
   if (!b) return fail(CBX_ERR_INVALID, "null batch");
+  if (!(who & (CBX_WHO_ATTACKER | CBX_WHO_DEFENDER))) return fail(CBX_ERR_INVALID, "reset: nobody selected");
   CUDA_TRY(cudaSetDevice(b->device));
   b->p.reset_mask = mask_or_null;
   b->p.att_actions = nullptr; b->p.def_actions = nullptr; b->p.scan_u = nullptr; b->p.detect_u = nullptr;
-  return timed_launch(b, 1, (cudaStream_t)cuda_stream);
+  int op = CBX_OP_RESET | ((who & CBX_WHO_ATTACKER) ? CBX_OP_ATTACKER : 0) | ((who & CBX_WHO_DEFENDER) ? CBX_OP_DEFENDER : 0);
+  return timed_launch(b, op, (cudaStream_t)cuda_stream);
+}
+
+int cbx_batch_reset(cbx_batch* b, const uint8_t* mask_or_null, void* cuda_stream) {
+  return cbx_batch_reset_ex(b, mask_or_null, CBX_WHO_ATTACKER | CBX_WHO_DEFENDER, cuda_stream);
 }
 
 int cbx_batch_step(cbx_batch* b, const int32_t* att, const int32_t* def, const cbx_tape* tape, void* cuda_stream) {
-  if (!b || !att) return fail(CBX_ERR_INVALID, "null batch or attacker actions");
+  return cbx_batch_step_ex(b, att, def, tape, CBX_WHO_ATTACKER | CBX_WHO_DEFENDER, cuda_stream);
+}
+
+int cbx_batch_step_ex(cbx_batch* b, const int32_t* att, const int32_t* def, const cbx_tape* tape, int who, void* cuda_stream) {
+  if (!b) return fail(CBX_ERR_INVALID, "null batch");
   const cbx_config& c = b->p.cfg;
-  if (c.mode == CBX_MODE_MARLON && c.def_enabled && !def) return fail(CBX_ERR_INVALID, "defender actions required (def_enabled)");
+  if (c.mode != CBX_MODE_MARLON || !c.def_enabled) who &= ~CBX_WHO_DEFENDER;
+  if (c.mode != CBX_MODE_MARLON) who |= CBX_WHO_ATTACKER;
+  if (!(who & (CBX_WHO_ATTACKER | CBX_WHO_DEFENDER))) return fail(CBX_ERR_INVALID, "step: nobody selected");
+  if ((who & CBX_WHO_ATTACKER) && !att) return fail(CBX_ERR_INVALID, "attacker actions required");
+  if ((who & CBX_WHO_DEFENDER) && !def) return fail(CBX_ERR_INVALID, "defender actions required (def_enabled)");
   CUDA_TRY(cudaSetDevice(b->device));
   b->p.reset_mask = nullptr;
   b->p.att_actions = att; b->p.def_actions = def;
   b->p.scan_u = tape ? tape->scan_u : nullptr;
   b->p.detect_u = tape ? tape->detect_u : nullptr;
   if (tape && (!tape->scan_u || !tape->detect_u)) return fail(CBX_ERR_INVALID, "tape needs both scan_u and detect_u");
-  return timed_launch(b, 0, (cudaStream_t)cuda_stream);
+  int op = ((who & CBX_WHO_ATTACKER) ? CBX_OP_ATTACKER : 0) | ((who & CBX_WHO_DEFENDER) ? CBX_OP_DEFENDER : 0);
+  return timed_launch(b, op, (cudaStream_t)cuda_stream);
 }
 
 int cbx_batch_step_host(cbx_batch* b, const int32_t* h_att, const int32_t* h_def, void* host_out, size_t host_out_bytes, void* cuda_stream) {
@@ -559,6 +588,25 @@ int cbx_batch_export_state(cbx_batch* b, int64_t begin, int64_t end, int32_t* ou
 }
 
 int64_t cbx_batch_launch_count(const cbx_batch* b) { return b ? b->launches : -1; }
+
+int cbx_batch_phase_cycles(cbx_batch* b, int enable, uint64_t* out16) {
+  if (!b) return fail(CBX_ERR_INVALID, "null batch");
+  CUDA_TRY(cudaSetDevice(b->device));
+  if (enable && !b->p.prof) {
+    void* pp = nullptr;
+    CUDA_TRY(cudaMalloc(&pp, 16 * sizeof(unsigned long long)));
+    b->allocs.push_back(pp);
+    CUDA_TRY(cudaMemset(pp, 0, 16 * sizeof(unsigned long long)));
+    b->p.prof = (unsigned long long*)pp;
+  }
+  if (out16 && b->p.prof) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(out16, b->p.prof, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemset(b->p.prof, 0, 16 * sizeof(unsigned long long)));
+  }
+  if (!enable) b->p.prof = nullptr;
+  return CBX_OK;
+}
 
 int cbx_batch_enable_timing(cbx_batch* b, int enabled) {
   if (!b) return fail(CBX_ERR_INVALID, "null batch");

@@ -58,7 +58,19 @@ __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.b
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__device__ __forceinline__ void st_stream(void* p, uint4 v) { __stcs(reinterpret_cast<uint4*>(p), v); }
+// Output stores.  CBX_STREAMING_STORES=1 selects st.global.cs (evict-first); default is a plain write-back store.
+#ifndef CBX_STREAMING_STORES
+#define CBX_STREAMING_STORES 0
+#endif
+template <class T>
+__device__ __forceinline__ void st_out(T* p, T v) {
+#if CBX_STREAMING_STORES
+  __stcs(p, v);
+#else
+  *p = v;
+#endif
+}
+__device__ __forceinline__ void st_stream(void* p, uint4 v) { st_out(reinterpret_cast<uint4*>(p), v); }
 
 // ---- encoder -----------------------------------------------------------------------------------------------------------
 struct Target {  // output pointers already offset to the tile's first env
@@ -204,10 +216,168 @@ __device__ __forceinline__ void write_rowmask(int8_t* dst, int bpe, FastDiv denv
   }
 }
 
+
+// ---- warp-per-env encoder (fast path) ------------------------------------------------------------------------------------
+// One warp writes one env's whole observation: the env index is warp-uniform, so the per-env quantities (counts, owned
+// bits) live in registers and no lane does index arithmetic across envs.  Every row of the remote / connect masks is
+// either zero or the env's one template row: each lane computes its (at most CBX_MAXG) granules of that
+// template once per env, in registers, and then only issues stores, one row after the other.
+#define CBX_MAXG 4
+
+template <int U> struct Gran;
+template <> struct Gran<16> {
+  typedef uint4 T;
+  static __device__ __forceinline__ T zero() { return make_uint4(0, 0, 0, 0); }
+  static __device__ __forceinline__ T expand(uint32_t m, const uint2* lut) {
+    uint2 lo = lut[m & 0xFFu], hi = lut[(m >> 8) & 0xFFu];
+    return make_uint4(lo.x, lo.y, hi.x, hi.y);
+  }
+};
+template <> struct Gran<8> {
+  typedef uint2 T;
+  static __device__ __forceinline__ T zero() { return make_uint2(0, 0); }
+  static __device__ __forceinline__ T expand(uint32_t m, const uint2* lut) { return lut[m & 0xFFu]; }
+};
+template <> struct Gran<4> {
+  typedef uint32_t T;
+  static __device__ __forceinline__ T zero() { return 0u; }
+  static __device__ __forceinline__ T expand(uint32_t m, const uint2*) { return ((m & 0xFu) * 0x00204081u) & 0x01010101u; }
+};
+
+template <int U, bool CONNECT>
+__device__ __noinline__ void warp_rowmask(int8_t* envdst, int row_len, int N, int C, cbx_fastdiv dCv, const uint32_t* desc_e,
+                                          const uint2* lut, int lane) {
+  typedef typename Gran<U>::T G;
+  const FastDiv dC(dCv);
+  const int gpr = row_len / U;
+  const int lim = (int)(CONNECT ? desc_e[D_LIMC] : desc_e[D_LIMR]);
+  const int nc = (int)desc_e[D_NC];
+  const uint64_t base = ((uint64_t)desc_e[D_BHI] << 32) | desc_e[D_BLO];
+  G tm[CBX_MAXG];
+  bool valid[CBX_MAXG];
+#pragma unroll
+  for (int k = 0; k < CBX_MAXG; ++k) {
+    const int g = lane + 32 * k;
+    valid[k] = g < gpr;
+    const int w = g * U;
+    uint32_t m = lowmask(min(max(lim - w, 0), U));
+    if (CONNECT) {
+      const int ph = (int)((uint32_t)w - dC.div((uint32_t)w) * C);
+      uint32_t pm;
+      if (C <= 48) pm = (uint32_t)(base >> ph) & 0xFFFFu;
+      else pm = lowmask(min(max(nc - ph, 0), 16)) | (lowmask(min(max(C - ph + nc, 0), 16)) & ~lowmask(min(max(C - ph, 0), 16)));
+      m &= pm;
+    }
+    tm[k] = Gran<U>::expand(m, lut);
+  }
+  G* p = reinterpret_cast<G*>(envdst) + lane;
+  uint32_t ow = desc_e[D_OWNED];
+  for (int s = 0; s < N; ++s, p += gpr) {
+    if (s && (s & 31) == 0) ow = desc_e[D_OWNED + (s >> 5)];
+    if ((ow >> (s & 31)) & 1u) {  // warp-uniform
+#pragma unroll
+      for (int k = 0; k < CBX_MAXG; ++k)
+        if (valid[k]) st_out(p + 32 * k, tm[k]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < CBX_MAXG; ++k)
+        if (valid[k]) st_out(p + 32 * k, Gran<U>::zero());
+    }
+  }
+}
+
+template <bool CONNECT>
+__device__ __forceinline__ void warp_rowmask_dispatch(int unit, int8_t* envdst, int row_len, int N, int C, cbx_fastdiv dC,
+                                                      const Tile& t, int e, int lane) {
+  const uint32_t* de = t.desc + e * t.DW;
+  if (unit == 16) warp_rowmask<16, CONNECT>(envdst, row_len, N, C, dC, de, t.lut, lane);
+  else if (unit == 8) warp_rowmask<8, CONNECT>(envdst, row_len, N, C, dC, de, t.lut, lane);
+  else warp_rowmask<4, CONNECT>(envdst, row_len, N, C, dC, de, t.lut, lane);
+}
+
+__device__ void encode_attacker_by_warp(const Tile& t, const Target& o, int n_valid, uint32_t enc_mask) {
+  const cbx_layout* L = t.L;
+  const cbx_enc_consts& K = *t.K;
+  const int lane = threadIdx.x & 31;
+  for (int e = threadIdx.x >> 5; e < n_valid; e += CBX_THREADS / 32) {
+    if (!((enc_mask >> e) & 1u)) continue;
+    const uint32_t nd = t.d(e, D_ND), nc = t.d(e, D_NC);
+    const bool blank = t.d(e, D_KIND) == OBS_BLANK;
+    if (lane < 8) st_out(o.scalars + e * 8 + lane, (int32_t)t.g(e, STG_SCALARS + lane));
+    for (int w = lane; w < 4 * L->LEAK; w += 32) st_out(o.leaked + e * 4 * L->LEAK + w, (int32_t)t.g(e, L->g_leaked + w));
+    for (int w = lane; w < 2 * L->C; w += 32) {
+      const int c = w >> 1;
+      uint32_t val = 0;
+      if (!blank && c < (int)nc) {
+        uint32_t tr = (t.w(e, L->o_cache + (c >> 1)) >> ((c & 1) * 16)) & 0xFFFFu;
+        const uint32_t* rec = t.tb + t.tb[CBX_H_OFF_TRIPLE] + 3 * tr;
+        val = (w & 1) ? rec[1] : t.byte(e, L->o_disc_idx, (int)rec[0]);
+      }
+      st_out(o.cachem + e * 2 * L->C + w, (int32_t)val);
+    }
+    const int npw = L->N * L->nprops;
+    for (int w = lane; w < npw; w += 32) {
+      uint32_t val = 2u;
+      if (!blank) {
+        uint32_t k = FastDiv(K.d_nprops).div((uint32_t)w), pi = w - k * L->nprops;
+        val = 0u;
+        if (k < nd) {
+          uint32_t node = t.byte(e, L->o_disc_order, (int)k);
+          val = (t.w(e, L->o_props + node * L->PW + (pi >> 5)) >> (pi & 31)) & 1u;
+        }
+      }
+      st_out(o.props + e * npw + w, (int32_t)val);
+    }
+    for (int w = lane; w < L->N; w += 32) {
+      uint32_t val = 0;
+      if (!blank && w < (int)nd) {
+        uint32_t node = t.byte(e, L->o_disc_order, w);
+        val = (t.g(e, L->g_priv + (node >> 4)) >> ((node & 15) * 2)) & 3u;
+      }
+      st_out(o.priv + e * L->N + w, (int32_t)val);
+    }
+    if (o.local) {
+      int8_t* dst = o.local + (size_t)e * L->sz_local;
+      for (int q = lane; q < L->sz_local / 4; q += 32) {  // fast path guarantees sz_local % 4 == 0
+        uint32_t word = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          uint32_t i = q * 4 + b, s = FastDiv(K.d_L).div(i), v = i - s * L->L;
+          if (t.owned(e, (int)s)) {
+            uint32_t node = t.byte(e, L->o_disc_order, (int)s);
+            word |= (t.tb[t.tb[CBX_H_OFF_VULN] + (node * (L->L + L->R) + v) * CBX_VULN_WORDS] & 1u) << (8 * b);
+          }
+        }
+        st_out(reinterpret_cast<uint32_t*>(dst) + q, word);
+      }
+      warp_rowmask_dispatch<false>(K.tmpl_unit_r, o.remote + (size_t)e * L->sz_remote, L->N * L->R, L->N, 1, cbx_fastdiv{0u, 0u}, t, e, lane);
+      warp_rowmask_dispatch<true>(K.tmpl_unit_c, o.connect + (size_t)e * L->sz_connect, L->N * L->P * L->C, L->N, L->C, K.d_C, t, e, lane);
+    }
+  }
+}
+
+__device__ void encode_defender_by_warp(const Tile& t, const Target& o, int n_valid, uint32_t enc_mask, bool static_too) {
+  const cbx_layout* L = t.L;
+  const int lane = threadIdx.x & 31;
+  for (int e = threadIdx.x >> 5; e < n_valid; e += CBX_THREADS / 32) {
+    if (!((enc_mask >> e) & 1u)) continue;
+    for (int i = lane; i < L->n; i += 32) o.infected[(size_t)e * L->n + i] = (int8_t)((t.d(e, D_OWNED + L->OW + (i >> 5)) >> (i & 31)) & 1u);
+    if (!static_too) continue;
+    for (int i = lane; i < 6 * L->n; i += 32) {
+      const int node = i / 6, r = i - node * 6;
+      const uint32_t dob = t.tb[t.tb[CBX_H_OFF_NODE] + node * CBX_NODE_WORDS + CBX_N_DEFOBS];
+      o.fw_in[(size_t)e * 6 * L->n + i] = (int8_t)((dob >> r) & 1u);
+      o.fw_out[(size_t)e * 6 * L->n + i] = (int8_t)((dob >> (8 + r)) & 1u);
+    }
+    for (int i = lane; i < L->nservices; i += 32) o.services[(size_t)e * L->nservices + i] = 1;
+  }
+}
+
 // Encode the attacker observation of the envs selected by enc_mask (bit e = env e of the tile).
 __device__ void encode_attacker(const Tile& t, const Target& o, int n_valid, uint32_t enc_mask) {
   const cbx_layout* L = t.L;
   const cbx_enc_consts& K = *t.K;
+  if (K.warp_env) { encode_attacker_by_warp(t, o, n_valid, enc_mask); return; }
   write_i32(o.scalars, 8, FastDiv(0u, 3u), n_valid, enc_mask, [&](int e, int wi) { return t.g(e, STG_SCALARS + wi); });
   write_i32(o.leaked, 4 * L->LEAK, K.d_leaked, n_valid, enc_mask, [&](int e, int wi) { return t.g(e, L->g_leaked + wi); });
   write_i32(o.cachem, 2 * L->C, K.d_cachem, n_valid, enc_mask, [&](int e, int wi) -> uint32_t {
@@ -242,6 +412,7 @@ __device__ void encode_attacker(const Tile& t, const Target& o, int n_valid, uin
 __device__ void encode_defender(const Tile& t, const Target& o, int n_valid, uint32_t enc_mask, bool static_too) {
   const cbx_layout* L = t.L;
   const cbx_enc_consts& K = *t.K;
+  if (K.warp_env) { encode_defender_by_warp(t, o, n_valid, enc_mask, static_too); return; }
   write_i8(o.infected, L->n, K.d_n, n_valid, enc_mask,
            [&](int e, int i) -> uint32_t { return (t.d(e, D_OWNED + L->OW + (i >> 5)) >> (i & 31)) & 1u; });
   if (!static_too) return;
@@ -473,7 +644,7 @@ __device__ void cyber_only_step(const Ctx& c, const cbx_params& p, const int32_t
 
 // ---- the kernel ----------------------------------------------------------------------------------------------------------
 template <bool USE_TMA>
-__global__ void __launch_bounds__(CBX_THREADS) cbx_step_kernel(const __grid_constant__ cbx_params p, const int reset_only) {
+__global__ void __launch_bounds__(CBX_THREADS, CBX_MIN_CTAS) cbx_step_kernel(const __grid_constant__ cbx_params p, const int op) {
   extern __shared__ __align__(128) uint32_t smem[];
   const cbx_layout& L = p.lay;
   const cbx_config& cfg = p.cfg;
@@ -486,6 +657,7 @@ __global__ void __launch_bounds__(CBX_THREADS) cbx_step_kernel(const __grid_cons
   __shared__ int s_tile;
   __shared__ uint32_t s_masks[4];
   const int tid = threadIdx.x;
+  const bool reset_only = op & CBX_OP_RESET, who_att = op & CBX_OP_ATTACKER, who_def = op & CBX_OP_DEFENDER;
   const int DW = p.enc.desc_words;
   const uint32_t* s_init = s_tb + p.table_words;  // initial per-env state follows the scenario blob
   const uint32_t table_bytes = (uint32_t)(p.table_words + ((L.S + 3) & ~3)) * 4u;
@@ -515,6 +687,14 @@ __global__ void __launch_bounds__(CBX_THREADS) cbx_step_kernel(const __grid_cons
   Acc acc;
 #pragma unroll
   for (int k = 0; k < CBX_STAT_COUNT; ++k) acc.v[k] = 0.0;
+  long long prof_t = p.prof ? clock64() : 0;
+#define CBX_PROF(slot)                                                                         \
+  if (p.prof && tid == 0) {                                                                    \
+    long long _now = clock64();                                                                \
+    atomicAdd(p.prof + (slot), (unsigned long long)(_now - prof_t));                           \
+    prof_t = _now;                                                                             \
+  }
+  CBX_PROF(0)  // prologue: LUT + tables
   uint32_t st_phase = 0;
   int slice_of_kind[3] = {p.slice_of_kind[0], p.slice_of_kind[1], p.slice_of_kind[2]};
 
@@ -536,6 +716,7 @@ __global__ void __launch_bounds__(CBX_THREADS) cbx_step_kernel(const __grid_cons
       __syncthreads();
     }
 
+    CBX_PROF(1)  // state tile load
     const bool active = tid < n_valid;
     Ctx c;
     c.st = s_st + tid; c.sg = s_sg + tid; c.tb = s_tb; c.L = &L; c.cfg = &cfg; c.env = e0 + tid;
@@ -546,23 +727,27 @@ __global__ void __launch_bounds__(CBX_THREADS) cbx_step_kernel(const __grid_cons
       if (active) {
         c.g(STG_ATT_DONE) = 0; c.g(STG_DEF_DONE) = 0;
         if (reset_only) {
+          c.g(STG_OBS_KIND) = OBS_KEEP;
           if (!p.reset_mask || p.reset_mask[c.env]) {
-            if (cfg.mode == CBX_MODE_MARLON) {
-              c.attacker_reset(s_init);
-              if (cfg.def_enabled) c.defender_reset(s_init);
+            if (cfg.mode == CBX_MODE_MARLON) {  // attacker.reset() then defender.reset(), either or both
+              if (who_att) c.attacker_reset(s_init);
+              if (who_def && cfg.def_enabled) c.defender_reset(s_init);
             } else {
               c.cyber_reset(s_init);
               c.setf32(L.o_att_return, 0.f);
             }
-            c.stage_reset_obs();
-            p.v.att_reward[c.env] = 0.f; p.v.att_terminated[c.env] = 0; p.v.att_truncated[c.env] = 0;
-            p.v.def_reward[c.env] = 0.f; p.v.def_terminated[c.env] = 0; p.v.def_truncated[c.env] = 0;
+            if (who_att || cfg.mode != CBX_MODE_MARLON) {
+              c.stage_reset_obs();
+              p.v.att_reward[c.env] = 0.f; p.v.att_terminated[c.env] = 0; p.v.att_truncated[c.env] = 0;
+              int4* ip = reinterpret_cast<int4*>(p.v.att_info + c.env * 8);
+              ip[0] = make_int4(0, 0, 0, 0); ip[1] = make_int4(0, 0, 0, 0);
+            }
+            if (who_def) { p.v.def_reward[c.env] = 0.f; p.v.def_terminated[c.env] = 0; p.v.def_truncated[c.env] = 0; }
             p.v.network_availability[c.env] = 1.0;
-            int4* ip = reinterpret_cast<int4*>(p.v.att_info + c.env * 8);
-            ip[0] = make_int4(0, 0, 0, 0); ip[1] = make_int4(0, 0, 0, 0);
-          } else c.g(STG_OBS_KIND) = OBS_KEEP;
+          }
         } else if (cfg.mode == CBX_MODE_MARLON) {
-          attacker_wrapper_step(c, p, p.att_actions + c.env * 10, slice_of_kind, acc);
+          if (who_att) attacker_wrapper_step(c, p, p.att_actions + c.env * 10, slice_of_kind, acc);
+          else c.g(STG_OBS_KIND) = OBS_KEEP;
         } else {
           cyber_only_step(c, p, p.att_actions + c.env * 5, acc);
         }
@@ -574,6 +759,7 @@ __global__ void __launch_bounds__(CBX_THREADS) cbx_step_kernel(const __grid_cons
       if (tid == 0) { s_masks[0] = done_mask; s_masks[1] = keep_mask; }
     }
     __syncthreads();
+    CBX_PROF(2)  // logic phase 1 (attacker move)
     const uint32_t att_done_mask = s_masks[0];
     Tile t;
     t.L = &L; t.tb = s_tb; t.st = s_st; t.sg = s_sg; t.desc = s_desc; t.lut = s_lut; t.K = &p.enc; t.DW = DW;
@@ -600,6 +786,7 @@ __global__ void __launch_bounds__(CBX_THREADS) cbx_step_kernel(const __grid_cons
       __syncthreads();
     }
 
+    CBX_PROF(3)  // terminal observations
     // ---- (2) game logic, phase 2: attacker auto-reset, defender move ----
     if (tid < CBX_TILE) {
       uint32_t def_done = 0, keep = 1;
@@ -610,7 +797,7 @@ __global__ void __launch_bounds__(CBX_THREADS) cbx_step_kernel(const __grid_cons
             else { c.cyber_reset(s_init); c.setf32(L.o_att_return, 0.f); }
             c.stage_reset_obs();
           }
-          if (cfg.mode == CBX_MODE_MARLON && cfg.def_enabled) defender_wrapper_step(c, p, p.def_actions + c.env * 12, acc);
+          if (cfg.mode == CBX_MODE_MARLON && cfg.def_enabled && who_def) defender_wrapper_step(c, p, p.def_actions + c.env * 12, acc);
         }
         def_done = c.g(STG_DEF_DONE) && cfg.auto_reset;
         keep = c.g(STG_OBS_KIND) == OBS_KEEP;
@@ -626,6 +813,7 @@ __global__ void __launch_bounds__(CBX_THREADS) cbx_step_kernel(const __grid_cons
       if (tid == 0) { s_masks[2] = dmask; s_masks[3] = kmask; }
     }
     __syncthreads();
+    CBX_PROF(4)  // logic phase 2 (auto-reset, defender move, descriptors)
     const uint32_t def_done_mask = s_masks[2];
     const uint32_t enc_mask = ~s_masks[3];
 
@@ -633,7 +821,7 @@ __global__ void __launch_bounds__(CBX_THREADS) cbx_step_kernel(const __grid_cons
     {
       Target tm = make_target(p.v, L, e0, false);
       encode_attacker(t, tm, n_valid, enc_mask);
-      if (cfg.mode == CBX_MODE_MARLON && cfg.def_enabled) {
+      if (cfg.mode == CBX_MODE_MARLON && cfg.def_enabled && who_def) {
         encode_defender(t, tm, n_valid, 0xFFFFFFFFu, true);
         if (def_done_mask && cfg.emit_terminal_obs) {
           // terminal defender observation = infected nodes seen by the step that ended the episode
@@ -648,6 +836,7 @@ __global__ void __launch_bounds__(CBX_THREADS) cbx_step_kernel(const __grid_cons
     }
     __syncthreads();
 
+    CBX_PROF(5)  // encode
     // ---- (4) deferred defender auto-reset (DummyVecEnv resets after the step; the attacker's observation of this
     //          step was taken before it), then stream the state tile back ----
     if (tid < CBX_TILE && active && ((def_done_mask >> tid) & 1u)) c.defender_reset(s_init);
@@ -666,6 +855,7 @@ __global__ void __launch_bounds__(CBX_THREADS) cbx_step_kernel(const __grid_cons
         p.state[(int64_t)(k / CBX_TILE) * p.n_pad + e0 + (k % CBX_TILE)] = s_st[k];
       __syncthreads();
     }
+    CBX_PROF(6)  // state write-back
   }
   if (USE_TMA && tid < 32) tma_store_wait_all();
 
@@ -758,9 +948,9 @@ __global__ void cbx_sample_kernel(const __grid_constant__ cbx_params p, int32_t*
 
 // ---- launch helpers used by cbx_api.cu ------------------------------------------------------------------------------------
 extern "C" {
-cudaError_t cbx_launch_step(const cbx_params* p, int reset_only, int grid, int smem_bytes, int use_tma, cudaStream_t stream) {
-  if (use_tma) cbx::cbx_step_kernel<true><<<grid, CBX_THREADS, smem_bytes, stream>>>(*p, reset_only);
-  else cbx::cbx_step_kernel<false><<<grid, CBX_THREADS, smem_bytes, stream>>>(*p, reset_only);
+cudaError_t cbx_launch_step(const cbx_params* p, int op, int grid, int smem_bytes, int use_tma, cudaStream_t stream) {
+  if (use_tma) cbx::cbx_step_kernel<true><<<grid, CBX_THREADS, smem_bytes, stream>>>(*p, op);
+  else cbx::cbx_step_kernel<false><<<grid, CBX_THREADS, smem_bytes, stream>>>(*p, op);
   return cudaGetLastError();
 }
 cudaError_t cbx_launch_sample(const cbx_params* p, int32_t* att, int32_t* def, uint64_t seed, uint32_t step, cudaStream_t stream) {

@@ -19,6 +19,13 @@
 #define CBX_TILE 32          // envs per tile (= one warp of game-logic threads)
 #define CBX_THREADS 128      // threads per CTA
 #define CBX_MAX_LEAK 64
+#ifndef CBX_MIN_CTAS
+#define CBX_MIN_CTAS 8       // resident CTAs per SM the step kernel is compiled for (caps registers at 64)
+#endif
+// kernel op bits
+#define CBX_OP_RESET 1
+#define CBX_OP_ATTACKER 2
+#define CBX_OP_DEFENDER 4
 
 struct cbx_layout {
   // dimensions
@@ -72,6 +79,10 @@ struct cbx_enc_consts {  // divisors of the encoder, fixed per batch
   cbx_fastdiv d_leaked, d_cachem, d_props, d_priv, d_nprops, d_L, d_local, d_remote, d_connect, d_rowr, d_rowc, d_C, d_n,
       d_6n, d_svc;
   int desc_words;
+  // warp-per-env fast path: every row of an env's remote / connect mask is either all zero or one and the same byte
+  // string; a warp keeps that string in registers and stores it row by row
+  int warp_env;                      // 1: fast path usable for this batch's dimensions
+  int tmpl_unit_r, tmpl_unit_c;      // store granule in bytes: gcd(row length, 16)
 };
 
 struct cbx_smem_plan {  // shared-memory carve-up in 32-bit words
@@ -97,6 +108,7 @@ struct cbx_params {
   const uint8_t* reset_mask;  // reset kernel only
   cbx_views v;
   int* tile_counter;      // dynamic tile scheduler
+  unsigned long long* prof;  // optional: 16 cycle counters accumulated per phase by thread 0 of every CTA (NULL = off)
 };
 
 #endif  // CBX_LAYOUT_H_

@@ -685,11 +685,17 @@ static int defender_action_valid(const orc_batch* b, const oenv_t* e, const int3
   }
 }
 
+static void defender_half_step(orc_batch* b, int64_t i, const int32_t* da);
+
 static void marlon_pair_step(orc_batch* b, int64_t i, const int32_t* aa, const int32_t* da, const double* scan_u,
-                             const double* detect_u) {
+                             const double* detect_u, int who) {
   oenv_t* e = &b->envs[i];
   const cbx_config* c = &b->cfg;
   obs_t o = obs_main(b, i);
+  if (!(who & CBX_WHO_ATTACKER)) {
+    if (c->def_enabled && (who & CBX_WHO_DEFENDER)) defender_half_step(b, i, da);
+    return;
+  }
   int32_t* info = b->v.att_info + i * 8;
   memset(info, 0, 8 * sizeof(int32_t));
   /* ---------------- AttackerEnvWrapper.step, ATT:255-398 ---------------- */
@@ -754,8 +760,14 @@ static void marlon_pair_step(orc_batch* b, int64_t i, const int32_t* aa, const i
       attacker_reset(b, e, &o);
     }
   }
-  if (!c->def_enabled) return;
-  /* ---------------- DefenderEnvWrapper.step, DWR:197-327 ---------------- */
+  if (!c->def_enabled || !(who & CBX_WHO_DEFENDER)) return;
+  defender_half_step(b, i, da);
+}
+
+/* ---------------- DefenderEnvWrapper.step, DWR:197-327 ---------------- */
+static void defender_half_step(orc_batch* b, int64_t i, const int32_t* da) {
+  oenv_t* e = &b->envs[i];
+  const cbx_config* c = &b->cfg;
   double dreward = 0.0;
   int dterm = 0, dtrunc = 0;
   int empty = da[0] < 0;
@@ -939,31 +951,45 @@ void orc_destroy(orc_batch* b) {
 
 void orc_views(orc_batch* b, cbx_views* out) { *out = b->v; }
 
-void orc_reset(orc_batch* b, const uint8_t* mask) {
+void orc_reset_ex(orc_batch* b, const uint8_t* mask, int who) {
   for (int64_t i = 0; i < b->n; ++i) {
     if (mask && !mask[i]) continue;
     oenv_t* e = &b->envs[i];
     obs_t o = obs_main(b, i);
+    int att = 1;
     if (b->cfg.mode == CBX_MODE_MARLON) {
-      attacker_reset(b, e, &o);
-      if (b->cfg.def_enabled) defender_reset(b, e, i);
+      att = who & CBX_WHO_ATTACKER;
+      if (att) attacker_reset(b, e, &o);
+      if (b->cfg.def_enabled && (who & CBX_WHO_DEFENDER)) {
+        defender_reset(b, e, i);
+        b->v.def_reward[i] = 0; b->v.def_terminated[i] = b->v.def_truncated[i] = 0;
+      }
     } else {
       cyber_reset(b, e, &o);
       e->att_return = 0.0;
     }
-    b->v.att_reward[i] = 0; b->v.att_terminated[i] = b->v.att_truncated[i] = 0;
-    b->v.def_reward[i] = 0; b->v.def_terminated[i] = b->v.def_truncated[i] = 0;
+    if (att) {
+      b->v.att_reward[i] = 0; b->v.att_terminated[i] = b->v.att_truncated[i] = 0;
+      memset(b->v.att_info + i * 8, 0, 32);
+    }
+    if (b->cfg.mode != CBX_MODE_MARLON || (who & CBX_WHO_DEFENDER)) { b->v.def_reward[i] = 0; b->v.def_terminated[i] = b->v.def_truncated[i] = 0; }
     b->v.network_availability[i] = e->availability;
-    memset(b->v.att_info + i * 8, 0, 32);
+  }
+}
+
+void orc_reset(orc_batch* b, const uint8_t* mask) { orc_reset_ex(b, mask, CBX_WHO_ATTACKER | CBX_WHO_DEFENDER); }
+
+void orc_step_ex(orc_batch* b, const int32_t* aa, const int32_t* da, const double* scan_u, const double* detect_u, int who) {
+  if (b->cfg.mode == CBX_MODE_MARLON) {
+    for (int64_t i = 0; i < b->n; ++i)
+      marlon_pair_step(b, i, aa ? aa + i * 10 : NULL, da ? da + i * 12 : NULL, scan_u, detect_u, who);
+  } else {
+    for (int64_t i = 0; i < b->n; ++i) cyber_only_step(b, i, aa + i * 5, scan_u, detect_u);
   }
 }
 
 void orc_step(orc_batch* b, const int32_t* aa, const int32_t* da, const double* scan_u, const double* detect_u) {
-  if (b->cfg.mode == CBX_MODE_MARLON) {
-    for (int64_t i = 0; i < b->n; ++i) marlon_pair_step(b, i, aa + i * 10, da ? da + i * 12 : NULL, scan_u, detect_u);
-  } else {
-    for (int64_t i = 0; i < b->n; ++i) cyber_only_step(b, i, aa + i * 5, scan_u, detect_u);
-  }
+  orc_step_ex(b, aa, da, scan_u, detect_u, CBX_WHO_ATTACKER | CBX_WHO_DEFENDER);
 }
 
 void orc_stats_reset(orc_batch* b) { memset(b->stats, 0, sizeof(b->stats)); }

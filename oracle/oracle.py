@@ -37,6 +37,8 @@ def lib():
         L.orc_views.argtypes = [C.c_void_p, C.POINTER(_abi.Views)]
         L.orc_reset.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_reset_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_step_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.orc_stats_reset.argtypes = [C.c_void_p]
         L.orc_export_words.restype = C.c_int64
         L.orc_export_words.argtypes = [C.c_void_p]
@@ -94,18 +96,18 @@ class OracleBatch:
         if h:
             self._lib.orc_destroy(h)
 
-    def reset(self, mask=None):
+    def reset(self, mask=None, who=3):
         if mask is not None:
             mask = np.ascontiguousarray(mask, dtype=np.uint8)
-        self._lib.orc_reset(self._h, None if mask is None else mask.ctypes.data)
+        self._lib.orc_reset_ex(self._h, None if mask is None else mask.ctypes.data, who)
 
-    def step(self, attacker_actions, defender_actions=None, scan_u=None, detect_u=None):
-        aa = np.ascontiguousarray(attacker_actions, dtype=np.int32)
+    def step(self, attacker_actions, defender_actions=None, scan_u=None, detect_u=None, who=3):
+        aa = None if attacker_actions is None else np.ascontiguousarray(attacker_actions, dtype=np.int32)
         da = None if defender_actions is None else np.ascontiguousarray(defender_actions, dtype=np.int32)
         su = None if scan_u is None else np.ascontiguousarray(scan_u, dtype=np.float64)
         du = None if detect_u is None else np.ascontiguousarray(detect_u, dtype=np.float64)
-        self._lib.orc_step(self._h, aa.ctypes.data, None if da is None else da.ctypes.data,
-                           None if su is None else su.ctypes.data, None if du is None else du.ctypes.data)
+        self._lib.orc_step_ex(self._h, None if aa is None else aa.ctypes.data, None if da is None else da.ctypes.data,
+                              None if su is None else su.ctypes.data, None if du is None else du.ctypes.data, who)
 
     def stats_reset(self):
         self._lib.orc_stats_reset(self._h)
