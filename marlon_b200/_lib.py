@@ -33,10 +33,11 @@ def load():
     global _LIB
     if _LIB is not None:
         return _LIB
-    if not os.path.exists(SO_PATH):
-        raise ImportError(f"{SO_PATH} is missing: build it with `python -m marlon_b200.build` "
+    path = os.environ.get("CBX_LIB") or SO_PATH  # CBX_LIB: an experiment build of the same sources (marlon_b200/build.py)
+    if not os.path.exists(path):
+        raise ImportError(f"{path} is missing: build it with `python -m marlon_b200.build` "
                           "(nvcc, sm_100a). marlon_b200 has no CPU fallback.")
-    L = C.CDLL(SO_PATH)
+    L = C.CDLL(path)
     vp, i64, i32p = C.c_void_p, C.c_int64, C.c_void_p
     L.cbx_last_error.restype = C.c_char_p
     L.cbx_abi_version.restype = C.c_int

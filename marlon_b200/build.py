@@ -20,6 +20,16 @@ def _stale() -> bool:
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
+def build_variant(name: str, defines: dict, verbose: bool = False) -> str:
+    """Experiment builds: libcbx_<name>.so with -D overrides (CBX_TILE, CBX_MIN_CTAS, ...); load with CBX_LIB=<path>."""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    out = os.path.join(HERE, f"libcbx_{name}.so")
+    cmd = [nvcc] + NVCC_FLAGS + [f"-D{k}={v}" for k, v in defines.items()] + (["-Xptxas", "-v"] if verbose else []) \
+        + ["-o", out] + [os.path.join(CSRC, f) for f in SOURCES]
+    subprocess.check_call(cmd, cwd=CSRC)
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return SO

@@ -16,7 +16,7 @@
 extern "C" {
 cudaError_t cbx_launch_step(const cbx_params* p, int op, int grid, int smem_bytes, int use_tma, cudaStream_t stream);
 cudaError_t cbx_launch_sample(const cbx_params* p, int32_t* att, int32_t* def, uint64_t seed, uint32_t step, cudaStream_t stream);
-cudaError_t cbx_kernel_attrs(int smem_bytes, int use_tma, int* blocks_per_sm);
+cudaError_t cbx_kernel_attrs(int smem_bytes, int use_tma, int fast, int* blocks_per_sm);
 }
 
 namespace {
@@ -287,6 +287,7 @@ int cbx_batch_create(const cbx_scenario* s, int64_t n_envs, const cbx_config* cf
   pl.state = o; o = align_up(o + L.S * CBX_TILE, 32);
   pl.stage = o; o = align_up(o + L.G * CBX_TILE, 32);
   pl.desc = o; o = align_up(o + K.desc_words * CBX_TILE, 32);
+  pl.acts = o; o = align_up(o + 22 * CBX_TILE, 32);
   pl.lut = o; o = align_up(o + 512, 32);
   pl.bars = o; o += 8;
   pl.total_bytes = o * 4;
@@ -298,7 +299,7 @@ int cbx_batch_create(const cbx_scenario* s, int64_t n_envs, const cbx_config* cf
   const char* no_tma = getenv("CBX_NO_TMA");
   b->use_tma = !(no_tma && no_tma[0] == '1');
   int bps = 0;
-  { cudaError_t e = cbx_kernel_attrs(b->smem_bytes, b->use_tma, &bps);
+  { cudaError_t e = cbx_kernel_attrs(b->smem_bytes, b->use_tma, b->p.enc.warp_env, &bps);
     if (e != cudaSuccess) { delete b; return fail(CBX_ERR_CUDA, "kernel attributes: %s", cudaGetErrorString(e)); } }
   if (bps < 1) { delete b; return fail(CBX_ERR_CUDA, "step kernel does not fit on an SM"); }
   int sms = 0;

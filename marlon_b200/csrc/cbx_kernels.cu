@@ -72,6 +72,43 @@ __device__ __forceinline__ void st_out(T* p, T v) {
 }
 __device__ __forceinline__ void st_stream(void* p, uint4 v) { st_out(reinterpret_cast<uint4*>(p), v); }
 
+// Per-tile env selection mask (bit e = env e of the tile); a tile has CBX_TILE/32 groups of 32 envs.
+constexpr int kGroups = CBX_TILE / 32;
+struct EnvMask {
+  uint32_t w[kGroups];
+  __device__ __forceinline__ bool test(int e) const { return (w[e >> 5] >> (e & 31)) & 1u; }
+  __device__ __forceinline__ bool any() const {
+    uint32_t a = 0;
+#pragma unroll
+    for (int k = 0; k < kGroups; ++k) a |= w[k];
+    return a != 0;
+  }
+};
+__device__ __forceinline__ EnvMask mask_and_not(const EnvMask& a, const EnvMask& b) {
+  EnvMask r;
+#pragma unroll
+  for (int k = 0; k < kGroups; ++k) r.w[k] = a.w[k] & ~b.w[k];
+  return r;
+}
+__device__ __forceinline__ EnvMask mask_and(const EnvMask& a, const EnvMask& b) {
+  EnvMask r;
+#pragma unroll
+  for (int k = 0; k < kGroups; ++k) r.w[k] = a.w[k] & b.w[k];
+  return r;
+}
+__device__ __forceinline__ EnvMask mask_not(const EnvMask& a) {
+  EnvMask r;
+#pragma unroll
+  for (int k = 0; k < kGroups; ++k) r.w[k] = ~a.w[k];
+  return r;
+}
+__device__ __forceinline__ EnvMask mask_all() {
+  EnvMask r;
+#pragma unroll
+  for (int k = 0; k < kGroups; ++k) r.w[k] = 0xFFFFFFFFu;
+  return r;
+}
+
 // ---- encoder -----------------------------------------------------------------------------------------------------------
 struct Target {  // output pointers already offset to the tile's first env
   int32_t *scalars, *leaked, *cachem, *props, *priv;
@@ -98,7 +135,7 @@ struct Tile {
 
 // generic writer for int32 fields: `wpe` words per env, f(e, wi) -> value
 template <class F>
-__device__ __forceinline__ void write_i32(int32_t* dst, int wpe, FastDiv dv, int n_valid, uint32_t enc_mask, F f) {
+__device__ __forceinline__ void write_i32(int32_t* dst, int wpe, FastDiv dv, int n_valid, const EnvMask& enc_mask, F f) {
   if (!dst || wpe == 0) return;
   const uint32_t total = (uint32_t)wpe * n_valid;
   for (uint32_t v = threadIdx.x * 4; v < total; v += CBX_THREADS * 4) {
@@ -110,7 +147,7 @@ __device__ __forceinline__ void write_i32(int32_t* dst, int wpe, FastDiv dv, int
       vals[q] = 0;
       if (idx < total) {
         uint32_t e = dv.div(idx);
-        if ((enc_mask >> e) & 1u) { vals[q] = (uint32_t)f((int)e, (int)(idx - e * wpe)); keep |= 1u << q; }
+        if (enc_mask.test((int)e)) { vals[q] = (uint32_t)f((int)e, (int)(idx - e * wpe)); keep |= 1u << q; }
       }
     }
     if (keep == 15u) st_stream(dst + v, make_uint4(vals[0], vals[1], vals[2], vals[3]));
@@ -124,7 +161,7 @@ __device__ __forceinline__ void write_i32(int32_t* dst, int wpe, FastDiv dv, int
 
 // generic (slow) writer for int8 fields: f(e, i) -> 0/1
 template <class F>
-__device__ __forceinline__ void write_i8(int8_t* dst, int bpe, FastDiv dv, int n_valid, uint32_t enc_mask, F f) {
+__device__ __forceinline__ void write_i8(int8_t* dst, int bpe, FastDiv dv, int n_valid, const EnvMask& enc_mask, F f) {
   if (!dst || bpe == 0) return;
   const uint32_t total = (uint32_t)bpe * n_valid;
   for (uint32_t v = threadIdx.x * 16; v < total; v += CBX_THREADS * 16) {
@@ -135,7 +172,7 @@ __device__ __forceinline__ void write_i8(int8_t* dst, int bpe, FastDiv dv, int n
       uint32_t idx = v + q;
       if (idx < total) {
         uint32_t e = dv.div(idx);
-        if ((enc_mask >> e) & 1u) {
+        if (enc_mask.test((int)e)) {
           words[q >> 2] |= (uint32_t)(f((int)e, (int)(idx - e * bpe)) & 0xFF) << ((q & 3) * 8);
           keep |= 1u << q;
         }
@@ -178,14 +215,14 @@ __device__ __forceinline__ uint32_t rowmask_byte(const Tile& t, int e, uint32_t 
 
 template <bool CONNECT>
 __device__ __forceinline__ void write_rowmask(int8_t* dst, int bpe, FastDiv denv, int row_len, FastDiv drow, int C, FastDiv dC,
-                                              int n_valid, uint32_t enc_mask, const Tile& t) {
+                                              int n_valid, const EnvMask& enc_mask, const Tile& t) {
   if (!dst || bpe == 0) return;
   const uint32_t total = (uint32_t)bpe * n_valid;
   const bool fast = (bpe % 16 == 0) && row_len >= 16;
   for (uint32_t v = threadIdx.x * 16; v < total; v += CBX_THREADS * 16) {
     if (fast) {
       uint32_t e = denv.div(v);
-      if (!((enc_mask >> e) & 1u)) continue;
+      if (!enc_mask.test((int)e)) continue;
       uint32_t i = v - e * bpe;
       uint32_t s = drow.div(i), w0 = i - s * row_len;
       int lim = (int)(CONNECT ? t.d(e, D_LIMC) : t.d(e, D_LIMR));
@@ -202,7 +239,7 @@ __device__ __forceinline__ void write_rowmask(int8_t* dst, int bpe, FastDiv denv
         uint32_t idx = v + q;
         if (idx < total) {
           uint32_t e = denv.div(idx);
-          if ((enc_mask >> e) & 1u) {
+          if (enc_mask.test((int)e)) {
             words[q >> 2] |= rowmask_byte<CONNECT>(t, (int)e, idx - e * bpe, row_len, drow, C, dC) << ((q & 3) * 8);
             keep |= 1u << q;
           }
@@ -244,31 +281,37 @@ template <> struct Gran<4> {
   static __device__ __forceinline__ T expand(uint32_t m, const uint2*) { return ((m & 0xFu) * 0x00204081u) & 0x01010101u; }
 };
 
+// granule `g` (U bytes at row offset g*U) of an env's template row
 template <int U, bool CONNECT>
+__device__ __forceinline__ typename Gran<U>::T template_granule(int g, int lim, int nc, uint64_t base, int C, FastDiv dC, const uint2* lut) {
+  const int w = g * U;
+  uint32_t m = lowmask(min(max(lim - w, 0), U));
+  if (CONNECT) {
+    const int ph = (int)((uint32_t)w - dC.div((uint32_t)w) * C);
+    uint32_t pm;
+    if (C <= 48) pm = (uint32_t)(base >> ph) & 0xFFFFu;
+    else pm = lowmask(min(max(nc - ph, 0), 16)) | (lowmask(min(max(C - ph + nc, 0), 16)) & ~lowmask(min(max(C - ph, 0), 16)));
+    m &= pm;
+  }
+  return Gran<U>::expand(m, lut);
+}
+
+// Long rows (more than 16 granules): one row after the other, NG granules per lane.
+template <int U, int NG, bool CONNECT>
 __device__ __noinline__ void warp_rowmask(int8_t* envdst, int row_len, int N, int C, cbx_fastdiv dCv, const uint32_t* desc_e,
                                           const uint2* lut, int lane) {
   typedef typename Gran<U>::T G;
-  const FastDiv dC(dCv);
   const int gpr = row_len / U;
   const int lim = (int)(CONNECT ? desc_e[D_LIMC] : desc_e[D_LIMR]);
   const int nc = (int)desc_e[D_NC];
   const uint64_t base = ((uint64_t)desc_e[D_BHI] << 32) | desc_e[D_BLO];
-  G tm[CBX_MAXG];
-  bool valid[CBX_MAXG];
+  G tm[NG];
+  bool valid[NG];
 #pragma unroll
-  for (int k = 0; k < CBX_MAXG; ++k) {
+  for (int k = 0; k < NG; ++k) {
     const int g = lane + 32 * k;
     valid[k] = g < gpr;
-    const int w = g * U;
-    uint32_t m = lowmask(min(max(lim - w, 0), U));
-    if (CONNECT) {
-      const int ph = (int)((uint32_t)w - dC.div((uint32_t)w) * C);
-      uint32_t pm;
-      if (C <= 48) pm = (uint32_t)(base >> ph) & 0xFFFFu;
-      else pm = lowmask(min(max(nc - ph, 0), 16)) | (lowmask(min(max(C - ph + nc, 0), 16)) & ~lowmask(min(max(C - ph, 0), 16)));
-      m &= pm;
-    }
-    tm[k] = Gran<U>::expand(m, lut);
+    tm[k] = template_granule<U, CONNECT>(g, lim, nc, base, C, FastDiv(dCv), lut);
   }
   G* p = reinterpret_cast<G*>(envdst) + lane;
   uint32_t ow = desc_e[D_OWNED];
@@ -276,33 +319,64 @@ __device__ __noinline__ void warp_rowmask(int8_t* envdst, int row_len, int N, in
     if (s && (s & 31) == 0) ow = desc_e[D_OWNED + (s >> 5)];
     if ((ow >> (s & 31)) & 1u) {  // warp-uniform
 #pragma unroll
-      for (int k = 0; k < CBX_MAXG; ++k)
+      for (int k = 0; k < NG; ++k)
         if (valid[k]) st_out(p + 32 * k, tm[k]);
     } else {
 #pragma unroll
-      for (int k = 0; k < CBX_MAXG; ++k)
+      for (int k = 0; k < NG; ++k)
         if (valid[k]) st_out(p + 32 * k, Gran<U>::zero());
     }
   }
 }
 
-template <bool CONNECT>
-__device__ __forceinline__ void warp_rowmask_dispatch(int unit, int8_t* envdst, int row_len, int N, int C, cbx_fastdiv dC,
-                                                      const Tile& t, int e, int lane) {
-  const uint32_t* de = t.desc + e * t.DW;
-  if (unit == 16) warp_rowmask<16, CONNECT>(envdst, row_len, N, C, dC, de, t.lut, lane);
-  else if (unit == 8) warp_rowmask<8, CONNECT>(envdst, row_len, N, C, dC, de, t.lut, lane);
-  else warp_rowmask<4, CONNECT>(envdst, row_len, N, C, dC, de, t.lut, lane);
+// Short rows (at most 16 granules): 32 / gpr rows per store instruction.
+template <int U, bool CONNECT>
+__device__ __noinline__ void warp_rowmask_packed(int8_t* envdst, int row_len, int N, int C, cbx_fastdiv dCv, const uint32_t* desc_e,
+                                                 const uint2* lut, int lane) {
+  typedef typename Gran<U>::T G;
+  const int gpr = row_len / U;
+  const int rpi = 32 / gpr;  // rows per iteration
+  const int r = lane / gpr, g = lane - r * gpr;
+  const bool active = r < rpi;
+  const int lim = (int)(CONNECT ? desc_e[D_LIMC] : desc_e[D_LIMR]);
+  const uint64_t base = ((uint64_t)desc_e[D_BHI] << 32) | desc_e[D_BLO];
+  const G tm = template_granule<U, CONNECT>(g, lim, (int)desc_e[D_NC], base, C, FastDiv(dCv), lut);
+  G* p = reinterpret_cast<G*>(envdst) + lane;  // row r, granule g of the first group == granule index lane
+  for (int s = r; s < N + r; s += rpi, p += rpi * gpr) {
+    if (active && s < N) {
+      const bool own = (desc_e[D_OWNED + (s >> 5)] >> (s & 31)) & 1u;
+      st_out(p, own ? tm : Gran<U>::zero());
+    }
+  }
 }
 
-__device__ void encode_attacker_by_warp(const Tile& t, const Target& o, int n_valid, uint32_t enc_mask) {
+template <int U, bool CONNECT>
+__device__ __forceinline__ void warp_rowmask_u(int8_t* envdst, int row_len, int N, int C, cbx_fastdiv dC, const uint32_t* de,
+                                               const uint2* lut, int lane) {
+  const int gpr = row_len / U;
+  if (gpr <= 16) warp_rowmask_packed<U, CONNECT>(envdst, row_len, N, C, dC, de, lut, lane);
+  else if (gpr <= 32) warp_rowmask<U, 1, CONNECT>(envdst, row_len, N, C, dC, de, lut, lane);
+  else if (gpr <= 64) warp_rowmask<U, 2, CONNECT>(envdst, row_len, N, C, dC, de, lut, lane);
+  else warp_rowmask<U, 4, CONNECT>(envdst, row_len, N, C, dC, de, lut, lane);
+}
+
+template <bool CONNECT>
+__device__ __forceinline__ void warp_rowmask_dispatch(int unit, int8_t* envdst, int row_len, int N, int C, cbx_fastdiv dC,
+                                                      const uint32_t* de, const uint2* lut, int lane) {
+  if (unit == 16) warp_rowmask_u<16, CONNECT>(envdst, row_len, N, C, dC, de, lut, lane);
+  else if (unit == 8) warp_rowmask_u<8, CONNECT>(envdst, row_len, N, C, dC, de, lut, lane);
+  else warp_rowmask_u<4, CONNECT>(envdst, row_len, N, C, dC, de, lut, lane);
+}
+
+__device__ void encode_attacker_by_warp(const Tile& t, const Target& o, int n_valid, const EnvMask& enc_mask) {
   const cbx_layout* L = t.L;
   const cbx_enc_consts& K = *t.K;
   const int lane = threadIdx.x & 31;
   for (int e = threadIdx.x >> 5; e < n_valid; e += CBX_THREADS / 32) {
-    if (!((enc_mask >> e) & 1u)) continue;
-    const uint32_t nd = t.d(e, D_ND), nc = t.d(e, D_NC);
-    const bool blank = t.d(e, D_KIND) == OBS_BLANK;
+    if (!enc_mask.test((int)e)) continue;
+    const uint32_t* de = t.desc + e * t.DW;
+    const uint32_t nd = de[D_ND], nc = de[D_NC];
+    const bool blank = de[D_KIND] == OBS_BLANK;
     if (lane < 8) st_out(o.scalars + e * 8 + lane, (int32_t)t.g(e, STG_SCALARS + lane));
     for (int w = lane; w < 4 * L->LEAK; w += 32) st_out(o.leaked + e * 4 * L->LEAK + w, (int32_t)t.g(e, L->g_leaked + w));
     for (int w = lane; w < 2 * L->C; w += 32) {
@@ -343,25 +417,26 @@ __device__ void encode_attacker_by_warp(const Tile& t, const Target& o, int n_va
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
           uint32_t i = q * 4 + b, s = FastDiv(K.d_L).div(i), v = i - s * L->L;
-          if (t.owned(e, (int)s)) {
+          if ((de[D_OWNED + (s >> 5)] >> (s & 31)) & 1u) {
             uint32_t node = t.byte(e, L->o_disc_order, (int)s);
             word |= (t.tb[t.tb[CBX_H_OFF_VULN] + (node * (L->L + L->R) + v) * CBX_VULN_WORDS] & 1u) << (8 * b);
           }
         }
         st_out(reinterpret_cast<uint32_t*>(dst) + q, word);
       }
-      warp_rowmask_dispatch<false>(K.tmpl_unit_r, o.remote + (size_t)e * L->sz_remote, L->N * L->R, L->N, 1, cbx_fastdiv{0u, 0u}, t, e, lane);
-      warp_rowmask_dispatch<true>(K.tmpl_unit_c, o.connect + (size_t)e * L->sz_connect, L->N * L->P * L->C, L->N, L->C, K.d_C, t, e, lane);
+      warp_rowmask_dispatch<false>(K.tmpl_unit_r, o.remote + (size_t)e * L->sz_remote, L->N * L->R, L->N, 1, cbx_fastdiv{0u, 0u}, de, t.lut, lane);
+      warp_rowmask_dispatch<true>(K.tmpl_unit_c, o.connect + (size_t)e * L->sz_connect, L->N * L->P * L->C, L->N, L->C, K.d_C, de, t.lut, lane);
     }
   }
 }
 
-__device__ void encode_defender_by_warp(const Tile& t, const Target& o, int n_valid, uint32_t enc_mask, bool static_too) {
+__device__ void encode_defender_by_warp(const Tile& t, const Target& o, int n_valid, const EnvMask& enc_mask, bool static_too) {
   const cbx_layout* L = t.L;
   const int lane = threadIdx.x & 31;
   for (int e = threadIdx.x >> 5; e < n_valid; e += CBX_THREADS / 32) {
-    if (!((enc_mask >> e) & 1u)) continue;
-    for (int i = lane; i < L->n; i += 32) o.infected[(size_t)e * L->n + i] = (int8_t)((t.d(e, D_OWNED + L->OW + (i >> 5)) >> (i & 31)) & 1u);
+    if (!enc_mask.test((int)e)) continue;
+    const uint32_t* di = t.desc + e * t.DW + D_OWNED + L->OW;
+    for (int i = lane; i < L->n; i += 32) o.infected[(size_t)e * L->n + i] = (int8_t)((di[i >> 5] >> (i & 31)) & 1u);
     if (!static_too) continue;
     for (int i = lane; i < 6 * L->n; i += 32) {
       const int node = i / 6, r = i - node * 6;
@@ -374,10 +449,11 @@ __device__ void encode_defender_by_warp(const Tile& t, const Target& o, int n_va
 }
 
 // Encode the attacker observation of the envs selected by enc_mask (bit e = env e of the tile).
-__device__ void encode_attacker(const Tile& t, const Target& o, int n_valid, uint32_t enc_mask) {
+template <bool FAST>
+__device__ __forceinline__ void encode_attacker(const Tile& t, const Target& o, int n_valid, const EnvMask& enc_mask) {
   const cbx_layout* L = t.L;
   const cbx_enc_consts& K = *t.K;
-  if (K.warp_env) { encode_attacker_by_warp(t, o, n_valid, enc_mask); return; }
+  if (FAST) { encode_attacker_by_warp(t, o, n_valid, enc_mask); return; }
   write_i32(o.scalars, 8, FastDiv(0u, 3u), n_valid, enc_mask, [&](int e, int wi) { return t.g(e, STG_SCALARS + wi); });
   write_i32(o.leaked, 4 * L->LEAK, K.d_leaked, n_valid, enc_mask, [&](int e, int wi) { return t.g(e, L->g_leaked + wi); });
   write_i32(o.cachem, 2 * L->C, K.d_cachem, n_valid, enc_mask, [&](int e, int wi) -> uint32_t {
@@ -409,10 +485,11 @@ __device__ void encode_attacker(const Tile& t, const Target& o, int n_valid, uin
   write_rowmask<true>(o.connect, L->sz_connect, K.d_connect, L->N * L->P * L->C, K.d_rowc, L->C, K.d_C, n_valid, enc_mask, t);
 }
 
-__device__ void encode_defender(const Tile& t, const Target& o, int n_valid, uint32_t enc_mask, bool static_too) {
+template <bool FAST>
+__device__ __forceinline__ void encode_defender(const Tile& t, const Target& o, int n_valid, const EnvMask& enc_mask, bool static_too) {
   const cbx_layout* L = t.L;
   const cbx_enc_consts& K = *t.K;
-  if (K.warp_env) { encode_defender_by_warp(t, o, n_valid, enc_mask, static_too); return; }
+  if (FAST) { encode_defender_by_warp(t, o, n_valid, enc_mask, static_too); return; }
   write_i8(o.infected, L->n, K.d_n, n_valid, enc_mask,
            [&](int e, int i) -> uint32_t { return (t.d(e, D_OWNED + L->OW + (i >> 5)) >> (i & 31)) & 1u; });
   if (!static_too) return;
@@ -428,10 +505,10 @@ __device__ void encode_defender(const Tile& t, const Target& o, int n_valid, uin
 }
 
 // copy env rows main -> terminal buffers (terminal observation of an intercepted-and-truncated step is the previous one)
-__device__ void copy_rows(void* dst, const void* src, int bpe, int n_valid, uint32_t mask) {
+__device__ void copy_rows(void* dst, const void* src, int bpe, int n_valid, const EnvMask& mask) {
   if (!dst || !src || bpe == 0) return;
   for (int e = 0; e < n_valid; ++e) {
-    if (!((mask >> e) & 1u)) continue;
+    if (!mask.test(e)) continue;
     const uint8_t* s = (const uint8_t*)src + (size_t)e * bpe;
     uint8_t* d = (uint8_t*)dst + (size_t)e * bpe;
     for (int k = threadIdx.x; k < bpe; k += CBX_THREADS) d[k] = s[k];
@@ -482,12 +559,9 @@ __device__ void build_desc(const Ctx& c, uint32_t* d, int DW, const uint32_t* de
   d[D_LIMR] = (uint32_t)(nd * L->R);
   d[D_LIMC] = (uint32_t)(nd * L->P * L->C);
   uint64_t base = 0;
-  if (L->C <= 48) {
-    int ph = 0;
-    for (int b = 0; b < 64; ++b) {
-      if (ph < nc) base |= 1ull << b;
-      if (++ph == L->C) ph = 0;
-    }
+  if (L->C <= 48) {  // bit b set iff (b mod C) < nc: replicate the first period by doubling
+    base = nc >= 64 ? ~0ull : ((1ull << nc) - 1ull);
+    for (int sh = L->C; sh < 64; sh <<= 1) base |= base << sh;
   }
   d[D_BLO] = (uint32_t)base;
   d[D_BHI] = (uint32_t)(base >> 32);
@@ -643,7 +717,7 @@ __device__ void cyber_only_step(const Ctx& c, const cbx_params& p, const int32_t
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------------------------------
-template <bool USE_TMA>
+template <bool USE_TMA, bool FAST>
 __global__ void __launch_bounds__(CBX_THREADS, CBX_MIN_CTAS) cbx_step_kernel(const __grid_constant__ cbx_params p, const int op) {
   extern __shared__ __align__(128) uint32_t smem[];
   const cbx_layout& L = p.lay;
@@ -652,13 +726,17 @@ __global__ void __launch_bounds__(CBX_THREADS, CBX_MIN_CTAS) cbx_step_kernel(con
   uint32_t* s_st = smem + p.plan.state;
   uint32_t* s_sg = smem + p.plan.stage;
   uint32_t* s_desc = smem + p.plan.desc;
+  int32_t* s_act = reinterpret_cast<int32_t*>(smem + p.plan.acts);
   uint2* s_lut = reinterpret_cast<uint2*>(smem + p.plan.lut);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.plan.bars);
-  __shared__ int s_tile;
-  __shared__ uint32_t s_masks[4];
+  __shared__ uint32_t s_masks[4][kGroups];
   const int tid = threadIdx.x;
+  const int warp = tid >> 5;
   const bool reset_only = op & CBX_OP_RESET, who_att = op & CBX_OP_ATTACKER, who_def = op & CBX_OP_DEFENDER;
+  const bool marlon = cfg.mode == CBX_MODE_MARLON;
+  const bool def_on = marlon && cfg.def_enabled && who_def;
   const int DW = p.enc.desc_words;
+  const int AW = marlon ? 10 : 5;  // attacker action words per env
   const uint32_t* s_init = s_tb + p.table_words;  // initial per-env state follows the scenario blob
   const uint32_t table_bytes = (uint32_t)(p.table_words + ((L.S + 3) & ~3)) * 4u;
 
@@ -697,31 +775,40 @@ __global__ void __launch_bounds__(CBX_THREADS, CBX_MIN_CTAS) cbx_step_kernel(con
   CBX_PROF(0)  // prologue: LUT + tables
   uint32_t st_phase = 0;
   int slice_of_kind[3] = {p.slice_of_kind[0], p.slice_of_kind[1], p.slice_of_kind[2]};
+  constexpr uint32_t kRowBytes = CBX_TILE * 4u;
 
   for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
     const int64_t e0 = (int64_t)tile * CBX_TILE;
     const int n_valid = (int)min((int64_t)CBX_TILE, p.n_envs - e0);
-    // ---- (0) stage the state tile: S rows of 128 B ----
+    // ---- (0) stage the state tile (S rows of CBX_TILE words) and the tile's actions ----
     if (USE_TMA) {
       if (tid < 32) {
-        if (tid == 0) mbar_expect_tx(&bars[1], (uint32_t)L.S * 128u);
+        if (tid == 0) mbar_expect_tx(&bars[1], (uint32_t)L.S * kRowBytes);
         __syncwarp();
-        for (int r = tid; r < L.S; r += 32) tma_load_1d(s_st + r * CBX_TILE, p.state + (int64_t)r * p.n_pad + e0, 128u, &bars[1]);
+        for (int r = tid; r < L.S; r += 32) tma_load_1d(s_st + r * CBX_TILE, p.state + (int64_t)r * p.n_pad + e0, kRowBytes, &bars[1]);
       }
-      mbar_wait(&bars[1], st_phase);
-      st_phase ^= 1;
     } else {
       for (int k = tid; k < L.S * CBX_TILE; k += CBX_THREADS)
         s_st[k] = p.state[(int64_t)(k / CBX_TILE) * p.n_pad + e0 + (k % CBX_TILE)];
-      __syncthreads();
     }
+    if (!reset_only) {  // coalesced: the tile's actions are contiguous in the [n, width] action arrays
+      if (p.att_actions && (who_att || !marlon))
+        for (int k = tid; k < n_valid * AW; k += CBX_THREADS) s_act[k] = p.att_actions[e0 * AW + k];
+      if (def_on)
+        for (int k = tid; k < n_valid * 12; k += CBX_THREADS) s_act[CBX_TILE * 10 + k] = p.def_actions[e0 * 12 + k];
+    }
+    if (USE_TMA) {
+      mbar_wait(&bars[1], st_phase);
+      st_phase ^= 1;
+    }
+    __syncthreads();
 
-    CBX_PROF(1)  // state tile load
+    CBX_PROF(1)  // state tile + action load
     const bool active = tid < n_valid;
     Ctx c;
     c.st = s_st + tid; c.sg = s_sg + tid; c.tb = s_tb; c.L = &L; c.cfg = &cfg; c.env = e0 + tid;
 
-    // ---- (1) game logic, phase 1: attacker move (or reset) ----
+    // ---- (1) game logic, phase 1: attacker move (or reset); one thread per env ----
     if (tid < CBX_TILE) {
       uint32_t att_done = 0, keep = 1;
       if (active) {
@@ -729,14 +816,14 @@ __global__ void __launch_bounds__(CBX_THREADS, CBX_MIN_CTAS) cbx_step_kernel(con
         if (reset_only) {
           c.g(STG_OBS_KIND) = OBS_KEEP;
           if (!p.reset_mask || p.reset_mask[c.env]) {
-            if (cfg.mode == CBX_MODE_MARLON) {  // attacker.reset() then defender.reset(), either or both
+            if (marlon) {  // attacker.reset() then defender.reset(), either or both
               if (who_att) c.attacker_reset(s_init);
               if (who_def && cfg.def_enabled) c.defender_reset(s_init);
             } else {
               c.cyber_reset(s_init);
               c.setf32(L.o_att_return, 0.f);
             }
-            if (who_att || cfg.mode != CBX_MODE_MARLON) {
+            if (who_att || !marlon) {
               c.stage_reset_obs();
               p.v.att_reward[c.env] = 0.f; p.v.att_terminated[c.env] = 0; p.v.att_truncated[c.env] = 0;
               int4* ip = reinterpret_cast<int4*>(p.v.att_info + c.env * 8);
@@ -745,34 +832,35 @@ __global__ void __launch_bounds__(CBX_THREADS, CBX_MIN_CTAS) cbx_step_kernel(con
             if (who_def) { p.v.def_reward[c.env] = 0.f; p.v.def_terminated[c.env] = 0; p.v.def_truncated[c.env] = 0; }
             p.v.network_availability[c.env] = 1.0;
           }
-        } else if (cfg.mode == CBX_MODE_MARLON) {
-          if (who_att) attacker_wrapper_step(c, p, p.att_actions + c.env * 10, slice_of_kind, acc);
+        } else if (marlon) {
+          if (who_att) attacker_wrapper_step(c, p, s_act + tid * 10, slice_of_kind, acc);
           else c.g(STG_OBS_KIND) = OBS_KEEP;
         } else {
-          cyber_only_step(c, p, p.att_actions + c.env * 5, acc);
+          cyber_only_step(c, p, s_act + tid * 5, acc);
         }
         att_done = c.g(STG_ATT_DONE);
         keep = c.g(STG_OBS_KIND) == OBS_KEEP;
       }
       uint32_t done_mask = __ballot_sync(0xFFFFFFFFu, att_done != 0);
       uint32_t keep_mask = __ballot_sync(0xFFFFFFFFu, keep != 0);
-      if (tid == 0) { s_masks[0] = done_mask; s_masks[1] = keep_mask; }
+      if ((tid & 31) == 0) { s_masks[0][warp] = done_mask; s_masks[1][warp] = keep_mask; }
     }
     __syncthreads();
     CBX_PROF(2)  // logic phase 1 (attacker move)
-    const uint32_t att_done_mask = s_masks[0];
+    EnvMask att_done_mask, keep1;
+#pragma unroll
+    for (int k = 0; k < kGroups; ++k) { att_done_mask.w[k] = s_masks[0][k]; keep1.w[k] = s_masks[1][k]; }
     Tile t;
     t.L = &L; t.tb = s_tb; t.st = s_st; t.sg = s_sg; t.desc = s_desc; t.lut = s_lut; t.K = &p.enc; t.DW = DW;
 
     // ---- (1b) terminal observations of the envs that finished (rare): encode BEFORE the auto-reset ----
-    if (att_done_mask && cfg.auto_reset && cfg.emit_terminal_obs && !reset_only) {
-      const uint32_t keep_mask = s_masks[1];
-      if (tid < CBX_TILE && active && ((att_done_mask >> tid) & 1u)) build_desc(c, s_desc + tid * DW, DW, nullptr);
+    if (att_done_mask.any() && cfg.auto_reset && cfg.emit_terminal_obs && !reset_only) {
+      if (tid < CBX_TILE && active && att_done_mask.test(tid)) build_desc(c, s_desc + tid * DW, DW, nullptr);
       __syncthreads();
       Target tt = make_target(p.v, L, e0, true);
-      encode_attacker(t, tt, n_valid, att_done_mask & ~keep_mask);
-      const uint32_t cp = att_done_mask & keep_mask;
-      if (cp) {
+      encode_attacker<FAST>(t, tt, n_valid, mask_and_not(att_done_mask, keep1));
+      const EnvMask cp = mask_and(att_done_mask, keep1);
+      if (cp.any()) {
         Target tm = make_target(p.v, L, e0, false);
         copy_rows(tt.scalars, tm.scalars, 32, n_valid, cp);
         copy_rows(tt.leaked, tm.leaked, 16 * L.LEAK, n_valid, cp);
@@ -787,17 +875,17 @@ __global__ void __launch_bounds__(CBX_THREADS, CBX_MIN_CTAS) cbx_step_kernel(con
     }
 
     CBX_PROF(3)  // terminal observations
-    // ---- (2) game logic, phase 2: attacker auto-reset, defender move ----
+    // ---- (2) game logic, phase 2: attacker auto-reset, defender move, encoder descriptors ----
     if (tid < CBX_TILE) {
       uint32_t def_done = 0, keep = 1;
       if (active) {
         if (!reset_only) {
           if (c.g(STG_ATT_DONE) && cfg.auto_reset) {
-            if (cfg.mode == CBX_MODE_MARLON) c.attacker_reset(s_init);
+            if (marlon) c.attacker_reset(s_init);
             else { c.cyber_reset(s_init); c.setf32(L.o_att_return, 0.f); }
             c.stage_reset_obs();
           }
-          if (cfg.mode == CBX_MODE_MARLON && cfg.def_enabled && who_def) defender_wrapper_step(c, p, p.def_actions + c.env * 12, acc);
+          if (def_on) defender_wrapper_step(c, p, s_act + CBX_TILE * 10 + tid * 12, acc);
         }
         def_done = c.g(STG_DEF_DONE) && cfg.auto_reset;
         keep = c.g(STG_OBS_KIND) == OBS_KEEP;
@@ -810,27 +898,29 @@ __global__ void __launch_bounds__(CBX_THREADS, CBX_MIN_CTAS) cbx_step_kernel(con
       }
       uint32_t dmask = __ballot_sync(0xFFFFFFFFu, def_done != 0);
       uint32_t kmask = __ballot_sync(0xFFFFFFFFu, keep != 0);
-      if (tid == 0) { s_masks[2] = dmask; s_masks[3] = kmask; }
+      if ((tid & 31) == 0) { s_masks[2][warp] = dmask; s_masks[3][warp] = kmask; }
     }
     __syncthreads();
     CBX_PROF(4)  // logic phase 2 (auto-reset, defender move, descriptors)
-    const uint32_t def_done_mask = s_masks[2];
-    const uint32_t enc_mask = ~s_masks[3];
+    EnvMask def_done_mask, keep2;
+#pragma unroll
+    for (int k = 0; k < kGroups; ++k) { def_done_mask.w[k] = s_masks[2][k]; keep2.w[k] = s_masks[3][k]; }
+    const EnvMask enc_mask = mask_not(keep2);
 
     // ---- (3) encode ----
     {
       Target tm = make_target(p.v, L, e0, false);
-      encode_attacker(t, tm, n_valid, enc_mask);
-      if (cfg.mode == CBX_MODE_MARLON && cfg.def_enabled && who_def) {
-        encode_defender(t, tm, n_valid, 0xFFFFFFFFu, true);
-        if (def_done_mask && cfg.emit_terminal_obs) {
+      encode_attacker<FAST>(t, tm, n_valid, enc_mask);
+      if (marlon && cfg.def_enabled && who_def) {
+        encode_defender<FAST>(t, tm, n_valid, mask_all(), true);
+        if (def_done_mask.any() && cfg.emit_terminal_obs) {
           // terminal defender observation = infected nodes seen by the step that ended the episode
           __syncthreads();
-          if (tid < CBX_TILE && active && ((def_done_mask >> tid) & 1u))
+          if (tid < CBX_TILE && active && def_done_mask.test(tid))
             for (int k = 0; k < L.Wn; ++k) s_desc[tid * DW + D_OWNED + L.OW + k] = c.g(STG_DEF_TERM_INST + k);
           __syncthreads();
           Target tt = make_target(p.v, L, e0, true);
-          encode_defender(t, tt, n_valid, def_done_mask, false);
+          encode_defender<FAST>(t, tt, n_valid, def_done_mask, false);
         }
       }
     }
@@ -839,12 +929,12 @@ __global__ void __launch_bounds__(CBX_THREADS, CBX_MIN_CTAS) cbx_step_kernel(con
     CBX_PROF(5)  // encode
     // ---- (4) deferred defender auto-reset (DummyVecEnv resets after the step; the attacker's observation of this
     //          step was taken before it), then stream the state tile back ----
-    if (tid < CBX_TILE && active && ((def_done_mask >> tid) & 1u)) c.defender_reset(s_init);
+    if (tid < CBX_TILE && active && def_done_mask.test(tid)) c.defender_reset(s_init);
     if (USE_TMA) {
       fence_async_smem();
       __syncthreads();
       if (tid < 32) {
-        for (int r = tid; r < L.S; r += 32) tma_store_1d(p.state + (int64_t)r * p.n_pad + e0, s_st + r * CBX_TILE, 128u);
+        for (int r = tid; r < L.S; r += 32) tma_store_1d(p.state + (int64_t)r * p.n_pad + e0, s_st + r * CBX_TILE, kRowBytes);
         tma_store_commit();
         tma_store_wait_read();  // the tile buffer is reused by the next iteration
       }
@@ -859,17 +949,16 @@ __global__ void __launch_bounds__(CBX_THREADS, CBX_MIN_CTAS) cbx_step_kernel(con
   }
   if (USE_TMA && tid < 32) tma_store_wait_all();
 
-  // ---- episode statistics: warp shuffle reduce, one atomic per slot per CTA ----
-  if (tid < 32) {
+  // ---- episode statistics: warp shuffle reduce, one atomic per slot per warp ----
+  if (tid < CBX_TILE) {
 #pragma unroll
     for (int k = 0; k < CBX_STAT_COUNT; ++k) {
       double x = acc.v[k];
       for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xFFFFFFFFu, x, o);
-      if (tid == 0 && x != 0.0) atomicAdd(p.v.episode_stats + k, x);
+      if ((tid & 31) == 0 && x != 0.0) atomicAdd(p.v.episode_stats + k, x);
     }
   }
 }
-
 
 // ---- uniformly sampled valid actions (benchmark load; ENV:959-1047 semantics) -------------------------------------------
 // One thread per env reads its state words straight from HBM (column access is coalesced across the warp).
@@ -947,10 +1036,19 @@ __global__ void cbx_sample_kernel(const __grid_constant__ cbx_params p, int32_t*
 }  // namespace cbx
 
 // ---- launch helpers used by cbx_api.cu ------------------------------------------------------------------------------------
+template <bool A, bool B>
+static cudaError_t attrs_of(int smem_bytes, int* blocks_per_sm) {
+  cudaError_t e = cudaFuncSetAttribute(cbx::cbx_step_kernel<A, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  if (e != cudaSuccess) return e;
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, cbx::cbx_step_kernel<A, B>, CBX_THREADS, smem_bytes);
+}
 extern "C" {
 cudaError_t cbx_launch_step(const cbx_params* p, int op, int grid, int smem_bytes, int use_tma, cudaStream_t stream) {
-  if (use_tma) cbx::cbx_step_kernel<true><<<grid, CBX_THREADS, smem_bytes, stream>>>(*p, op);
-  else cbx::cbx_step_kernel<false><<<grid, CBX_THREADS, smem_bytes, stream>>>(*p, op);
+  const bool fast = p->enc.warp_env;
+  if (use_tma && fast) cbx::cbx_step_kernel<true, true><<<grid, CBX_THREADS, smem_bytes, stream>>>(*p, op);
+  else if (use_tma) cbx::cbx_step_kernel<true, false><<<grid, CBX_THREADS, smem_bytes, stream>>>(*p, op);
+  else if (fast) cbx::cbx_step_kernel<false, true><<<grid, CBX_THREADS, smem_bytes, stream>>>(*p, op);
+  else cbx::cbx_step_kernel<false, false><<<grid, CBX_THREADS, smem_bytes, stream>>>(*p, op);
   return cudaGetLastError();
 }
 cudaError_t cbx_launch_sample(const cbx_params* p, int32_t* att, int32_t* def, uint64_t seed, uint32_t step, cudaStream_t stream) {
@@ -959,15 +1057,10 @@ cudaError_t cbx_launch_sample(const cbx_params* p, int32_t* att, int32_t* def, u
   cbx::cbx_sample_kernel<<<grid, threads, 0, stream>>>(*p, att, def, seed, step);
   return cudaGetLastError();
 }
-cudaError_t cbx_kernel_attrs(int smem_bytes, int use_tma, int* blocks_per_sm) {
-  cudaError_t e;
-  if (use_tma) {
-    e = cudaFuncSetAttribute(cbx::cbx_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, cbx::cbx_step_kernel<true>, CBX_THREADS, smem_bytes);
-  }
-  e = cudaFuncSetAttribute(cbx::cbx_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-  if (e != cudaSuccess) return e;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, cbx::cbx_step_kernel<false>, CBX_THREADS, smem_bytes);
+cudaError_t cbx_kernel_attrs(int smem_bytes, int use_tma, int fast, int* blocks_per_sm) {
+  if (use_tma && fast) return attrs_of<true, true>(smem_bytes, blocks_per_sm);
+  if (use_tma) return attrs_of<true, false>(smem_bytes, blocks_per_sm);
+  if (fast) return attrs_of<false, true>(smem_bytes, blocks_per_sm);
+  return attrs_of<false, false>(smem_bytes, blocks_per_sm);
 }
 }

@@ -16,7 +16,9 @@
 
 #include "../../include/cbx.h"
 
-#define CBX_TILE 32          // envs per tile (= one warp of game-logic threads)
+#ifndef CBX_TILE
+#define CBX_TILE 32          // envs per tile (a multiple of 32, at most CBX_THREADS: one game-logic thread per env)
+#endif
 #define CBX_THREADS 128      // threads per CTA
 #define CBX_MAX_LEAK 64
 #ifndef CBX_MIN_CTAS
@@ -86,7 +88,7 @@ struct cbx_enc_consts {  // divisors of the encoder, fixed per batch
 };
 
 struct cbx_smem_plan {  // shared-memory carve-up in 32-bit words
-  int tables, state, stage, desc, lut, bars, total_bytes;
+  int tables, state, stage, desc, acts, lut, bars, total_bytes;
 };
 
 struct cbx_params {
