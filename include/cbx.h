@@ -153,6 +153,8 @@ typedef struct cbx_config {
   int32_t scan_capacity;
   int32_t scan_frequency;
   uint64_t seed;                     /* Philox key for the built-in defender's draws */
+  int64_t env_index_base;            /* global index of this batch's env 0: Philox counters use base + local index, so a
+                                        run sharded over several GPUs draws exactly what the unsharded run draws */
   /* AttackerEnvWrapper (attack_wrapper.py:34-42); MultiDiscrete layout [3, slice0.., slice1.., slice2..] */
   int32_t kind_of_index[3];          /* CBX_KIND_* selected by action[0] = 0,1,2 (gymnasium 0.29 sorts: connect, local, remote) */
   int32_t att_max_timesteps;
@@ -330,6 +332,11 @@ enum { CBX_WHO_ATTACKER = 1, CBX_WHO_DEFENDER = 2 };
 int cbx_batch_step_ex(cbx_batch* b, const int32_t* attacker_actions, const int32_t* defender_actions,
                       const cbx_tape* tape_or_null, int who, void* cuda_stream);
 int cbx_batch_reset_ex(cbx_batch* b, const uint8_t* mask_or_null, int who, void* cuda_stream);
+
+/* EnvironmentEventSource.notify_reset(last_reward) delivered from outside (environment_event_source.py:30-38; used by
+ * marl_algorithm.run_episode, marl_algorithm.py:176-178): sets reset_request on the selected wrappers of the masked envs and,
+ * for the defender, records last_reward (defend_wrapper.py:479-482). */
+int cbx_batch_notify_reset(cbx_batch* b, const uint8_t* mask_or_null, int who, double last_reward, void* cuda_stream);
 
 /* Same step on HOST buffers: pinned staging + H2D of the actions, the step, D2H of rewards and done flags
  * (att_reward, def_reward, 4 flag arrays -> host_out, layout: float[n], float[n], uint8[4][n]); synchronises. */

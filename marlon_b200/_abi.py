@@ -51,6 +51,7 @@ class Config(C.Structure):
         ("scan_capacity", C.c_int32),
         ("scan_frequency", C.c_int32),
         ("seed", C.c_uint64),
+        ("env_index_base", C.c_int64),
         ("kind_of_index", C.c_int32 * 3),
         ("att_max_timesteps", C.c_int32),
         ("att_invalid_action_reward_modifier", C.c_double),

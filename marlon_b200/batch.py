@@ -96,18 +96,31 @@ class Batch:
         return a
 
     # ------------------------------------------------------------------------------------------------
-    def reset(self, mask=None):
-        """Reset the envs selected by `mask` (all when None) and write their reset observations."""
+    WHO_ATTACKER, WHO_DEFENDER, WHO_BOTH = 1, 2, 3
+
+    def reset(self, mask=None, who: int = 3):
+        """Reset the envs selected by `mask` (all when None) and write their reset observations.  In MARLon mode `who`
+        selects AttackerEnvWrapper.reset() (1), DefenderEnvWrapper.reset() (2) or both, attacker first (3)."""
         torch = self._torch
         m = self._dev(mask, torch.uint8) if mask is not None else None
         with torch.cuda.device(self.device):
-            _lib.check(self._L.cbx_batch_reset(self._h, C.c_void_p(m.data_ptr()) if m is not None else None, self._stream()))
+            _lib.check(self._L.cbx_batch_reset_ex(self._h, C.c_void_p(m.data_ptr()) if m is not None else None, int(who), self._stream()))
         self._keep = [m]
 
-    def step(self, attacker_actions, defender_actions=None, scan_u=None, detect_u=None):
-        """One env-step for every env. Actions: int32 [n,10] (MARLon) or [n,5] (CyberBattleEnv), defender [n,12]."""
+    def notify_reset(self, who: int, last_reward: float = 0.0, mask=None):
+        """EnvironmentEventSource.notify_reset from outside: raise reset_request on the selected wrappers."""
         torch = self._torch
-        a = self._dev(attacker_actions, torch.int32, self.att_width)
+        m = self._dev(mask, torch.uint8) if mask is not None else None
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.cbx_batch_notify_reset(self._h, C.c_void_p(m.data_ptr()) if m is not None else None, int(who),
+                                                      float(last_reward), self._stream()))
+        self._keep = [m]
+
+    def step(self, attacker_actions, defender_actions=None, scan_u=None, detect_u=None, who: int = 3):
+        """One env-step for every env. Actions: int32 [n,10] (MARLon) or [n,5] (CyberBattleEnv), defender [n,12].
+        `who`: both halves of the MARLon pair step (3), only the attacker's (1) or only the defender's (2)."""
+        torch = self._torch
+        a = self._dev(attacker_actions, torch.int32, self.att_width) if attacker_actions is not None else None
         d = self._dev(defender_actions, torch.int32, 12) if defender_actions is not None else None
         tape = None
         su = du = None
@@ -116,8 +129,9 @@ class Batch:
             tape = _abi.Tape(C.cast(C.c_void_p(su.data_ptr()), C.POINTER(C.c_double)),
                              C.cast(C.c_void_p(du.data_ptr()), C.POINTER(C.c_double)))
         with torch.cuda.device(self.device):
-            _lib.check(self._L.cbx_batch_step(self._h, C.c_void_p(a.data_ptr()), C.c_void_p(d.data_ptr()) if d is not None else None,
-                                              C.byref(tape) if tape is not None else None, self._stream()))
+            _lib.check(self._L.cbx_batch_step_ex(self._h, C.c_void_p(a.data_ptr()) if a is not None else None,
+                                                 C.c_void_p(d.data_ptr()) if d is not None else None,
+                                                 C.byref(tape) if tape is not None else None, int(who), self._stream()))
         self._keep = [a, d, su, du]  # keep inputs alive until the next call (stream-ordered use)
 
     def step_host(self, attacker_actions: np.ndarray, defender_actions: Optional[np.ndarray] = None):

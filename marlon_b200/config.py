@@ -68,6 +68,7 @@ def make_config(
     losing_reward: float = 0.0,
     throws_on_invalid_actions: bool = True,
     seed: int = 0,
+    env_index_base: int = 0,
     # AttackerEnvWrapper
     attacker_max_timesteps: int = 2000,
     attacker_invalid_action_reward_modifier: float = -1.0,
@@ -119,6 +120,7 @@ def make_config(
         raise NotImplementedError(f"built-in defender {type(defender_agent).__name__} is not on the batched path "
                                   "(only ScanAndReimageCompromisedMachines; SURVEY.md section 2 row 4)")
     c.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    c.env_index_base = int(env_index_base)
     order = KIND_ORDERS[action_kind_order] if isinstance(action_kind_order, str) else tuple(int(k) for k in action_kind_order)
     if sorted(order) != [0, 1, 2]:
         raise ValueError("action_kind_order must be a permutation of the three action kinds")

@@ -433,6 +433,17 @@ int cbx_batch_reset_ex(cbx_batch* b, const uint8_t* mask_or_null, int who, void*
   return timed_launch(b, op, (cudaStream_t)cuda_stream);
 }
 
+int cbx_batch_notify_reset(cbx_batch* b, const uint8_t* mask_or_null, int who, double last_reward, void* cuda_stream) {
+  if (!b) return fail(CBX_ERR_INVALID, "null batch");
+  if (!(who & (CBX_WHO_ATTACKER | CBX_WHO_DEFENDER))) return fail(CBX_ERR_INVALID, "notify: nobody selected");
+  CUDA_TRY(cudaSetDevice(b->device));
+  b->p.reset_mask = mask_or_null;
+  b->p.notify_last_reward = (float)last_reward;
+  b->p.att_actions = nullptr; b->p.def_actions = nullptr; b->p.scan_u = nullptr; b->p.detect_u = nullptr;
+  int op = CBX_OP_RESET | CBX_OP_NOTIFY | ((who & CBX_WHO_ATTACKER) ? CBX_OP_ATTACKER : 0) | ((who & CBX_WHO_DEFENDER) ? CBX_OP_DEFENDER : 0);
+  return timed_launch(b, op, (cudaStream_t)cuda_stream);
+}
+
 int cbx_batch_reset(cbx_batch* b, const uint8_t* mask_or_null, void* cuda_stream) {
   return cbx_batch_reset_ex(b, mask_or_null, CBX_WHO_ATTACKER | CBX_WHO_DEFENDER, cuda_stream);
 }

@@ -295,7 +295,8 @@ struct Ctx {
         ud = detect_u[env * cap + k];
       } else {
         uint32_t o[4];
-        philox4x32_10((uint32_t)env, (uint32_t)(env >> 32), (uint32_t)stepcount, (uint32_t)k, (uint32_t)cfg->seed,
+        const int64_t ge = env + cfg->env_index_base;
+        philox4x32_10((uint32_t)ge, (uint32_t)(ge >> 32), (uint32_t)stepcount, (uint32_t)k, (uint32_t)cfg->seed,
                       (uint32_t)(cfg->seed >> 32), o);
         us = u53(o[0], o[1]);
         ud = u53(o[2], o[3]);

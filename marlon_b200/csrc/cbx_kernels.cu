@@ -815,7 +815,12 @@ __global__ void __launch_bounds__(CBX_THREADS, CBX_MIN_CTAS) cbx_step_kernel(con
         c.g(STG_ATT_DONE) = 0; c.g(STG_DEF_DONE) = 0;
         if (reset_only) {
           c.g(STG_OBS_KIND) = OBS_KEEP;
-          if (!p.reset_mask || p.reset_mask[c.env]) {
+          if (op & CBX_OP_NOTIFY) {
+            if (!p.reset_mask || p.reset_mask[c.env]) {
+              if (who_att) c.setflag(HDR_ATT_RR, true);
+              if (who_def) { c.setflag(HDR_DEF_RR, true); c.setf32(L.o_last_att, p.notify_last_reward); }
+            }
+          } else if (!p.reset_mask || p.reset_mask[c.env]) {
             if (marlon) {  // attacker.reset() then defender.reset(), either or both
               if (who_att) c.attacker_reset(s_init);
               if (who_def && cfg.def_enabled) c.defender_reset(s_init);
@@ -911,7 +916,7 @@ __global__ void __launch_bounds__(CBX_THREADS, CBX_MIN_CTAS) cbx_step_kernel(con
     {
       Target tm = make_target(p.v, L, e0, false);
       encode_attacker<FAST>(t, tm, n_valid, enc_mask);
-      if (marlon && cfg.def_enabled && who_def) {
+      if (marlon && cfg.def_enabled && who_def && !(op & CBX_OP_NOTIFY)) {
         encode_defender<FAST>(t, tm, n_valid, mask_all(), true);
         if (def_done_mask.any() && cfg.emit_terminal_obs) {
           // terminal defender observation = infected nodes seen by the step that ended the episode

@@ -28,6 +28,7 @@
 #define CBX_OP_RESET 1
 #define CBX_OP_ATTACKER 2
 #define CBX_OP_DEFENDER 4
+#define CBX_OP_NOTIFY 8    // with CBX_OP_RESET: only raise the reset_request flags (EnvironmentEventSource.notify_reset)
 
 struct cbx_layout {
   // dimensions
@@ -108,6 +109,7 @@ struct cbx_params {
   const double* scan_u;
   const double* detect_u;
   const uint8_t* reset_mask;  // reset kernel only
+  float notify_last_reward;   // CBX_OP_NOTIFY
   cbx_views v;
   int* tile_counter;      // dynamic tile scheduler
   unsigned long long* prof;  // optional: 16 cycle counters accumulated per phase by thread 0 of every CTA (NULL = off)

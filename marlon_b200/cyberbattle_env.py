@@ -99,37 +99,36 @@ class CyberBattleEnv:
                  throws_on_invalid_actions=True, *, device: int = 0, seed: int = 0):
         if not observation_padding:
             raise NotImplementedError("observation_padding=False (variable-size observations) is not on the batched path")
-        self.__initial_environment = initial_environment
+        self._initial_environment = initial_environment
         self.compiled = scenario.compile_scenario(initial_environment)  # validate_environment's checks live in the compiler
-        self.__bounds = EnvironmentBounds.of_identifiers(initial_environment.identifiers, maximum_total_credentials,
+        self._bounds = EnvironmentBounds.of_identifiers(initial_environment.identifiers, maximum_total_credentials,
                                                          maximum_node_count, maximum_discoverable_credentials_per_action)
         if self.compiled.n_nodes > maximum_node_count:
             raise ValueError(f"Network node count ({self.compiled.n_nodes}) exceeds the specified limit of {maximum_node_count}.")
-        if self.compiled.max_leak > int(self.__bounds.maximum_discoverable_credentials_per_action):
+        if self.compiled.max_leak > int(self._bounds.maximum_discoverable_credentials_per_action):
             raise ValueError(f"Some action in the environment returns {self.compiled.max_leak} credentials which exceeds the maximum "
-                             f"number of discoverable credentials of {self.__bounds.maximum_discoverable_credentials_per_action}")
+                             f"number of discoverable credentials of {self._bounds.maximum_discoverable_credentials_per_action}")
         self.env_kwargs = dict(
             maximum_total_credentials=maximum_total_credentials, maximum_node_count=maximum_node_count,
-            maximum_discoverable_credentials_per_action=int(self.__bounds.maximum_discoverable_credentials_per_action),
+            maximum_discoverable_credentials_per_action=int(self._bounds.maximum_discoverable_credentials_per_action),
             defender_agent=defender_agent, attacker_goal=attacker_goal, defender_goal=defender_goal,
             defender_constraint=defender_constraint, winning_reward=winning_reward, losing_reward=losing_reward,
             throws_on_invalid_actions=throws_on_invalid_actions, seed=seed)
-        self.__attacker_goal, self.__defender_goal, self.__defender_constraint = attacker_goal, defender_goal, defender_constraint
-        self.__WINNING_REWARD, self.__LOSING_REWARD = winning_reward, losing_reward
-        self.__defender_agent = defender_agent
-        self.__throws_on_invalid_actions = throws_on_invalid_actions
-        self.__node_count = self.compiled.n_nodes
+        self._attacker_goal, self._defender_goal, self._defender_constraint = attacker_goal, defender_goal, defender_constraint
+        self._winning_reward, self._losing_reward = winning_reward, losing_reward
+        self._defender_agent = defender_agent
+        self._throws_on_invalid_actions = throws_on_invalid_actions
+        self._node_count = self.compiled.n_nodes
         self.device = device
-        self.action_space = action_space_of(self.__bounds)
-        self.observation_space = observation_space_of(self.__bounds)
+        self.action_space = action_space_of(self._bounds)
+        self.observation_space = observation_space_of(self._bounds)
         self.reward_range = (-float("inf"), float("inf"))
         self.np_random = np.random.default_rng()
         self.viewer = None
         self._batch = None
         self._marlon_batch = None  # set by AttackerEnvWrapper when the MARLon wrappers drive this env
-        self.__episode_rewards: List[float] = []
-        self.__done = False
-        self.__reset_environment()
+        self._episode_rewards: List[float] = []
+        self._done = False
 
     # ---- plumbing ---------------------------------------------------------------------------------------
     def _make_batch(self):
@@ -147,9 +146,9 @@ class CyberBattleEnv:
             self._batch = self._make_batch()
         return self._batch
 
-    def __reset_environment(self) -> None:
-        self.__episode_rewards = []
-        self.__done = False
+    def _reset_environment(self) -> None:
+        self._episode_rewards = []
+        self._done = False
         if self._marlon_batch is None:
             self.batch.reset()
 
@@ -159,7 +158,7 @@ class CyberBattleEnv:
 
     @property
     def environment(self) -> model.Environment:
-        return self.__initial_environment
+        return self._initial_environment
 
     @property
     def name(self) -> str:
@@ -167,11 +166,11 @@ class CyberBattleEnv:
 
     @property
     def identifiers(self) -> model.Identifiers:
-        return self.__initial_environment.identifiers
+        return self._initial_environment.identifiers
 
     @property
     def bounds(self) -> EnvironmentBounds:
-        return self.__bounds
+        return self._bounds
 
     # ---- state peeks (what MARLon reaches for through name-mangled attributes) -----------------------------
     def _state(self) -> Dict[str, Any]:
@@ -179,7 +178,7 @@ class CyberBattleEnv:
         n = self.compiled.n_nodes
         h = _abi.X_HEADER_WORDS
         nd, nc = int(x[2]), int(x[3])
-        C = int(self.__bounds.maximum_total_credentials)
+        C = int(self._bounds.maximum_total_credentials)
         return {
             "stepcount": int(x[0]), "done": bool(x[1]),
             "discovered": [self.compiled.node_ids[i] for i in x[h:h + nd]],
@@ -208,7 +207,7 @@ class CyberBattleEnv:
     # ---- observation assembly -----------------------------------------------------------------------------
     def _observation(self, prefix: str = "") -> Dict[str, Any]:
         """The reference's Observation dict (cyberbattle_env.py:753-773, 859-933) from the device arrays."""
-        b, bd = self.batch, self.__bounds
+        b, bd = self.batch, self._bounds
         g = lambda k: b.numpy(prefix + k)[0]  # noqa: E731
         sc = g("scalars")
         leak, C = int(bd.maximum_discoverable_credentials_per_action), int(bd.maximum_total_credentials)
@@ -248,7 +247,7 @@ class CyberBattleEnv:
     # ---- gym API ------------------------------------------------------------------------------------------------
     def step(self, action) -> Tuple[Dict[str, Any], float, bool, bool, Dict[str, Any]]:
         """cyberbattle_env.py:1145-1185"""
-        if self.__done:
+        if self._done:
             raise RuntimeError("new episode must be started with env.reset()")
         if self._marlon_batch is not None:
             raise RuntimeError("this env is driven by MARLon wrappers: step through AttackerEnvWrapper / DefenderEnvWrapper")
@@ -268,13 +267,13 @@ class CyberBattleEnv:
             raise ValueError("Agent has not discovered credential")
         obs = self._observation()
         reward = float(self.batch.numpy("att_reward")[0])
-        self.__done = bool(self.batch.numpy("att_terminated")[0])
-        self.__episode_rewards.append(reward)
-        return obs, reward, self.__done, False, self._info()
+        self._done = bool(self.batch.numpy("att_terminated")[0])
+        self._episode_rewards.append(reward)
+        return obs, reward, self._done, False, self._info()
 
     def reset(self, *, seed: Optional[int] = None, options: Optional[dict] = None):
         """cyberbattle_env.py:1187-1209"""
-        self.__reset_environment()
+        self._reset_environment()
         self.np_random = np.random.default_rng(seed)
         obs = self._observation()
         info = self._info()
@@ -292,7 +291,7 @@ class CyberBattleEnv:
     # ---- helpers of the reference -----------------------------------------------------------------------------------
     def compute_action_mask(self):
         """cyberbattle_env.py:679-683 (recomputed from the live state: owned set, discovery and cache counts)."""
-        bd = self.__bounds
+        bd = self._bounds
         N, C, P = int(bd.maximum_node_count), int(bd.maximum_total_credentials), int(bd.port_count)
         L, R = int(bd.local_attacks_count), int(bd.remote_attacks_count)
         st = self._state()
@@ -332,7 +331,7 @@ class CyberBattleEnv:
         """cyberbattle_env.py:1016-1039"""
         kind = spaces.DiscriminatedUnion.kind(action)
         st = self._state()
-        nd, nc, bd = len(st["discovered"]), len(st["cache"]), self.__bounds
+        nd, nc, bd = len(st["discovered"]), len(st["cache"]), self._bounds
         c = [int(x) for x in action[kind]]
         if kind == "local_vulnerability":
             ok = c[0] < nd and self.is_node_owned(c[0]) and c[1] < bd.local_attacks_count
@@ -346,7 +345,7 @@ class CyberBattleEnv:
         """cyberbattle_env.py:959-1047: sample within the expected ranges until the mask admits the action
         (kind 1 -> local, kind 0 -> remote, as in the reference)."""
         st = self._state()
-        nd, nc, bd = len(st["discovered"]), len(st["cache"]), self.__bounds
+        nd, nc, bd = len(st["discovered"]), len(st["cache"]), self._bounds
         idx = {k: i for i, k in enumerate(self.compiled.node_ids)}
         owned = [s for s, k in enumerate(st["discovered"]) if st["privilege"][idx[k]] >= 1]
         mask = self.compute_action_mask()
@@ -377,23 +376,23 @@ class CyberBattleEnv:
 
     # goal predicates on the live state (MARLon's defender wrapper calls the name-mangled one, defend_wrapper.py:260)
     def _CyberBattleEnv__defender_goal_reached(self) -> bool:  # noqa: N802
-        return bool(self.__defender_goal.eviction and not (self._state()["privilege"] >= 1).any())
+        return bool(self._defender_goal.eviction and not (self._state()["privilege"] >= 1).any())
 
     @property
     def _CyberBattleEnv__defender_constraint(self):  # noqa: N802
-        return self.__defender_constraint
+        return self._defender_constraint
 
     @property
     def _CyberBattleEnv__WINNING_REWARD(self):  # noqa: N802
-        return self.__WINNING_REWARD
+        return self._winning_reward
 
     @property
     def _CyberBattleEnv__LOSING_REWARD(self):  # noqa: N802
-        return self.__LOSING_REWARD
+        return self._losing_reward
 
     @property
     def _CyberBattleEnv__episode_rewards(self):  # noqa: N802
-        return self.__episode_rewards
+        return self._episode_rewards
 
 
 class CyberBattleToyCtf(CyberBattleEnv):

@@ -427,7 +427,8 @@ static void scan_and_reimage(orc_batch* b, oenv_t* e, int64_t env_index, const d
       us = scan_u[env_index * cap + k];
       ud = detect_u[env_index * cap + k];
     } else {
-      uint32_t ctr[4] = {(uint32_t)env_index, (uint32_t)(env_index >> 32), (uint32_t)e->stepcount, (uint32_t)k};
+      const int64_t ge = env_index + c->env_index_base;
+      uint32_t ctr[4] = {(uint32_t)ge, (uint32_t)(ge >> 32), (uint32_t)e->stepcount, (uint32_t)k};
       uint32_t key[2] = {(uint32_t)c->seed, (uint32_t)(c->seed >> 32)}, o[4];
       philox4x32_10(ctr, key, o);
       us = u53(o[0], o[1]);
@@ -974,6 +975,16 @@ void orc_reset_ex(orc_batch* b, const uint8_t* mask, int who) {
     }
     if (b->cfg.mode != CBX_MODE_MARLON || (who & CBX_WHO_DEFENDER)) { b->v.def_reward[i] = 0; b->v.def_terminated[i] = b->v.def_truncated[i] = 0; }
     b->v.network_availability[i] = e->availability;
+  }
+}
+
+/* EnvironmentEventSource.notify_reset delivered from outside (environment_event_source.py:30-38) */
+void orc_notify_reset(orc_batch* b, const uint8_t* mask, int who, double last_reward) {
+  for (int64_t i = 0; i < b->n; ++i) {
+    if (mask && !mask[i]) continue;
+    oenv_t* e = &b->envs[i];
+    if (who & CBX_WHO_ATTACKER) e->att_reset_request = 1;
+    if (who & CBX_WHO_DEFENDER) { e->def_reset_request = 1; e->last_attacker_reward = (double)(float)last_reward; }
   }
 }
 

@@ -39,6 +39,7 @@ def lib():
         L.orc_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_reset_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.orc_step_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_notify_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double]
         L.orc_stats_reset.argtypes = [C.c_void_p]
         L.orc_export_words.restype = C.c_int64
         L.orc_export_words.argtypes = [C.c_void_p]
@@ -108,6 +109,11 @@ class OracleBatch:
         du = None if detect_u is None else np.ascontiguousarray(detect_u, dtype=np.float64)
         self._lib.orc_step_ex(self._h, None if aa is None else aa.ctypes.data, None if da is None else da.ctypes.data,
                               None if su is None else su.ctypes.data, None if du is None else du.ctypes.data, who)
+
+    def notify_reset(self, who, last_reward=0.0, mask=None):
+        if mask is not None:
+            mask = np.ascontiguousarray(mask, dtype=np.uint8)
+        self._lib.orc_notify_reset(self._h, None if mask is None else mask.ctypes.data, who, float(last_reward))
 
     def stats_reset(self):
         self._lib.orc_stats_reset(self._h)

@@ -1,0 +1,207 @@
+"""GPU tests of the reference-shaped Python surface: CyberBattleEnv, the MARLon wrappers (driven exactly like the
+golden-tape generator drove the reference's), the batched universe / VecEnv adapter, half steps and sharding."""
+import numpy as np
+import pytest
+
+import helpers
+from marlon_b200 import _abi, config, scenario, scenarios
+
+pytestmark = pytest.mark.gpu
+
+SCALAR_KEYS = ["newly_discovered_nodes_count", "lateral_move", "customer_data_found", "probe_result", "escalation",
+               "credential_cache_length", "discovered_node_count"]
+
+
+def _check_cyber_obs(obs, z, s, t=0):
+    assert [int(obs[k]) for k in SCALAR_KEYS] == z["scalars"][s, t, :7].tolist()
+    assert np.array_equal(np.concatenate(obs["leaked_credentials"]), z["leaked"][s, t])
+    assert np.array_equal(np.concatenate(obs["credential_cache_matrix"]), z["cachem"][s, t])
+    assert np.array_equal(obs["discovered_nodes_properties"].reshape(-1), z["props"][s, t].astype(np.int32))
+    assert np.array_equal(obs["nodes_privilegelevel"], z["priv"][s, t].astype(np.int32))
+    am = obs["action_mask"]
+    assert np.array_equal(am["local_vulnerability"], z["local"][s, t])
+    assert helpers.crc_rows(am["remote_vulnerability"][None])[0] == z["remote_crc"][s, t]
+    assert helpers.crc_rows(am["connect"][None])[0] == z["connect_crc"][s, t]
+
+
+def test_cyberbattle_env_replays_the_reference_chain10_fixture():
+    """cyberbattle_env_test.py:43-114 through the gym-shaped CyberBattleEnv: same observations, rewards, done flag,
+    RuntimeError on the step after done."""
+    from marlon_b200 import cyberbattle_env as cbe
+
+    meta, z = helpers.load_tape("raw_chain10_fixture")
+    env = cbe.make("CyberBattleChain-v0", size=10, maximum_node_count=12, maximum_total_credentials=12,
+                   attacker_goal=cbe.AttackerGoal(own_atleast_percent=1.0))
+    assert env.name == "CyberBattleChain-10" and env.bounds.maximum_node_count == 12
+    obs, info = env.reset()
+    assert obs["discovered_node_count"] == 1 and info["step_count"] == 0
+    kinds = {0: "local_vulnerability", 1: "remote_vulnerability", 2: "connect"}
+    width = {0: 2, 1: 3, 2: 4}
+    for s in range(meta["steps"]):
+        a = z["action"][s, 0]
+        action = {kinds[int(a[0])]: a[1:1 + width[int(a[0])]]}
+        assert env.is_action_valid(action)
+        obs, reward, done, truncated, info = env.step(action)
+        assert reward == z["reward"][s, 0] and done == bool(z["terminated"][s, 0]) and truncated is False
+        assert info["step_count"] == z["stepcount"][s, 0]
+        _check_cyber_obs(obs, z, s)
+    assert done and reward == 5000.0
+    with pytest.raises(RuntimeError, match=r"new episode must be started with env\.reset\(\)"):
+        env.step({"connect": np.array([10, 5, 2, 4])})
+    env.reset()
+    a = env.sample_valid_action()
+    assert env.apply_mask(a)
+    env.close()
+
+
+def test_cyberbattle_env_invalid_actions():
+    from marlon_b200 import cyberbattle_env as cbe
+
+    env = cbe.make("CyberBattleToyCtf-v0", maximum_node_count=12, maximum_total_credentials=10)  # throws_on_invalid_actions=True
+    env.reset()
+    obs, r, done, _, _ = env.step({"local_vulnerability": np.array([5, 0])})  # OutOfBoundIndexError swallowed: blank observation
+    assert r == 0.0 and not done and (obs["discovered_nodes_properties"] == 2).all() and not obs["action_mask"]["connect"].any()
+    assert obs["discovered_node_count"] == 1
+    with pytest.raises(cbe.OutOfBoundIndexError):
+        env.is_node_owned(7)
+    env.step({"local_vulnerability": np.array([0, 2])})  # SearchEdgeHistory: discovers Website
+    with pytest.raises(ValueError, match="does not owned"):
+        env.step({"local_vulnerability": np.array([1, 0])})  # Website is discovered but not owned
+    env.close()
+
+
+@pytest.mark.parametrize("name", ["marlon_toyctf_short", "marlon_chain10_valid"])
+def test_wrappers_replay_reference_tape(name):
+    """AttackerEnvWrapper / DefenderEnvWrapper objects driven with the DummyVecEnv protocol the tape was recorded with."""
+    from marlon_b200 import cyberbattle_env as cbe
+    from marlon_b200.wrappers import AttackerEnvWrapper, DefenderEnvWrapper, EnvironmentEventSource
+
+    meta, z = helpers.load_tape(name)
+    kw = helpers._decode_kwargs(meta["env_kwargs"])
+    env = cbe.make(meta["env_id"], **kw)
+    es = EnvironmentEventSource()
+    att = AttackerEnvWrapper(env, es, **meta["att_kwargs"])
+    dfn = DefenderEnvWrapper(env, att, es, defender=True, **meta["def_kwargs"])
+    assert att.action_space.nvec.tolist() == meta["att_nvec"] and dfn.action_space.nvec.tolist() == meta["def_nvec"]
+    aobs, _ = att.reset()
+    dobs, _ = dfn.reset()
+    t = 0  # tape 0 of the file
+    for s in range(min(meta["steps"], 300)):
+        aobs, ar, aterm, atrunc, ainfo = att.step(z["att_action"][s, t])
+        assert abs(ar - z["att_reward"][s, t]) <= 1e-6 * max(1, abs(z["att_reward"][s, t])), (s, ar)
+        assert (aterm, atrunc) == (bool(z["att_terminated"][s, t]), bool(z["att_truncated"][s, t])), s
+        assert bool(ainfo.get("invalid_action", False)) == bool(z["intercepted"][s, t])
+        if aterm or atrunc:
+            aobs, _ = att.reset()
+        assert [aobs[k] for k in SCALAR_KEYS] == z["scalars"][s, t, :7].tolist(), s
+        assert np.array_equal(aobs["discovered_nodes_properties"], z["props"][s, t].astype(np.int32))
+        assert np.array_equal(aobs["local_vulnerability"], z["local"][s, t])
+        assert helpers.crc_rows(aobs["connect"][None])[0] == z["connect_crc"][s, t]
+        d_act = z["def_action"][s, t]
+        dobs, dr, dterm, dtrunc, _ = dfn.step([] if d_act[0] < 0 else d_act)
+        assert abs(dr - z["def_reward"][s, t]) <= 1e-6 * max(1, abs(z["def_reward"][s, t])), (s, dr)
+        assert (dterm, dtrunc) == (bool(z["def_terminated"][s, t]), bool(z["def_truncated"][s, t])), s
+        if dterm or dtrunc:
+            dobs, _ = dfn.reset()
+        assert np.array_equal(dobs["infected_nodes"], z["infected"][s, t])
+        assert np.array_equal(dobs["incoming_firewall_status"], z["fw_in"][s, t])
+        assert att.valid_action_count == z["digest"][s, t, 9] and att.invalid_action_count == z["digest"][s, t, 10]
+        assert att.reset_request == bool(z["digest"][s, t, 6]) and dfn.reset_request == bool(z["digest"][s, t, 7])
+    att.close()
+
+
+def test_half_steps_and_notify_match_oracle():
+    from marlon_b200.batch import Batch
+    from oracle import OracleBatch
+
+    comp = scenario.compile_scenario(scenarios.toyctf_environment())
+    cfg = config.make_config(_abi.MODE_MARLON, maximum_node_count=12, maximum_total_credentials=10, throws_on_invalid_actions=False,
+                             attacker_goal=config.AttackerGoal(own_atleast=6), defender_constraint=config.DefenderConstraint(0.6),
+                             losing_reward=-5000.0, defender_enabled=True, attacker_max_timesteps=40, defender_max_timesteps=30,
+                             auto_reset=False)
+    n = 300
+    b, o = Batch(comp, cfg, n), OracleBatch(comp, cfg, n)
+    rng = np.random.default_rng(5)
+    b.reset(); o.reset()
+    for s in range(120):
+        att, dfn = b.sample_actions(seed=9)
+        att, dfn = att.cpu().numpy(), dfn.cpu().numpy()
+        b.step(att, None, who=1); o.step(att, None, who=1)
+        adone = (o.arrays["att_terminated"] | o.arrays["att_truncated"]).astype(bool)
+        if adone.any():
+            b.reset(mask=adone, who=1); o.reset(mask=adone.astype(np.uint8), who=1)
+        b.step(None, dfn, who=2); o.step(None, dfn, who=2)
+        ddone = (o.arrays["def_terminated"] | o.arrays["def_truncated"]).astype(bool)
+        if ddone.any():
+            b.reset(mask=ddone, who=2); o.reset(mask=ddone.astype(np.uint8), who=2)
+        if s % 17 == 3:  # an outside notify_reset, as marl_algorithm.run_episode does for the defender
+            m = rng.random(n) < 0.1
+            b.notify_reset(2, 3.0, mask=m); o.notify_reset(2, 3.0, mask=m)
+        for k, t in b.tensors.items():
+            if not k.startswith("term_"):
+                assert np.array_equal(t.cpu().numpy(), o.arrays[k]), (s, k)
+        assert np.array_equal(b.export_state(), o.export_state()), s
+    b.close()
+
+
+def test_universe_and_vec_env_contract():
+    from marlon_b200.universe import MultiAgentUniversalEnv
+    from oracle import OracleBatch
+
+    n = 96
+    u = MultiAgentUniversalEnv("CyberBattleToyCtf-v0", n, maximum_node_count=12, maximum_total_credentials=10,
+                               max_timesteps=25, emit_terminal_obs=True)
+    o = OracleBatch(u.compiled, u.cfg, n)
+    o.reset()
+    av, dv = u.attacker_vec_env, u.defender_vec_env
+    assert av.num_envs == n and av.action_space.nvec.tolist() == [3, 12, 12, 7, 10, 12, 3, 12, 12, 8]
+    aobs, dobs = av.reset(), dv.reset()
+    assert aobs["connect"].shape == (n, 12, 12, 7, 10) and aobs["connect"].dtype == np.int8 and dobs["infected_nodes"].shape == (n, 10)
+    episodes = 0
+    for s in range(60):
+        att, dfn = u.sample_actions(seed=3)
+        att, dfn = att.cpu().numpy(), dfn.cpu().numpy()
+        aobs, ar, adone, ainfos = av.step(att)
+        dobs, dr, ddone, dinfos = dv.step(dfn)
+        o.step(att, dfn)
+        assert np.array_equal(ar, o.arrays["att_reward"]) and np.array_equal(dr, o.arrays["def_reward"])
+        assert np.array_equal(adone, (o.arrays["att_terminated"] | o.arrays["att_truncated"]).astype(bool))
+        assert np.array_equal(aobs["connect"], o.arrays["connect"]) and np.array_equal(dobs["infected_nodes"], o.arrays["def_infected_nodes"])
+        for i in np.nonzero(adone)[0]:
+            info = ainfos[i]
+            episodes += 1
+            assert set(info) >= {"TimeLimit.truncated", "episode", "terminal_observation"}
+            assert info["TimeLimit.truncated"] == bool(o.arrays["att_truncated"][i] and not o.arrays["att_terminated"][i])
+            assert info["episode"]["l"] >= 1 and info["terminal_observation"]["connect"].shape == (12, 12, 7, 10)
+            assert np.array_equal(info["terminal_observation"]["discovered_nodes_properties"], o.arrays["term_discovered_nodes_properties"][i])
+        assert all(ainfos[i] == {} for i in np.nonzero(~adone)[0])
+    assert episodes > 0
+    masks = av.env_method("action_masks")
+    assert len(masks) == n and masks[0].shape == (11268,) and masks[0].dtype == np.bool_
+    st = u.episode_statistics(reduce=True)
+    assert st["env_steps"] == n * 60 and st["episodes"] == episodes
+    u.close()
+
+
+def test_sharding_does_not_change_the_random_draws():
+    """env_index_base: envs [128, 256) of a 256-env run == a separate 128-env batch with base 128 (Philox keyed by global index)."""
+    from marlon_b200.batch import Batch
+
+    comp = scenario.compile_scenario(scenarios.toyctf_environment())
+
+    def cfg(base):
+        return config.make_config(_abi.MODE_CYBERBATTLE, maximum_node_count=12, maximum_total_credentials=10, throws_on_invalid_actions=False,
+                                  attacker_goal=config.AttackerGoal(own_atleast=6), seed=77, env_index_base=base,
+                                  defender_agent=config.ScanAndReimageCompromisedMachines(0.9, 3, 2),
+                                  defender_constraint=config.DefenderConstraint(0.5), auto_reset=True)
+
+    whole, part = Batch(comp, cfg(0), 256), Batch(comp, cfg(128), 128)
+    whole.reset(); part.reset()
+    for s in range(80):
+        att, _ = whole.sample_actions(seed=1)
+        whole.step(att)
+        part.step(att[128:].contiguous())
+    assert np.array_equal(whole.export_state(128, 256), part.export_state())
+    assert np.array_equal(whole.numpy("connect")[128:], part.numpy("connect"))
+    assert whole.export_state()[:, 13].sum() > 0  # some nodes are being re-imaged: the defender did act
+    whole.close(); part.close()
