@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- attacker+defender env-steps/sec of the batched step, against the HBM roofline.
 
-    python bench.py --gpus 1 --steps 50 --warmup 5
+    python bench.py --gpus 1 --steps 200 --warmup 10
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
     python bench.py --impl reference ...      # the CPU arm (oracle port of the reference step on the host cores)
@@ -69,7 +69,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -278,8 +278,11 @@ def run_ours(args):
     b.enable_timing(False)
 
     # ---- e2e: the same step through the public API with HOST action buffers and host-side results ----
-    h_a = tape_a[W:W + K].cpu().numpy()
-    h_d = tape_d[W:W + K].cpu().numpy()
+    # host action buffers in page-locked memory (what a host-side policy loop would hand over)
+    h_a = torch.empty((K, n, 10), dtype=torch.int32, pin_memory=True)
+    h_d = torch.empty((K, n, 12), dtype=torch.int32, pin_memory=True)
+    h_a.copy_(tape_a[W:W + K]); h_d.copy_(tape_d[W:W + K])
+    h_a, h_d = h_a.numpy(), h_d.numpy()
     b2 = Batch(comp, cfg, n, device=local)
     b2.reset()
     for s in range(W):
@@ -321,7 +324,8 @@ def run_ours(args):
                          "kernel": "cbx_step_kernel", "kernel_ms": kernel_ms, "kernel_launches_timed": kernel_n},
             "e2e": {"value": total_envs * K / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": n * (10 + 12) * 4,
                     "d2h_bytes_per_step": n * 12,
-                    "note": "cbx_batch_step_host: pinned H2D of actions, step, D2H of rewards + done flags; observations stay in HBM as torch tensors"},
+                    "note": "cbx_batch_step_host per step: H2D of this step's actions from page-locked host memory, the step kernel, "
+                            "D2H of rewards + done flags, stream sync; observations stay in HBM as torch tensors (consumers are GPU policies)"},
             "gpu_launches": launches,
             "clocks": clk,
             "episode_stats": {k: float(v) for k, v in zip(_abi.STAT_NAMES, stats.cpu().numpy())},
@@ -350,8 +354,8 @@ def _packed_state_words(comp, cfg):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=65536)
     ap.add_argument("--seed", type=int, default=2026)

@@ -139,10 +139,13 @@ class Batch:
         a = np.ascontiguousarray(attacker_actions, dtype=np.int32)
         d = None if defender_actions is None else np.ascontiguousarray(defender_actions, dtype=np.int32)
         n = self.n_envs
-        out = np.empty(n * 12, dtype=np.uint8)
+        if getattr(self, "_host_out", None) is None:  # page-locked result buffer, reused: D2H lands in it directly
+            self._host_out = self._torch.empty(n * 12, dtype=self._torch.uint8, pin_memory=True).numpy()
+        out = self._host_out
         with self._torch.cuda.device(self.device):
             _lib.check(self._L.cbx_batch_step_host(self._h, a.ctypes.data, None if d is None else d.ctypes.data,
                                                    out.ctypes.data, out.nbytes, self._stream()))
+        out = out.copy()
         return {
             "att_reward": out[: 4 * n].view(np.float32), "def_reward": out[4 * n: 8 * n].view(np.float32),
             "att_terminated": out[8 * n: 9 * n], "att_truncated": out[9 * n: 10 * n],

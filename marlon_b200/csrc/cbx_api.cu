@@ -488,16 +488,25 @@ int cbx_batch_step_host(cbx_batch* b, const int32_t* h_att, const int32_t* h_def
     CUDA_TRY(cudaMalloc((void**)&b->d_att, (size_t)n * 10 * 4));
     CUDA_TRY(cudaMalloc((void**)&b->d_def, (size_t)n * 12 * 4));
   }
-  memcpy(b->h_att, h_att, (size_t)n * aw * 4);
-  CUDA_TRY(cudaMemcpyAsync(b->d_att, b->h_att, (size_t)n * aw * 4, cudaMemcpyHostToDevice, st));
+  // caller buffers that are already page-locked go to the device directly; pageable ones through the pinned staging
+  auto is_pinned = [](const void* ptr) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+  };
+  const int32_t* src_att = h_att;
+  if (!is_pinned(h_att)) { memcpy(b->h_att, h_att, (size_t)n * aw * 4); src_att = b->h_att; }
+  CUDA_TRY(cudaMemcpyAsync(b->d_att, src_att, (size_t)n * aw * 4, cudaMemcpyHostToDevice, st));
   if (need_def) {
-    memcpy(b->h_def, h_def, (size_t)n * 12 * 4);
-    CUDA_TRY(cudaMemcpyAsync(b->d_def, b->h_def, (size_t)n * 12 * 4, cudaMemcpyHostToDevice, st));
+    const int32_t* src_def = h_def;
+    if (!is_pinned(h_def)) { memcpy(b->h_def, h_def, (size_t)n * 12 * 4); src_def = b->h_def; }
+    CUDA_TRY(cudaMemcpyAsync(b->d_def, src_def, (size_t)n * 12 * 4, cudaMemcpyHostToDevice, st));
   }
   int rc = cbx_batch_step(b, b->d_att, need_def ? b->d_def : nullptr, nullptr, cuda_stream);
   if (rc) return rc;
   const cbx_views& v = b->p.v;
-  uint8_t* o = b->h_out;
+  const bool out_pinned = is_pinned(host_out);
+  uint8_t* o = out_pinned ? (uint8_t*)host_out : b->h_out;
   CUDA_TRY(cudaMemcpyAsync(o, v.att_reward, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemcpyAsync(o + (size_t)n * 4, v.def_reward, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemcpyAsync(o + (size_t)n * 8, v.att_terminated, (size_t)n, cudaMemcpyDeviceToHost, st));
@@ -505,7 +514,7 @@ int cbx_batch_step_host(cbx_batch* b, const int32_t* h_att, const int32_t* h_def
   CUDA_TRY(cudaMemcpyAsync(o + (size_t)n * 10, v.def_terminated, (size_t)n, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemcpyAsync(o + (size_t)n * 11, v.def_truncated, (size_t)n, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
-  memcpy(host_out, o, out_bytes);
+  if (!out_pinned) memcpy(host_out, o, out_bytes);
   return CBX_OK;
 }
 
