@@ -266,6 +266,7 @@ int cbx_batch_create(const cbx_scenario* s, int64_t n_envs, const cbx_config* cf
   K.d_rowc = make_fastdiv(L.N * L.P * L.C); K.d_C = make_fastdiv(L.C); K.d_n = make_fastdiv(L.n);
   K.d_6n = make_fastdiv(6 * L.n); K.d_svc = make_fastdiv(L.nservices > 0 ? L.nservices : 1);
   K.desc_words = 8 + L.OW + L.Wn;
+  { const char* dbg = getenv("CBX_DEBUG_SKIP"); K.debug_skip = dbg ? atoi(dbg) : 0; }
   auto gcd16 = [](int x) { int g = 16; while (x % g) g >>= 1; return g; };
   {
     const int row_r = L.N * L.R, row_c = L.N * L.P * L.C;
@@ -279,17 +280,30 @@ int cbx_batch_create(const cbx_scenario* s, int64_t n_envs, const cbx_config* cf
            L.sz_local % 4 == 0;
     }
     K.warp_env = ok ? 1 : 0;
+    // statically specialised encoders for MARLon's canonical configurations (dense masks)
+    const char* nospec = getenv("CBX_NO_STATIC_DIMS");
+    if (ok && cfg->mask_mode == CBX_MASK_DENSE && !(nospec && nospec[0] == '1')) {
+      auto is = [&](int N, int Lv, int R, int P, int C, int props, int leak, int n, int svc) {
+        return L.N == N && L.L == Lv && L.R == R && L.P == P && L.C == C && L.nprops == props && L.LEAK == leak && L.n == n &&
+               L.nservices == svc;
+      };
+      if (is(12, 3, 8, 7, 10, 10, 5, 10, 13)) K.warp_env = 2;       // ToyCtf (12, 10)
+      else if (is(12, 5, 2, 8, 12, 14, 5, 12, 22)) K.warp_env = 3;  // Chain-10 (12, 12)
+    }
   }
   // shared-memory plan
   cbx_smem_plan& pl = b->p.plan;
   int o = 0;
   pl.tables = o; o = align_up(o + b->p.table_words + ((L.S + 3) & ~3), 32);
+  pl.lut = o; o = align_up(o + 512, 32);
+  pl.bars = o; o = align_up(o + 8, 32);
+  // one buffer set = {state tile, staging, descriptors, actions}; the pipelined loop uses two of them
+  const int set0 = o;
   pl.state = o; o = align_up(o + L.S * CBX_TILE, 32);
   pl.stage = o; o = align_up(o + L.G * CBX_TILE, 32);
   pl.desc = o; o = align_up(o + K.desc_words * CBX_TILE, 32);
   pl.acts = o; o = align_up(o + 22 * CBX_TILE, 32);
-  pl.lut = o; o = align_up(o + 512, 32);
-  pl.bars = o; o += 8;
+  pl.buf_stride = o - set0;
   pl.total_bytes = o * 4;
   b->smem_bytes = pl.total_bytes;
   if (b->smem_bytes > 227 * 1024) {
@@ -550,14 +564,17 @@ int cbx_batch_export_state(cbx_batch* b, int64_t begin, int64_t end, int32_t* ou
   cudaStream_t st = (cudaStream_t)cuda_stream;
   const cbx_layout& L = b->p.lay;
   const int64_t m = end - begin;
-  std::vector<uint32_t> raw((size_t)L.S * m);
+  // state is a tiled structure of arrays: tile t holds words [S][CBX_TILE] contiguously
+  const int64_t t0 = begin / CBX_TILE, t1 = (end + CBX_TILE - 1) / CBX_TILE;
+  std::vector<uint32_t> raw((size_t)(t1 - t0) * L.S * CBX_TILE);
   CUDA_TRY(cudaStreamSynchronize(st));
-  CUDA_TRY(cudaMemcpy2D(raw.data(), (size_t)m * 4, b->p.state + begin, (size_t)b->p.n_pad * 4, (size_t)m * 4, (size_t)L.S, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(raw.data(), b->p.state + t0 * L.S * CBX_TILE, raw.size() * 4, cudaMemcpyDeviceToHost));
   const int n = L.n;
   const int64_t W = cbx_export_words(b->scn, &b->p.cfg);
   const bool def = b->p.cfg.mode == CBX_MODE_MARLON && b->p.cfg.def_enabled;
   for (int64_t i = 0; i < m; ++i) {
-    auto w = [&](int off) { return raw[(size_t)off * m + i]; };
+    const int64_t ge = begin + i;
+    auto w = [&](int off) { return raw[(size_t)((ge / CBX_TILE - t0) * L.S + off) * CBX_TILE + (size_t)(ge % CBX_TILE)]; };
     auto byte = [&](int off, int k) { return (w(off + k / 4) >> ((k & 3) * 8)) & 0xFFu; };
     auto bit = [&](int off, int k) { return (w(off + k / 32) >> (k & 31)) & 1u; };
     int32_t* x = out + i * W;

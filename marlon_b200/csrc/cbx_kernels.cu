@@ -368,18 +368,103 @@ __device__ __forceinline__ void warp_rowmask_dispatch(int unit, int8_t* envdst, 
   else warp_rowmask_u<4, CONNECT>(envdst, row_len, N, C, dC, de, lut, lane);
 }
 
-__device__ void encode_attacker_by_warp(const Tile& t, const Target& o, int n_valid, const EnvMask& enc_mask) {
+// ---- compile-time dimension sets ---------------------------------------------------------------------------------------
+// The encoder's loop bounds are the scenario / bounds dimensions.  For MARLon's canonical configurations they are baked in
+// at compile time (every row loop unrolls to bare stores with immediate offsets); DimsDyn reads them from the layout.
+struct DimsDyn {
+  static constexpr bool kStatic = false;
+  static constexpr int N = 0, L = 0, R = 0, P = 0, C = 0, NPROPS = 0, LEAK = 0, NN = 0, NSVC = 0;
+};
+template <int N_, int L_, int R_, int P_, int C_, int NPROPS_, int LEAK_, int NN_, int NSVC_>
+struct DimsStatic {
+  static constexpr bool kStatic = true;
+  static constexpr int N = N_, L = L_, R = R_, P = P_, C = C_, NPROPS = NPROPS_, LEAK = LEAK_, NN = NN_, NSVC = NSVC_;
+};
+// ToyCtf with MARLon's bounds (ppo/train_marl.py:12-14: 12 nodes, 10 credentials): 7 ports, 3 local / 8 remote ids, 10 props
+typedef DimsStatic<12, 3, 8, 7, 10, 10, 5, 10, 13> DimsToyCtf;
+// Chain size 10 at (12, 12): 8 ports, 5 local / 2 remote ids, 14 properties, 12 nodes, 22 services
+typedef DimsStatic<12, 5, 2, 8, 12, 14, 5, 12, 22> DimsChain10;
+#define CBX_DIM(D, name, dyn) (D::kStatic ? (int)D::name : (int)(dyn))
+
+// Static-dimension row masks: everything but the env's counts and owned bits is a compile-time constant.
+template <class D, bool CONNECT>
+__device__ __forceinline__ void rowmask_static(int8_t* envdst, const uint32_t* desc_e, const uint2* lut, int lane) {
+  constexpr int ROW = CONNECT ? D::N * D::P * D::C : D::N * D::R;
+  constexpr int U = (ROW % 16 == 0) ? 16 : (ROW % 8 == 0) ? 8 : 4;
+  constexpr int GPR = ROW / U;
+  constexpr int C = CONNECT ? D::C : 1;
+  typedef typename Gran<U>::T G;
+  const int lim = (int)(CONNECT ? desc_e[D_LIMC] : desc_e[D_LIMR]);
+  const int nc = (int)desc_e[D_NC];
+  const uint64_t base = ((uint64_t)desc_e[D_BHI] << 32) | desc_e[D_BLO];
+  const uint32_t ow = desc_e[D_OWNED];  // D::N <= 32
+  auto granule = [&](int g) -> G {
+    const int w = g * U;
+    uint32_t m = lowmask(min(max(lim - w, 0), U));
+    if (CONNECT) {
+      const int ph = w % C;
+      uint32_t pm;
+      if (C <= 48) pm = (uint32_t)(base >> ph) & 0xFFFFu;
+      else pm = lowmask(min(max(nc - ph, 0), 16)) | (lowmask(min(max(C - ph + nc, 0), 16)) & ~lowmask(min(max(C - ph, 0), 16)));
+      m &= pm;
+    }
+    return Gran<U>::expand(m, lut);
+  };
+  if constexpr (GPR <= 16) {
+    constexpr int RPI = 32 / GPR;
+    const int r = lane / GPR, g = lane - r * GPR;
+    const G tm = granule(g);
+    G* p = reinterpret_cast<G*>(envdst) + lane;
+    if (r < RPI) {
+#pragma unroll
+      for (int s0 = 0; s0 < D::N; s0 += RPI) {
+        const int s = s0 + r;
+        if (s < D::N) st_out(p + s0 * GPR, ((ow >> s) & 1u) ? tm : Gran<U>::zero());
+      }
+    }
+  } else {
+    constexpr int NG = (GPR + 31) / 32;
+    G tm[NG];
+#pragma unroll
+    for (int k = 0; k < NG; ++k) tm[k] = granule(lane + 32 * k);
+    G* p = reinterpret_cast<G*>(envdst) + lane;
+#pragma unroll
+    for (int s = 0; s < D::N; ++s) {
+      if ((ow >> s) & 1u) {  // warp-uniform
+#pragma unroll
+        for (int k = 0; k < NG; ++k)
+          if (32 * k + 32 <= GPR || lane + 32 * k < GPR) st_out(p + s * GPR + 32 * k, tm[k]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < NG; ++k)
+          if (32 * k + 32 <= GPR || lane + 32 * k < GPR) st_out(p + s * GPR + 32 * k, Gran<U>::zero());
+      }
+    }
+  }
+}
+
+// (wid, nw): this warp's index within the group of warps that share the tile's encoding, and the size of that group
+template <class D>
+__device__ __forceinline__ void encode_attacker_by_warp(const Tile& t, const Target& o, int n_valid, const EnvMask& enc_mask,
+                                                        int wid, int nw) {
   const cbx_layout* L = t.L;
   const cbx_enc_consts& K = *t.K;
   const int lane = threadIdx.x & 31;
-  for (int e = threadIdx.x >> 5; e < n_valid; e += CBX_THREADS / 32) {
+  const int N = CBX_DIM(D, N, L->N), NL = CBX_DIM(D, L, L->L), NR = CBX_DIM(D, R, L->R), NP = CBX_DIM(D, P, L->P);
+  const int NC = CBX_DIM(D, C, L->C), NPROPS = CBX_DIM(D, NPROPS, L->nprops), LEAK = CBX_DIM(D, LEAK, L->LEAK);
+  const int PW = D::kStatic ? (D::NPROPS + 31) / 32 : L->PW;
+  for (int e = wid; e < n_valid; e += nw) {
     if (!enc_mask.test((int)e)) continue;
     const uint32_t* de = t.desc + e * t.DW;
     const uint32_t nd = de[D_ND], nc = de[D_NC];
     const bool blank = de[D_KIND] == OBS_BLANK;
+    const int skip = K.debug_skip;
+    if (!(skip & 1)) {
     if (lane < 8) st_out(o.scalars + e * 8 + lane, (int32_t)t.g(e, STG_SCALARS + lane));
-    for (int w = lane; w < 4 * L->LEAK; w += 32) st_out(o.leaked + e * 4 * L->LEAK + w, (int32_t)t.g(e, L->g_leaked + w));
-    for (int w = lane; w < 2 * L->C; w += 32) {
+#pragma unroll
+    for (int w = lane; w < 4 * LEAK; w += 32) st_out(o.leaked + e * 4 * LEAK + w, (int32_t)t.g(e, L->g_leaked + w));
+#pragma unroll
+    for (int w = lane; w < 2 * NC; w += 32) {
       const int c = w >> 1;
       uint32_t val = 0;
       if (!blank && c < (int)nc) {
@@ -387,73 +472,100 @@ __device__ void encode_attacker_by_warp(const Tile& t, const Target& o, int n_va
         const uint32_t* rec = t.tb + t.tb[CBX_H_OFF_TRIPLE] + 3 * tr;
         val = (w & 1) ? rec[1] : t.byte(e, L->o_disc_idx, (int)rec[0]);
       }
-      st_out(o.cachem + e * 2 * L->C + w, (int32_t)val);
+      st_out(o.cachem + e * 2 * NC + w, (int32_t)val);
     }
-    const int npw = L->N * L->nprops;
+    const int npw = N * NPROPS;
+#pragma unroll
     for (int w = lane; w < npw; w += 32) {
       uint32_t val = 2u;
       if (!blank) {
-        uint32_t k = FastDiv(K.d_nprops).div((uint32_t)w), pi = w - k * L->nprops;
+        uint32_t k = D::kStatic ? (uint32_t)w / (uint32_t)(D::kStatic ? D::NPROPS : 1) : FastDiv(K.d_nprops).div((uint32_t)w);
+        uint32_t pi = w - k * NPROPS;
         val = 0u;
         if (k < nd) {
           uint32_t node = t.byte(e, L->o_disc_order, (int)k);
-          val = (t.w(e, L->o_props + node * L->PW + (pi >> 5)) >> (pi & 31)) & 1u;
+          val = (t.w(e, L->o_props + node * PW + (pi >> 5)) >> (pi & 31)) & 1u;
         }
       }
       st_out(o.props + e * npw + w, (int32_t)val);
     }
-    for (int w = lane; w < L->N; w += 32) {
+#pragma unroll
+    for (int w = lane; w < N; w += 32) {
       uint32_t val = 0;
       if (!blank && w < (int)nd) {
         uint32_t node = t.byte(e, L->o_disc_order, w);
         val = (t.g(e, L->g_priv + (node >> 4)) >> ((node & 15) * 2)) & 3u;
       }
-      st_out(o.priv + e * L->N + w, (int32_t)val);
+      st_out(o.priv + e * N + w, (int32_t)val);
+    }
     }
     if (o.local) {
-      int8_t* dst = o.local + (size_t)e * L->sz_local;
-      for (int q = lane; q < L->sz_local / 4; q += 32) {  // fast path guarantees sz_local % 4 == 0
+      const int sz_local = N * NL;
+      if (!(skip & 2)) {
+      int8_t* dst = o.local + (size_t)e * sz_local;
+#pragma unroll
+      for (int q = lane; q < sz_local / 4; q += 32) {  // fast path guarantees sz_local % 4 == 0
         uint32_t word = 0;
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-          uint32_t i = q * 4 + b, s = FastDiv(K.d_L).div(i), v = i - s * L->L;
+          uint32_t i = q * 4 + b;
+          uint32_t s = D::kStatic ? i / (uint32_t)(D::kStatic ? D::L : 1) : FastDiv(K.d_L).div(i);
+          uint32_t v = i - s * NL;
           if ((de[D_OWNED + (s >> 5)] >> (s & 31)) & 1u) {
             uint32_t node = t.byte(e, L->o_disc_order, (int)s);
-            word |= (t.tb[t.tb[CBX_H_OFF_VULN] + (node * (L->L + L->R) + v) * CBX_VULN_WORDS] & 1u) << (8 * b);
+            word |= (t.tb[t.tb[CBX_H_OFF_VULN] + (node * (NL + NR) + v) * CBX_VULN_WORDS] & 1u) << (8 * b);
           }
         }
         st_out(reinterpret_cast<uint32_t*>(dst) + q, word);
       }
-      warp_rowmask_dispatch<false>(K.tmpl_unit_r, o.remote + (size_t)e * L->sz_remote, L->N * L->R, L->N, 1, cbx_fastdiv{0u, 0u}, de, t.lut, lane);
-      warp_rowmask_dispatch<true>(K.tmpl_unit_c, o.connect + (size_t)e * L->sz_connect, L->N * L->P * L->C, L->N, L->C, K.d_C, de, t.lut, lane);
+      }
+      if constexpr (D::kStatic) {
+        if (!(skip & 4)) rowmask_static<D, false>(o.remote + (size_t)e * (D::N * D::N * D::R), de, t.lut, lane);
+        if (!(skip & 8)) rowmask_static<D, true>(o.connect + (size_t)e * (D::N * D::N * D::P * D::C), de, t.lut, lane);
+      } else {
+        warp_rowmask_dispatch<false>(K.tmpl_unit_r, o.remote + (size_t)e * L->sz_remote, N * NR, N, 1, cbx_fastdiv{0u, 0u}, de, t.lut, lane);
+        warp_rowmask_dispatch<true>(K.tmpl_unit_c, o.connect + (size_t)e * L->sz_connect, N * NP * NC, N, NC, K.d_C, de, t.lut, lane);
+      }
     }
   }
 }
 
-__device__ void encode_defender_by_warp(const Tile& t, const Target& o, int n_valid, const EnvMask& enc_mask, bool static_too) {
+template <class D>
+__device__ __forceinline__ void encode_defender_by_warp(const Tile& t, const Target& o, int n_valid, const EnvMask& enc_mask,
+                                                        bool static_too, int wid, int nw) {
   const cbx_layout* L = t.L;
   const int lane = threadIdx.x & 31;
-  for (int e = threadIdx.x >> 5; e < n_valid; e += CBX_THREADS / 32) {
+  const int n = CBX_DIM(D, NN, L->n), nsvc = CBX_DIM(D, NSVC, L->nservices);
+  const int OW = D::kStatic ? (D::N + 31) / 32 : L->OW;
+  for (int e = wid; e < n_valid; e += nw) {
     if (!enc_mask.test((int)e)) continue;
-    const uint32_t* di = t.desc + e * t.DW + D_OWNED + L->OW;
-    for (int i = lane; i < L->n; i += 32) o.infected[(size_t)e * L->n + i] = (int8_t)((di[i >> 5] >> (i & 31)) & 1u);
+    const uint32_t* di = t.desc + e * t.DW + D_OWNED + OW;
+    if (t.K->debug_skip & 16) continue;
+#pragma unroll
+    for (int i = lane; i < n; i += 32) o.infected[(size_t)e * n + i] = (int8_t)((di[i >> 5] >> (i & 31)) & 1u);
     if (!static_too) continue;
-    for (int i = lane; i < 6 * L->n; i += 32) {
+#pragma unroll
+    for (int i = lane; i < 6 * n; i += 32) {
       const int node = i / 6, r = i - node * 6;
       const uint32_t dob = t.tb[t.tb[CBX_H_OFF_NODE] + node * CBX_NODE_WORDS + CBX_N_DEFOBS];
-      o.fw_in[(size_t)e * 6 * L->n + i] = (int8_t)((dob >> r) & 1u);
-      o.fw_out[(size_t)e * 6 * L->n + i] = (int8_t)((dob >> (8 + r)) & 1u);
+      o.fw_in[(size_t)e * 6 * n + i] = (int8_t)((dob >> r) & 1u);
+      o.fw_out[(size_t)e * 6 * n + i] = (int8_t)((dob >> (8 + r)) & 1u);
     }
-    for (int i = lane; i < L->nservices; i += 32) o.services[(size_t)e * L->nservices + i] = 1;
+#pragma unroll
+    for (int i = lane; i < nsvc; i += 32) o.services[(size_t)e * nsvc + i] = 1;
   }
 }
 
 // Encode the attacker observation of the envs selected by enc_mask (bit e = env e of the tile).
-template <bool FAST>
-__device__ __forceinline__ void encode_attacker(const Tile& t, const Target& o, int n_valid, const EnvMask& enc_mask) {
+// ENC: 0 generic flat encoder | 1 warp-per-env, runtime dimensions | 2 warp-per-env ToyCtf(12,10) | 3 warp-per-env Chain-10(12,12)
+template <int ENC>
+__device__ __forceinline__ void encode_attacker(const Tile& t, const Target& o, int n_valid, const EnvMask& enc_mask,
+                                                int wid = threadIdx.x >> 5, int nw = CBX_THREADS / 32) {
   const cbx_layout* L = t.L;
   const cbx_enc_consts& K = *t.K;
-  if (FAST) { encode_attacker_by_warp(t, o, n_valid, enc_mask); return; }
+  if (ENC == 1) { encode_attacker_by_warp<DimsDyn>(t, o, n_valid, enc_mask, wid, nw); return; }
+  if (ENC == 2) { encode_attacker_by_warp<DimsToyCtf>(t, o, n_valid, enc_mask, wid, nw); return; }
+  if (ENC == 3) { encode_attacker_by_warp<DimsChain10>(t, o, n_valid, enc_mask, wid, nw); return; }
   write_i32(o.scalars, 8, FastDiv(0u, 3u), n_valid, enc_mask, [&](int e, int wi) { return t.g(e, STG_SCALARS + wi); });
   write_i32(o.leaked, 4 * L->LEAK, K.d_leaked, n_valid, enc_mask, [&](int e, int wi) { return t.g(e, L->g_leaked + wi); });
   write_i32(o.cachem, 2 * L->C, K.d_cachem, n_valid, enc_mask, [&](int e, int wi) -> uint32_t {
@@ -485,11 +597,14 @@ __device__ __forceinline__ void encode_attacker(const Tile& t, const Target& o, 
   write_rowmask<true>(o.connect, L->sz_connect, K.d_connect, L->N * L->P * L->C, K.d_rowc, L->C, K.d_C, n_valid, enc_mask, t);
 }
 
-template <bool FAST>
-__device__ __forceinline__ void encode_defender(const Tile& t, const Target& o, int n_valid, const EnvMask& enc_mask, bool static_too) {
+template <int ENC>
+__device__ __forceinline__ void encode_defender(const Tile& t, const Target& o, int n_valid, const EnvMask& enc_mask, bool static_too,
+                                                int wid = threadIdx.x >> 5, int nw = CBX_THREADS / 32) {
   const cbx_layout* L = t.L;
   const cbx_enc_consts& K = *t.K;
-  if (FAST) { encode_defender_by_warp(t, o, n_valid, enc_mask, static_too); return; }
+  if (ENC == 1) { encode_defender_by_warp<DimsDyn>(t, o, n_valid, enc_mask, static_too, wid, nw); return; }
+  if (ENC == 2) { encode_defender_by_warp<DimsToyCtf>(t, o, n_valid, enc_mask, static_too, wid, nw); return; }
+  if (ENC == 3) { encode_defender_by_warp<DimsChain10>(t, o, n_valid, enc_mask, static_too, wid, nw); return; }
   write_i8(o.infected, L->n, K.d_n, n_valid, enc_mask,
            [&](int e, int i) -> uint32_t { return (t.d(e, D_OWNED + L->OW + (i >> 5)) >> (i & 31)) & 1u; });
   if (!static_too) return;
@@ -505,13 +620,14 @@ __device__ __forceinline__ void encode_defender(const Tile& t, const Target& o, 
 }
 
 // copy env rows main -> terminal buffers (terminal observation of an intercepted-and-truncated step is the previous one)
-__device__ void copy_rows(void* dst, const void* src, int bpe, int n_valid, const EnvMask& mask) {
+__device__ void copy_rows(void* dst, const void* src, int bpe, int n_valid, const EnvMask& mask, int tidx = threadIdx.x,
+                          int nthreads = CBX_THREADS) {
   if (!dst || !src || bpe == 0) return;
   for (int e = 0; e < n_valid; ++e) {
     if (!mask.test(e)) continue;
     const uint8_t* s = (const uint8_t*)src + (size_t)e * bpe;
     uint8_t* d = (uint8_t*)dst + (size_t)e * bpe;
-    for (int k = threadIdx.x; k < bpe; k += CBX_THREADS) d[k] = s[k];
+    for (int k = tidx; k < bpe; k += nthreads) d[k] = s[k];
   }
 }
 
@@ -717,7 +833,7 @@ __device__ void cyber_only_step(const Ctx& c, const cbx_params& p, const int32_t
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------------------------------
-template <bool USE_TMA, bool FAST>
+template <bool USE_TMA, int ENC>
 __global__ void __launch_bounds__(CBX_THREADS, CBX_MIN_CTAS) cbx_step_kernel(const __grid_constant__ cbx_params p, const int op) {
   extern __shared__ __align__(128) uint32_t smem[];
   const cbx_layout& L = p.lay;
@@ -783,13 +899,14 @@ __global__ void __launch_bounds__(CBX_THREADS, CBX_MIN_CTAS) cbx_step_kernel(con
     // ---- (0) stage the state tile (S rows of CBX_TILE words) and the tile's actions ----
     if (USE_TMA) {
       if (tid < 32) {
-        if (tid == 0) mbar_expect_tx(&bars[1], (uint32_t)L.S * kRowBytes);
-        __syncwarp();
-        for (int r = tid; r < L.S; r += 32) tma_load_1d(s_st + r * CBX_TILE, p.state + (int64_t)r * p.n_pad + e0, kRowBytes, &bars[1]);
+        if (tid == 0) {  // the tile's state is one contiguous block (tiled structure of arrays): a single bulk copy
+          mbar_expect_tx(&bars[1], (uint32_t)L.S * kRowBytes);
+          tma_load_1d(s_st, p.state + (int64_t)tile * L.S * CBX_TILE, (uint32_t)L.S * kRowBytes, &bars[1]);
+        }
       }
     } else {
       for (int k = tid; k < L.S * CBX_TILE; k += CBX_THREADS)
-        s_st[k] = p.state[(int64_t)(k / CBX_TILE) * p.n_pad + e0 + (k % CBX_TILE)];
+        s_st[k] = p.state[(int64_t)tile * L.S * CBX_TILE + k];
     }
     if (!reset_only) {  // coalesced: the tile's actions are contiguous in the [n, width] action arrays
       if (p.att_actions && (who_att || !marlon))
@@ -863,7 +980,7 @@ __global__ void __launch_bounds__(CBX_THREADS, CBX_MIN_CTAS) cbx_step_kernel(con
       if (tid < CBX_TILE && active && att_done_mask.test(tid)) build_desc(c, s_desc + tid * DW, DW, nullptr);
       __syncthreads();
       Target tt = make_target(p.v, L, e0, true);
-      encode_attacker<FAST>(t, tt, n_valid, mask_and_not(att_done_mask, keep1));
+      encode_attacker<ENC>(t, tt, n_valid, mask_and_not(att_done_mask, keep1));
       const EnvMask cp = mask_and(att_done_mask, keep1);
       if (cp.any()) {
         Target tm = make_target(p.v, L, e0, false);
@@ -915,9 +1032,9 @@ __global__ void __launch_bounds__(CBX_THREADS, CBX_MIN_CTAS) cbx_step_kernel(con
     // ---- (3) encode ----
     {
       Target tm = make_target(p.v, L, e0, false);
-      encode_attacker<FAST>(t, tm, n_valid, enc_mask);
+      encode_attacker<ENC>(t, tm, n_valid, enc_mask);
       if (marlon && cfg.def_enabled && who_def && !(op & CBX_OP_NOTIFY)) {
-        encode_defender<FAST>(t, tm, n_valid, mask_all(), true);
+        encode_defender<ENC>(t, tm, n_valid, mask_all(), true);
         if (def_done_mask.any() && cfg.emit_terminal_obs) {
           // terminal defender observation = infected nodes seen by the step that ended the episode
           __syncthreads();
@@ -925,7 +1042,7 @@ __global__ void __launch_bounds__(CBX_THREADS, CBX_MIN_CTAS) cbx_step_kernel(con
             for (int k = 0; k < L.Wn; ++k) s_desc[tid * DW + D_OWNED + L.OW + k] = c.g(STG_DEF_TERM_INST + k);
           __syncthreads();
           Target tt = make_target(p.v, L, e0, true);
-          encode_defender<FAST>(t, tt, n_valid, def_done_mask, false);
+          encode_defender<ENC>(t, tt, n_valid, def_done_mask, false);
         }
       }
     }
@@ -939,7 +1056,7 @@ __global__ void __launch_bounds__(CBX_THREADS, CBX_MIN_CTAS) cbx_step_kernel(con
       fence_async_smem();
       __syncthreads();
       if (tid < 32) {
-        for (int r = tid; r < L.S; r += 32) tma_store_1d(p.state + (int64_t)r * p.n_pad + e0, s_st + r * CBX_TILE, kRowBytes);
+        if (tid == 0) tma_store_1d(p.state + (int64_t)tile * L.S * CBX_TILE, s_st, (uint32_t)L.S * kRowBytes);
         tma_store_commit();
         tma_store_wait_read();  // the tile buffer is reused by the next iteration
       }
@@ -947,7 +1064,7 @@ __global__ void __launch_bounds__(CBX_THREADS, CBX_MIN_CTAS) cbx_step_kernel(con
     } else {
       __syncthreads();
       for (int k = tid; k < L.S * CBX_TILE; k += CBX_THREADS)
-        p.state[(int64_t)(k / CBX_TILE) * p.n_pad + e0 + (k % CBX_TILE)] = s_st[k];
+        p.state[(int64_t)tile * L.S * CBX_TILE + k] = s_st[k];
       __syncthreads();
     }
     CBX_PROF(6)  // state write-back
@@ -971,7 +1088,7 @@ __global__ void cbx_sample_kernel(const __grid_constant__ cbx_params p, int32_t*
   const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= p.n_envs) return;
   const cbx_layout& L = p.lay;
-  auto W = [&](int off) { return p.state[(int64_t)off * p.n_pad + env]; };
+  auto W = [&](int off) { return p.state[((env / CBX_TILE) * L.S + off) * CBX_TILE + (env % CBX_TILE)]; };
   uint32_t r[4];
   philox4x32_10((uint32_t)env, (uint32_t)(env >> 32), step, 0x5A17u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
   uint32_t r2[4];
@@ -1041,19 +1158,26 @@ __global__ void cbx_sample_kernel(const __grid_constant__ cbx_params p, int32_t*
 }  // namespace cbx
 
 // ---- launch helpers used by cbx_api.cu ------------------------------------------------------------------------------------
-template <bool A, bool B>
+template <bool A, int B>
 static cudaError_t attrs_of(int smem_bytes, int* blocks_per_sm) {
   cudaError_t e = cudaFuncSetAttribute(cbx::cbx_step_kernel<A, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   if (e != cudaSuccess) return e;
   return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, cbx::cbx_step_kernel<A, B>, CBX_THREADS, smem_bytes);
 }
 extern "C" {
+// enc: encoder variant (cbx_enc_consts.warp_env): 0 generic, 1 warp-per-env, 2 ToyCtf(12,10) static, 3 Chain-10(12,12) static.
+// The statically specialised variants exist with TMA staging only.
 cudaError_t cbx_launch_step(const cbx_params* p, int op, int grid, int smem_bytes, int use_tma, cudaStream_t stream) {
-  const bool fast = p->enc.warp_env;
-  if (use_tma && fast) cbx::cbx_step_kernel<true, true><<<grid, CBX_THREADS, smem_bytes, stream>>>(*p, op);
-  else if (use_tma) cbx::cbx_step_kernel<true, false><<<grid, CBX_THREADS, smem_bytes, stream>>>(*p, op);
-  else if (fast) cbx::cbx_step_kernel<false, true><<<grid, CBX_THREADS, smem_bytes, stream>>>(*p, op);
-  else cbx::cbx_step_kernel<false, false><<<grid, CBX_THREADS, smem_bytes, stream>>>(*p, op);
+  const int enc = p->enc.warp_env;
+  if (use_tma) {
+    switch (enc) {
+      case 3: cbx::cbx_step_kernel<true, 3><<<grid, CBX_THREADS, smem_bytes, stream>>>(*p, op); break;
+      case 2: cbx::cbx_step_kernel<true, 2><<<grid, CBX_THREADS, smem_bytes, stream>>>(*p, op); break;
+      case 1: cbx::cbx_step_kernel<true, 1><<<grid, CBX_THREADS, smem_bytes, stream>>>(*p, op); break;
+      default: cbx::cbx_step_kernel<true, 0><<<grid, CBX_THREADS, smem_bytes, stream>>>(*p, op); break;
+    }
+  } else if (enc >= 1) cbx::cbx_step_kernel<false, 1><<<grid, CBX_THREADS, smem_bytes, stream>>>(*p, op);
+  else cbx::cbx_step_kernel<false, 0><<<grid, CBX_THREADS, smem_bytes, stream>>>(*p, op);
   return cudaGetLastError();
 }
 cudaError_t cbx_launch_sample(const cbx_params* p, int32_t* att, int32_t* def, uint64_t seed, uint32_t step, cudaStream_t stream) {
@@ -1062,10 +1186,16 @@ cudaError_t cbx_launch_sample(const cbx_params* p, int32_t* att, int32_t* def, u
   cbx::cbx_sample_kernel<<<grid, threads, 0, stream>>>(*p, att, def, seed, step);
   return cudaGetLastError();
 }
-cudaError_t cbx_kernel_attrs(int smem_bytes, int use_tma, int fast, int* blocks_per_sm) {
-  if (use_tma && fast) return attrs_of<true, true>(smem_bytes, blocks_per_sm);
-  if (use_tma) return attrs_of<true, false>(smem_bytes, blocks_per_sm);
-  if (fast) return attrs_of<false, true>(smem_bytes, blocks_per_sm);
-  return attrs_of<false, false>(smem_bytes, blocks_per_sm);
+cudaError_t cbx_kernel_attrs(int smem_bytes, int use_tma, int enc, int* blocks_per_sm) {
+  if (use_tma) {
+    switch (enc) {
+      case 3: return attrs_of<true, 3>(smem_bytes, blocks_per_sm);
+      case 2: return attrs_of<true, 2>(smem_bytes, blocks_per_sm);
+      case 1: return attrs_of<true, 1>(smem_bytes, blocks_per_sm);
+      default: return attrs_of<true, 0>(smem_bytes, blocks_per_sm);
+    }
+  }
+  if (enc >= 1) return attrs_of<false, 1>(smem_bytes, blocks_per_sm);
+  return attrs_of<false, 0>(smem_bytes, blocks_per_sm);
 }
 }

@@ -1,8 +1,8 @@
 // cbx_layout.h -- HBM data layout of a batch and the parameter block of the kernels (host + device).
 //
-// Per-env dynamic state is a structure of arrays of 32-bit words: word w of env e lives at
-// state[w * n_pad + e], so a tile of 32 consecutive envs is S rows of 128 contiguous bytes (one row per
-// state word).  A CTA stages the S x 32 tile in shared memory (row-major, i.e. word-major / env-minor: thread
+// Per-env dynamic state is a TILED structure of arrays of 32-bit words: word w of env e lives at
+// state[((e / 32) * S + w) * 32 + e % 32], so the state of a tile of 32 consecutive envs is one contiguous block of
+// S rows of 128 bytes (one row per state word) that moves with a single TMA bulk copy in each direction.  A CTA stages the S x 32 tile in shared memory (row-major, i.e. word-major / env-minor: thread
 // e touching word w hits bank e -- conflict-free for the one-thread-per-env game logic), plays the step on it
 // and streams it back.  What replaces the reference's Python objects:
 //   discovered order + inverse map, agent_installed / ever_owned / not-running bitsets, 2-bit privilege levels,
@@ -84,12 +84,14 @@ struct cbx_enc_consts {  // divisors of the encoder, fixed per batch
   int desc_words;
   // warp-per-env fast path: every row of an env's remote / connect mask is either all zero or one and the same byte
   // string; a warp keeps that string in registers and stores it row by row
-  int warp_env;                      // 1: fast path usable for this batch's dimensions
+  int warp_env;                      // encoder variant: 0 generic, 1 warp-per-env, 2/3 statically specialised
+  int debug_skip;                    // experiments only (env CBX_DEBUG_SKIP): bit0 small fields, 1 local, 2 remote, 3 connect, 4 defender
   int tmpl_unit_r, tmpl_unit_c;      // store granule in bytes: gcd(row length, 16)
 };
 
 struct cbx_smem_plan {  // shared-memory carve-up in 32-bit words
   int tables, state, stage, desc, acts, lut, bars, total_bytes;
+  int buf_stride;  // words between the two buffer sets {state, stage, desc, acts} of the pipelined tile loop
 };
 
 struct cbx_params {
