@@ -189,7 +189,10 @@ class Batch:
         _lib.check(self._L.cbx_batch_step_kernel_ms(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
-    PHASES = ["prologue", "state_load", "attacker_logic", "terminal_obs", "defender_logic_desc", "encode", "state_store"]
+    # slots 0-6: fused kernel (thread 0 of every CTA); slots 8-12: pipelined kernel (lane 0 of every logic / encoder warp)
+    PHASES = ["prologue", "state_load", "attacker_logic", "terminal_obs", "defender_logic_desc", "encode", "state_store", "_",
+              "pipe_logic_wait_slot", "pipe_logic_load", "pipe_logic_play", "pipe_logic_fields_writeback", "pipe_encoder_wait",
+              "pipe_enc_wait_tma_read", "pipe_enc_build_rows", "pipe_enc_issue_bulk"]
 
     def phase_cycles(self, enable: bool = True):
         """Per-phase SM cycles of the step kernel since the last call (summed over CTAs); switches counting on/off."""

@@ -17,6 +17,8 @@ extern "C" {
 cudaError_t cbx_launch_step(const cbx_params* p, int op, int grid, int smem_bytes, int use_tma, cudaStream_t stream);
 cudaError_t cbx_launch_sample(const cbx_params* p, int32_t* att, int32_t* def, uint64_t seed, uint32_t step, cudaStream_t stream);
 cudaError_t cbx_kernel_attrs(int smem_bytes, int use_tma, int fast, int* blocks_per_sm);
+cudaError_t cbx_pipe_attrs(int enc, int smem_bytes);
+cudaError_t cbx_launch_pipe(const cbx_params* p, int op, int grid, cudaStream_t stream);
 }
 
 namespace {
@@ -54,6 +56,69 @@ cbx_fastdiv make_fastdiv(uint32_t d) {
 
 int align_up(int x, int a) { return (x + a - 1) / a * a; }
 
+// Shared-memory plan of the pipelined kernel (cbx_pipe.cuh) for `wl` logic and `we` encoder warps; false when the
+// configuration does not qualify (mask rows that no bulk copy can carry) or does not fit in 227 KiB.
+bool plan_pipe(const cbx_params& p, int wl, int we, cbx_pipe_plan* Q) {
+  const cbx_layout& L = p.lay;
+  memset(Q, 0, sizeof(*Q));
+  if (p.enc.warp_env < 1 || CBX_TILE != 32 || wl < 1 || we < 1 || (wl + we) * 32 > 512) return false;
+  const bool dense = L.sz_connect > 0;
+  const int ROWR = L.N * L.R, ROWC = L.N * L.P * L.C;
+  int gs = 1;
+  if (dense) {
+    if (ROWR % 8 || ROWC % 8 || (L.N * ROWR) % 16 || L.sz_local % 4) return false;
+    if (ROWC % 16 == 0) gs = 1;
+    else if (L.N % 2 == 0) gs = 2;
+    else return false;
+  }
+  Q->wl = wl; Q->we = we; Q->nslot = 2 * wl; Q->gs = gs;
+  const bool defobs = p.cfg.mode == CBX_MODE_MARLON && p.cfg.def_enabled;
+  int64_t o = 0;
+  auto up = [](int64_t x, int a) { return (x + a - 1) / a * a; };
+  Q->tables = (int)o; o = up(o + p.table_words + ((L.S + 3) & ~3), 32);
+  Q->lut = (int)o; o += 512;
+  Q->bars = (int)o; o = up(o + 2 * (1 + wl + 2 * Q->nslot), 32);
+  Q->zero = (int)o; o = up(o + (dense ? gs * ROWC / 4 : 0), 32);
+  Q->def_static = (int)o; o = up(o + (defobs ? CBX_TILE * (12 * L.n + L.nservices) / 4 : 0), 32);
+  // logic buffers: state tile | staging | field images [32][words per env] | actions (aliasing the property image when it
+  // is large enough: the actions are consumed before the images are laid out)
+  Q->lbufs = (int)o;
+  {
+    int64_t q = 0;
+    q += (int64_t)L.S * CBX_TILE;
+    Q->l_stage = (int)q; q += (int64_t)L.G * CBX_TILE;
+    Q->i_scal = (int)q; q += 8 * CBX_TILE;
+    Q->i_leak = (int)q; q += 4 * L.LEAK * CBX_TILE;
+    Q->i_cachem = (int)q; q += 2 * L.C * CBX_TILE;
+    Q->i_props = (int)q; q += (int64_t)L.N * L.nprops * CBX_TILE;
+    Q->i_priv = (int)q; q += L.N * CBX_TILE;
+    Q->i_local = (int)q; q += (int64_t)(L.sz_local / 4) * CBX_TILE;
+    if (L.N * L.nprops >= 22) Q->l_acts = Q->i_props;
+    else { Q->l_acts = (int)q; q += 22 * CBX_TILE; }
+    q = up(q, 32);
+    if (q * 4 * wl > 227 * 1024) return false;
+    Q->lbuf_words = (int)q;
+  }
+  o += (int64_t)wl * Q->lbuf_words;
+  Q->slots = (int)o;
+  Q->s_hdr = p.enc.desc_words * CBX_TILE;
+  Q->slot_words = Q->s_hdr + 32;
+  o += (int64_t)Q->nslot * Q->slot_words;
+  Q->wbufs = (int)o;
+  {
+    int64_t bo = 0;
+    Q->b_remote = (int)bo; bo = up(bo + (dense ? L.N * ROWR : 0), 16);
+    Q->b_conn = (int)bo; bo = up(bo + (dense ? (int64_t)(gs == 1 ? ROWC : 6 * ROWC) : 0), 16);
+    Q->b_inf = (int)bo; bo = up(bo + (defobs ? CBX_TILE * L.n : 0), 16);
+    if (bo * we > 227 * 1024) return false;
+    Q->wbuf_words = (int)up(bo / 4, 32);
+  }
+  o += (int64_t)we * Q->wbuf_words;
+  if (o * 4 > 227 * 1024) return false;
+  Q->total_bytes = (int)(o * 4);
+  return true;
+}
+
 }  // namespace
 
 struct cbx_scenario {
@@ -64,6 +129,7 @@ struct cbx_scenario {
 struct cbx_batch {
   cbx_params p;
   int device, grid, smem_bytes, use_tma;
+  int pipe_grid;  // pipelined kernel: CTAs (one per SM); the kernel is used when p.pipe.enabled
   std::vector<void*> allocs;
   uint32_t* d_tables;
   int64_t launches;
@@ -322,6 +388,29 @@ int cbx_batch_create(const cbx_scenario* s, int64_t n_envs, const cbx_config* cf
   if (b->grid > b->p.n_tiles) b->grid = b->p.n_tiles;
   const char* gridenv = getenv("CBX_GRID");
   if (gridenv && atoi(gridenv) > 0) b->grid = atoi(gridenv) < b->p.n_tiles ? atoi(gridenv) : b->p.n_tiles;
+  // pipelined kernel (logic warps ahead of TMA-storing encoder warps) when the configuration qualifies; CBX_PIPE=0 forces the
+  // fused kernel, CBX_PIPE_WL / CBX_PIPE_WE / CBX_PIPE_CTAS (CTAs per SM) are tuning knobs
+  b->p.pipe.enabled = 0; b->pipe_grid = 0;
+  {
+    const char* pe = getenv("CBX_PIPE");
+    if (b->use_tma && !(pe && pe[0] == '0')) {
+      const char *ewl = getenv("CBX_PIPE_WL"), *ewe = getenv("CBX_PIPE_WE"), *ect = getenv("CBX_PIPE_CTAS");
+      const int cand[4][2] = {{4, 8}, {3, 8}, {2, 8}, {2, 4}};
+      cbx_pipe_plan Q;
+      bool ok = false;
+      if (ewl || ewe) ok = plan_pipe(b->p, ewl ? atoi(ewl) : 4, ewe ? atoi(ewe) : 8, &Q);
+      for (int k = 0; k < 4 && !ok && !(ewl || ewe); ++k) ok = plan_pipe(b->p, cand[k][0], cand[k][1], &Q);
+      if (ok && cbx_pipe_attrs(b->p.enc.warp_env, Q.total_bytes) == cudaSuccess) {
+        Q.enabled = 1;
+        b->p.pipe = Q;
+        int per_sm = ect ? atoi(ect) : 1;
+        if (per_sm < 1) per_sm = 1;
+        b->pipe_grid = sms * per_sm < b->p.n_tiles ? sms * per_sm : b->p.n_tiles;
+      } else {
+        cudaGetLastError();
+      }
+    }
+  }
 
   auto dalloc = [&](void** ptr, size_t bytes) -> cudaError_t {
     if (bytes == 0) bytes = 16;
@@ -397,7 +486,9 @@ int cbx_batch_create(const cbx_scenario* s, int64_t n_envs, const cbx_config* cf
   // bring every env to its initial state (the reference resets before the first step as well)
   {
     b->p.reset_mask = nullptr;
-    cudaError_t e = cbx_launch_step(&b->p, CBX_OP_RESET | CBX_OP_ATTACKER | CBX_OP_DEFENDER, b->grid, b->smem_bytes, b->use_tma, 0);
+    const int op0 = CBX_OP_RESET | CBX_OP_ATTACKER | CBX_OP_DEFENDER;
+    cudaError_t e = b->p.pipe.enabled ? cbx_launch_pipe(&b->p, op0, b->pipe_grid, 0)
+                                      : cbx_launch_step(&b->p, op0, b->grid, b->smem_bytes, b->use_tma, 0);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { int rc2 = fail(CBX_ERR_CUDA, "initial reset: %s", cudaGetErrorString(e)); cbx_batch_destroy(b); return rc2; }
     b->launches++;
@@ -431,7 +522,8 @@ static int timed_launch(cbx_batch* b, int op, cudaStream_t st) {
     b->ev_used += 2;
     CUDA_TRY(cudaEventRecord(e0, st));
   }
-  CUDA_TRY(cbx_launch_step(&b->p, op, b->grid, b->smem_bytes, b->use_tma, st));
+  if (b->p.pipe.enabled) CUDA_TRY(cbx_launch_pipe(&b->p, op, b->pipe_grid, st));
+  else CUDA_TRY(cbx_launch_step(&b->p, op, b->grid, b->smem_bytes, b->use_tma, st));
   if (t) CUDA_TRY(cudaEventRecord(e1, st));
   b->launches++;
   return CBX_OK;

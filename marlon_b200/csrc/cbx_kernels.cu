@@ -832,6 +832,74 @@ __device__ void cyber_only_step(const Ctx& c, const cbx_params& p, const int32_t
   }
 }
 
+// ---- the two game-logic phases of one env (shared by the fused and the pipelined kernel) --------------------------------
+// Phase 1: the attacker's move (or an explicit reset / notify_reset).  `aa` = this env's attacker action words.
+__device__ __forceinline__ void logic_phase1(const Ctx& c, const cbx_params& p, const int op, const int32_t* aa, const uint32_t* s_init,
+                                             int slice_of_kind[3], Acc& acc) {
+  const cbx_layout& L = p.lay;
+  const cbx_config& cfg = p.cfg;
+  const bool reset_only = op & CBX_OP_RESET, who_att = op & CBX_OP_ATTACKER, who_def = op & CBX_OP_DEFENDER;
+  const bool marlon = cfg.mode == CBX_MODE_MARLON;
+  c.g(STG_ATT_DONE) = 0; c.g(STG_DEF_DONE) = 0;
+  if (reset_only) {
+    c.g(STG_OBS_KIND) = OBS_KEEP;
+    if (op & CBX_OP_NOTIFY) {
+      if (!p.reset_mask || p.reset_mask[c.env]) {
+        if (who_att) c.setflag(HDR_ATT_RR, true);
+        if (who_def) { c.setflag(HDR_DEF_RR, true); c.setf32(L.o_last_att, p.notify_last_reward); }
+      }
+    } else if (!p.reset_mask || p.reset_mask[c.env]) {
+      if (marlon) {  // attacker.reset() then defender.reset(), either or both
+        if (who_att) c.attacker_reset(s_init);
+        if (who_def && cfg.def_enabled) c.defender_reset(s_init);
+      } else {
+        c.cyber_reset(s_init);
+        c.setf32(L.o_att_return, 0.f);
+      }
+      if (who_att || !marlon) {
+        c.stage_reset_obs();
+        p.v.att_reward[c.env] = 0.f; p.v.att_terminated[c.env] = 0; p.v.att_truncated[c.env] = 0;
+        int4* ip = reinterpret_cast<int4*>(p.v.att_info + c.env * 8);
+        ip[0] = make_int4(0, 0, 0, 0); ip[1] = make_int4(0, 0, 0, 0);
+      }
+      if (who_def) { p.v.def_reward[c.env] = 0.f; p.v.def_terminated[c.env] = 0; p.v.def_truncated[c.env] = 0; }
+      p.v.network_availability[c.env] = 1.0;
+    }
+  } else if (marlon) {
+    if (who_att) attacker_wrapper_step(c, p, aa, slice_of_kind, acc);
+    else c.g(STG_OBS_KIND) = OBS_KEEP;
+  } else {
+    cyber_only_step(c, p, aa, acc);
+  }
+}
+
+// Phase 2: the attacker's auto-reset, the defender's move, the encoder descriptor.  `da` = this env's defender action words.
+// Returns whether the defender finished an episode that the VecEnv protocol resets (deferred: its observation comes first).
+__device__ __forceinline__ uint32_t logic_phase2(const Ctx& c, const cbx_params& p, const int op, const int32_t* da, const uint32_t* s_init,
+                                                 uint32_t* desc_e, Acc& acc) {
+  const cbx_layout& L = p.lay;
+  const cbx_config& cfg = p.cfg;
+  const bool reset_only = op & CBX_OP_RESET;
+  const bool marlon = cfg.mode == CBX_MODE_MARLON;
+  const bool def_on = marlon && cfg.def_enabled && (op & CBX_OP_DEFENDER);
+  if (!reset_only) {
+    if (c.g(STG_ATT_DONE) && cfg.auto_reset) {
+      if (marlon) c.attacker_reset(s_init);
+      else { c.cyber_reset(s_init); c.setf32(L.o_att_return, 0.f); }
+      c.stage_reset_obs();
+    }
+    if (def_on) defender_wrapper_step(c, p, da, acc);
+  }
+  const uint32_t def_done = c.g(STG_DEF_DONE) && cfg.auto_reset;
+  // main defender observation: after an auto-reset it shows the fresh environment (DWR:477)
+  build_desc(c, desc_e, p.enc.desc_words, def_done ? s_init + L.o_installed : nullptr);
+  if (c.g(STG_OBS_KIND) != OBS_KEEP) {
+    uint32_t* ob = p.v.owned_bits + c.env * L.OW;
+    for (int k = 0; k < L.OW; ++k) ob[k] = desc_e[D_OWNED + k];
+  }
+  return def_done;
+}
+
 // ---- the kernel ----------------------------------------------------------------------------------------------------------
 template <bool USE_TMA, int ENC>
 __global__ void __launch_bounds__(CBX_THREADS, CBX_MIN_CTAS) cbx_step_kernel(const __grid_constant__ cbx_params p, const int op) {
@@ -929,37 +997,7 @@ __global__ void __launch_bounds__(CBX_THREADS, CBX_MIN_CTAS) cbx_step_kernel(con
     if (tid < CBX_TILE) {
       uint32_t att_done = 0, keep = 1;
       if (active) {
-        c.g(STG_ATT_DONE) = 0; c.g(STG_DEF_DONE) = 0;
-        if (reset_only) {
-          c.g(STG_OBS_KIND) = OBS_KEEP;
-          if (op & CBX_OP_NOTIFY) {
-            if (!p.reset_mask || p.reset_mask[c.env]) {
-              if (who_att) c.setflag(HDR_ATT_RR, true);
-              if (who_def) { c.setflag(HDR_DEF_RR, true); c.setf32(L.o_last_att, p.notify_last_reward); }
-            }
-          } else if (!p.reset_mask || p.reset_mask[c.env]) {
-            if (marlon) {  // attacker.reset() then defender.reset(), either or both
-              if (who_att) c.attacker_reset(s_init);
-              if (who_def && cfg.def_enabled) c.defender_reset(s_init);
-            } else {
-              c.cyber_reset(s_init);
-              c.setf32(L.o_att_return, 0.f);
-            }
-            if (who_att || !marlon) {
-              c.stage_reset_obs();
-              p.v.att_reward[c.env] = 0.f; p.v.att_terminated[c.env] = 0; p.v.att_truncated[c.env] = 0;
-              int4* ip = reinterpret_cast<int4*>(p.v.att_info + c.env * 8);
-              ip[0] = make_int4(0, 0, 0, 0); ip[1] = make_int4(0, 0, 0, 0);
-            }
-            if (who_def) { p.v.def_reward[c.env] = 0.f; p.v.def_terminated[c.env] = 0; p.v.def_truncated[c.env] = 0; }
-            p.v.network_availability[c.env] = 1.0;
-          }
-        } else if (marlon) {
-          if (who_att) attacker_wrapper_step(c, p, s_act + tid * 10, slice_of_kind, acc);
-          else c.g(STG_OBS_KIND) = OBS_KEEP;
-        } else {
-          cyber_only_step(c, p, s_act + tid * 5, acc);
-        }
+        logic_phase1(c, p, op, s_act + tid * AW, s_init, slice_of_kind, acc);
         att_done = c.g(STG_ATT_DONE);
         keep = c.g(STG_OBS_KIND) == OBS_KEEP;
       }
@@ -1001,22 +1039,8 @@ __global__ void __launch_bounds__(CBX_THREADS, CBX_MIN_CTAS) cbx_step_kernel(con
     if (tid < CBX_TILE) {
       uint32_t def_done = 0, keep = 1;
       if (active) {
-        if (!reset_only) {
-          if (c.g(STG_ATT_DONE) && cfg.auto_reset) {
-            if (marlon) c.attacker_reset(s_init);
-            else { c.cyber_reset(s_init); c.setf32(L.o_att_return, 0.f); }
-            c.stage_reset_obs();
-          }
-          if (def_on) defender_wrapper_step(c, p, s_act + CBX_TILE * 10 + tid * 12, acc);
-        }
-        def_done = c.g(STG_DEF_DONE) && cfg.auto_reset;
+        def_done = logic_phase2(c, p, op, s_act + CBX_TILE * 10 + tid * 12, s_init, s_desc + tid * DW, acc);
         keep = c.g(STG_OBS_KIND) == OBS_KEEP;
-        // main defender observation: after an auto-reset it shows the fresh environment (DWR:477)
-        build_desc(c, s_desc + tid * DW, DW, def_done ? s_init + L.o_installed : nullptr);
-        if (!keep) {
-          uint32_t* ob = p.v.owned_bits + c.env * L.OW;
-          for (int k = 0; k < L.OW; ++k) ob[k] = s_desc[tid * DW + D_OWNED + k];
-        }
       }
       uint32_t dmask = __ballot_sync(0xFFFFFFFFu, def_done != 0);
       uint32_t kmask = __ballot_sync(0xFFFFFFFFu, keep != 0);
@@ -1081,6 +1105,12 @@ __global__ void __launch_bounds__(CBX_THREADS, CBX_MIN_CTAS) cbx_step_kernel(con
     }
   }
 }
+
+}  // namespace cbx
+
+#include "cbx_pipe.cuh"
+
+namespace cbx {
 
 // ---- uniformly sampled valid actions (benchmark load; ENV:959-1047 semantics) -------------------------------------------
 // One thread per env reads its state words straight from HBM (column access is coalesced across the warp).
@@ -1178,6 +1208,23 @@ cudaError_t cbx_launch_step(const cbx_params* p, int op, int grid, int smem_byte
     }
   } else if (enc >= 1) cbx::cbx_step_kernel<false, 1><<<grid, CBX_THREADS, smem_bytes, stream>>>(*p, op);
   else cbx::cbx_step_kernel<false, 0><<<grid, CBX_THREADS, smem_bytes, stream>>>(*p, op);
+  return cudaGetLastError();
+}
+// pipelined kernel: enc = 1 runtime dimensions, 2 ToyCtf(12,10), 3 Chain-10(12,12)
+cudaError_t cbx_pipe_attrs(int enc, int smem_bytes) {
+  switch (enc) {
+    case 3: return cudaFuncSetAttribute(cbx::cbx_pipe_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    case 2: return cudaFuncSetAttribute(cbx::cbx_pipe_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    default: return cudaFuncSetAttribute(cbx::cbx_pipe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  }
+}
+cudaError_t cbx_launch_pipe(const cbx_params* p, int op, int grid, cudaStream_t stream) {
+  const int threads = (p->pipe.wl + p->pipe.we) * 32;
+  switch (p->enc.warp_env) {
+    case 3: cbx::cbx_pipe_kernel<3><<<grid, threads, p->pipe.total_bytes, stream>>>(*p, op); break;
+    case 2: cbx::cbx_pipe_kernel<2><<<grid, threads, p->pipe.total_bytes, stream>>>(*p, op); break;
+    default: cbx::cbx_pipe_kernel<1><<<grid, threads, p->pipe.total_bytes, stream>>>(*p, op); break;
+  }
   return cudaGetLastError();
 }
 cudaError_t cbx_launch_sample(const cbx_params* p, int32_t* att, int32_t* def, uint64_t seed, uint32_t step, cudaStream_t stream) {

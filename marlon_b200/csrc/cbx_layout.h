@@ -94,10 +94,32 @@ struct cbx_smem_plan {  // shared-memory carve-up in 32-bit words
   int buf_stride;  // words between the two buffer sets {state, stage, desc, acts} of the pipelined tile loop
 };
 
+// Pipelined step kernel (cbx_pipe.cuh): per CTA `wl` game-logic warps (one thread per env; they also lay out the small
+// observation fields of their tile, env-major, and hand them to the TMA engine) run ahead of `we` encoder warps (which build
+// the action-mask template rows of each env and hand those to the TMA engine) through `nslot` descriptor slots.
+struct cbx_pipe_plan {
+  int enabled;
+  int wl, we, nslot;
+  int gs;           // connect-mask rows per bulk copy: 1 when a row is a multiple of 16 bytes, 2 when it is 8 mod 16
+  // shared-memory carve-up in 32-bit words
+  int tables, lut, bars, zero, def_static;
+  int lbufs, lbuf_words;    // per logic warp: state tile | staging | actions (aliased by the props image) | field images
+  int l_stage, l_acts;      // inside a logic buffer (the state tile is at 0)
+  int i_scal, i_leak, i_cachem, i_props, i_priv, i_local;  // field images [32 envs][words per env], inside a logic buffer
+  int slots, slot_words;    // per slot: descriptors [32][desc_words] | header (32 words)
+  int s_hdr;
+  int wbufs, wbuf_words;    // per encoder warp
+  int b_remote, b_conn, b_inf;  // inside an encoder warp's buffer, in bytes (multiples of 16)
+  int total_bytes;
+};
+// slot header words
+enum { CBX_SH_ENC_MASK = 0, CBX_SH_TILE = 1 };
+
 struct cbx_params {
   cbx_layout lay;
   cbx_enc_consts enc;
   cbx_smem_plan plan;
+  cbx_pipe_plan pipe;
   cbx_config cfg;
   int64_t n_envs;
   int64_t n_pad;          // n_envs rounded up to CBX_TILE

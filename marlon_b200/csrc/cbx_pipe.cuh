@@ -1,0 +1,467 @@
+// cbx_pipe.cuh -- pipelined (warp-specialised) step kernel for sm_100a; included by cbx_kernels.cu.
+//
+// Why: in the fused kernel every CTA alternates "warp 0 plays 32 envs" (latency bound, ~13 us, store path idle) and "all warps
+// encode" (bandwidth bound); the CTAs of an SM start together and stay in phase, so HBM idles while the SMs think
+// (profiles/r01_section_skip_experiment.txt: 0.065 ms of a 0.2 ms step is logic with nothing under it).  And the store
+// path itself is the second loss: 8-byte st.global rows reach 4.2 TB/s where TMA bulk stores of the same bytes reach
+// 6.0 TB/s (profiles/r01_store_path_microbench.txt).
+//
+// One persistent CTA per SM, two kinds of warps:
+//   * `wl` LOGIC warps, one thread per env, each on its own tile of 32 envs: TMA-load the state tile, play both agents
+//     (logic_phase1/2), then every thread lays out ITS env's small observation fields (scalars, leaked credentials,
+//     credential cache, property matrix, privilege levels, local-vulnerability mask) env-major in shared memory -- a
+//     tile's rows are contiguous in every output tensor, so each field leaves as ONE bulk copy per tile -- applies the
+//     deferred defender auto-reset, TMA-stores the state tile.  The tile's encoder descriptors go to a slot.
+//   * `we` ENCODER warps, one env at a time: build the template row of the env's remote / connect action masks in the
+//     warp's shared-memory buffer and hand it to the TMA engine: one cp.async.bulk per connect-mask row (or row pair when
+//     rows are 8 mod 16 bytes) whose source is the template or a shared zero row -- every row of those masks is either
+//     zero or the env's template.  One of them also emits the defender's observation of the tile.
+// mbarriers: ready[slot] (1 arrival: the logic warp), empty[slot] (`we` arrivals: the encoder warps).
+namespace cbx {
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int ENC> struct DimsOf { typedef DimsDyn T; };
+template <> struct DimsOf<2> { typedef DimsToyCtf T; };
+template <> struct DimsOf<3> { typedef DimsChain10 T; };
+
+struct FieldImages {  // env-major images of a tile's small observation fields (shared memory)
+  int32_t *scal, *leak, *cachem, *props, *priv;
+  uint32_t* local;
+};
+
+// One thread lays out the small observation fields of ITS env (ENV:859-933 encodings; same values as encode_attacker).
+// `de` = the env's encoder descriptor (owned-by-discovery-index bits), `e` = env index within the tile.
+template <class D>
+__device__ __forceinline__ void build_field_images(const Ctx& c, const uint32_t* de, const FieldImages& im, const int e, const bool dense) {
+  const cbx_layout* L = c.L;
+  const int N = CBX_DIM(D, N, L->N), NL = CBX_DIM(D, L, L->L);
+  const int NC = CBX_DIM(D, C, L->C), NPROPS = CBX_DIM(D, NPROPS, L->nprops), LEAK = CBX_DIM(D, LEAK, L->LEAK);
+  const int PW = D::kStatic ? (D::NPROPS + 31) / 32 : L->PW;
+  const int nd = (int)de[D_ND], nc = (int)de[D_NC];
+  const bool blank = de[D_KIND] == OBS_BLANK;
+  int32_t* o;
+  o = im.scal + e * 8;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) o[k] = (int32_t)c.g(STG_SCALARS + k);
+  o = im.leak + e * 4 * LEAK;
+#pragma unroll 4
+  for (int k = 0; k < 4 * LEAK; ++k) o[k] = (int32_t)c.g(L->g_leaked + k);
+  o = im.cachem + e * 2 * NC;
+#pragma unroll 2
+  for (int k = 0; k < NC; ++k) {
+    uint32_t a = 0, b = 0;
+    if (!blank && k < nc) {
+      const uint32_t* rec = c.triple((int)c.half(L->o_cache, k));
+      a = c.byte(L->o_disc_idx, (int)rec[0]);
+      b = rec[1];
+    }
+    o[2 * k] = (int32_t)a;
+    o[2 * k + 1] = (int32_t)b;
+  }
+  o = im.props + e * N * NPROPS;
+  for (int k = 0; k < N; ++k) {
+    uint32_t lo = 0, hi = 0;
+    if (!blank && k < nd) {
+      const int node = (int)c.byte(L->o_disc_order, k);
+      lo = c.w(L->o_props + node * PW);
+      if (PW > 1) hi = c.w(L->o_props + node * PW + 1);
+    }
+#pragma unroll 2
+    for (int pi = 0; pi < NPROPS; ++pi) {
+      const uint32_t bit = ((pi < 32 ? lo : hi) >> (pi & 31)) & 1u;
+      o[k * NPROPS + pi] = blank ? 2 : (int32_t)bit;
+    }
+  }
+  o = im.priv + e * N;
+#pragma unroll 2
+  for (int k = 0; k < N; ++k) {
+    uint32_t val = 0;
+    if (!blank && k < nd) {
+      const uint32_t node = c.byte(L->o_disc_order, k);
+      val = (c.g(L->g_priv + (node >> 4)) >> ((node & 15) * 2)) & 3u;
+    }
+    o[k] = (int32_t)val;
+  }
+  if (dense) {  // local-vulnerability mask [N][L] bytes, 4 per word (N * L is a multiple of 4 on this path)
+    uint32_t* lo = im.local + e * (N * NL / 4);
+    uint32_t word = 0;
+    int i = 0;
+    for (int s = 0; s < N; ++s) {
+      const bool own = (de[D_OWNED + (s >> 5)] >> (s & 31)) & 1u;
+      const uint32_t* rec = c.vuln_rec(own ? (int)c.byte(L->o_disc_order, s) : 0, 0);
+      for (int v = 0; v < NL; ++v, ++i) {
+        if (own) word |= (rec[v * CBX_VULN_WORDS] & 1u) << (8 * (i & 3));
+        if ((i & 3) == 3) { lo[i >> 2] = word; word = 0; }
+      }
+    }
+  }
+}
+
+// The remote / connect action masks of one env, by one warp: template rows into the warp buffer, then bulk copies.
+template <class D>
+__device__ __forceinline__ void encode_masks_pipe(const uint32_t* de, const uint2* lut, const cbx_layout* L, const cbx_enc_consts& K,
+                                                  int8_t* remote_env, int8_t* connect_env, uint8_t* wb, const cbx_pipe_plan& Q,
+                                                  const uint8_t* zero, const int lane, const bool prof, long long (&pacc)[3]) {
+  long long pt = prof ? clock64() : 0;
+#define CBX_EPROF(slot)                                                  \
+  if (prof) {                                                            \
+    long long _now = clock64();                                          \
+    pacc[(slot) - 13] += _now - pt;                                      \
+    pt = _now;                                                           \
+  }
+  const int N = CBX_DIM(D, N, L->N), NR = CBX_DIM(D, R, L->R), NP = CBX_DIM(D, P, L->P), NC = CBX_DIM(D, C, L->C);
+  const int ROWR = N * NR, ROWC = N * NP * NC;
+  const uint32_t nc = de[D_NC];
+  const int skip = K.debug_skip;  // experiments only (CBX_DEBUG_SKIP): 128 no connect copies, 256 no copies at all
+  // the bulk copies that read this buffer for the warp's previous env must have finished reading it
+  tma_store_wait_read();
+  __syncwarp();
+  CBX_EPROF(13)  // waiting for the TMA engine to finish reading the previous env's rows
+  // remote mask image: 8-byte granules never straddle a row (ROWR % 8 == 0)
+  const int limr = (int)de[D_LIMR];
+  uint2* rimg = reinterpret_cast<uint2*>(wb + Q.b_remote);
+#pragma unroll
+  for (int g = lane; g < N * ROWR / 8; g += 32) {
+    const uint32_t b = (uint32_t)g * 8u;
+    const uint32_t s = D::kStatic ? b / (uint32_t)(D::kStatic ? D::N * D::R : 1) : FastDiv(K.d_rowr).div(b);
+    const int w = (int)(b - s * ROWR);
+    const uint32_t m = ((de[D_OWNED + (s >> 5)] >> (s & 31)) & 1u) ? lowmask(min(max(limr - w, 0), 8)) : 0u;
+    rimg[g] = lut[m];
+  }
+  // connect template row (8-byte granules), written to every place a bulk copy reads it from:
+  //   gs == 1: [T]            gs == 2: [0 T | T 0 | T T] (the zero halves were cleared once at kernel start)
+  const int limc = (int)de[D_LIMC];
+  const uint64_t base = ((uint64_t)de[D_BHI] << 32) | de[D_BLO];
+  uint8_t* cb = wb + Q.b_conn;
+#pragma unroll
+  for (int g = lane; g < ROWC / 8; g += 32) {
+    const int w = g * 8;
+    uint32_t m = lowmask(min(max(limc - w, 0), 8));
+    const int ph = D::kStatic ? w % (D::kStatic ? D::C : 1) : (int)((uint32_t)w - FastDiv(K.d_C).div((uint32_t)w) * NC);
+    if (NC <= 48) m &= (uint32_t)(base >> ph);
+    else m &= lowmask(min(max((int)nc - ph, 0), 8)) | (lowmask(min(max(NC - ph + (int)nc, 0), 8)) & ~lowmask(min(max(NC - ph, 0), 8)));
+    const uint2 v = lut[m & 0xFFu];
+    if (Q.gs == 1) {
+      *reinterpret_cast<uint2*>(cb + 8 * g) = v;
+    } else {
+      *reinterpret_cast<uint2*>(cb + ROWC + 8 * g) = v;
+      *reinterpret_cast<uint2*>(cb + 2 * ROWC + 8 * g) = v;
+      *reinterpret_cast<uint2*>(cb + 4 * ROWC + 8 * g) = v;
+      *reinterpret_cast<uint2*>(cb + 5 * ROWC + 8 * g) = v;
+    }
+  }
+  fence_async_smem();  // generic-proxy writes above -> visible to the bulk copies below
+  __syncwarp();
+  CBX_EPROF(14)  // building the rows in shared memory
+  // ---- hand the rows to the TMA engine (lanes issue in parallel; every lane closes its own bulk group) ----
+  if (!(skip & 256)) {
+    if (lane == 31) tma_store_1d(remote_env, wb + Q.b_remote, (uint32_t)(N * ROWR));
+    if (skip & 128) {
+    } else if (Q.gs == 1) {
+      for (int s = lane; s < N; s += 32) {
+        const bool own = (de[D_OWNED + (s >> 5)] >> (s & 31)) & 1u;
+        tma_store_1d(connect_env + (size_t)s * ROWC, own ? cb : zero, (uint32_t)ROWC);
+      }
+    } else {
+      for (int j = lane; j < N / 2; j += 32) {
+        const uint32_t pr = (de[D_OWNED + ((2 * j) >> 5)] >> ((2 * j) & 31)) & 3u;  // bit 0: row 2j owned, bit 1: row 2j+1
+        const uint8_t* src = pr == 3u ? cb + 4 * ROWC : pr == 1u ? cb + 2 * ROWC : pr == 2u ? cb : zero;
+        tma_store_1d(connect_env + (size_t)j * 2 * ROWC, src, (uint32_t)(2 * ROWC));
+      }
+    }
+  }
+  tma_store_commit();
+  CBX_EPROF(15)  // issuing the bulk copies
+#undef CBX_EPROF
+}
+
+// The defender's observation of a whole tile (MultiBinary arrays, DWR:492-534): the firewall / service parts are static per
+// scenario (the LearningDefender acts on a stale copy) and leave from a CTA-wide image built once.
+template <class D>
+__device__ __forceinline__ void encode_defender_tile(const Tile& t, const Target& o, const int n_valid, uint8_t* wb, const cbx_pipe_plan& Q,
+                                                     const uint8_t* def_static, const int lane) {
+  const cbx_layout* L = t.L;
+  const int n = CBX_DIM(D, NN, L->n), nsvc = CBX_DIM(D, NSVC, L->nservices);
+  const int OW = D::kStatic ? (D::N + 31) / 32 : L->OW;
+  if (n_valid != CBX_TILE) {  // ragged last tile: plain stores
+    encode_defender_by_warp<D>(t, o, n_valid, mask_all(), true, 0, 1);
+    return;
+  }
+  tma_store_wait_read();
+  __syncwarp();
+  uint8_t* img = wb + Q.b_inf;
+  for (int idx = lane; idx < CBX_TILE * n; idx += 32) {
+    const uint32_t e = D::kStatic ? (uint32_t)idx / (uint32_t)(D::kStatic ? D::NN : 1) : FastDiv(t.K->d_n).div((uint32_t)idx);
+    const int i = idx - (int)e * n;
+    const uint32_t* di = t.desc + e * t.DW + D_OWNED + OW;
+    img[idx] = (uint8_t)((di[i >> 5] >> (i & 31)) & 1u);
+  }
+  fence_async_smem();
+  __syncwarp();
+  if (lane == 0) tma_store_1d(o.infected, img, (uint32_t)(CBX_TILE * n));
+  if (lane == 1) tma_store_1d(o.fw_in, def_static, (uint32_t)(CBX_TILE * 6 * n));
+  if (lane == 2) tma_store_1d(o.fw_out, def_static + CBX_TILE * 6 * n, (uint32_t)(CBX_TILE * 6 * n));
+  if (lane == 3 && nsvc > 0) tma_store_1d(o.services, def_static + 2 * CBX_TILE * 6 * n, (uint32_t)(CBX_TILE * nsvc));
+  tma_store_commit();
+}
+
+// field image -> output tensor for the selected envs of a tile, plain coalesced stores (ragged or partially kept tiles)
+__device__ __forceinline__ void copy_field_rows(int32_t* dst, const int32_t* img, const int wpe, const int n_valid, const uint32_t mask,
+                                                const int lane) {
+  for (int e = 0; e < n_valid; ++e) {
+    if (!((mask >> e) & 1u)) continue;
+    for (int w = lane; w < wpe; w += 32) dst[e * wpe + w] = img[e * wpe + w];
+  }
+}
+
+template <int ENC>
+__global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant__ cbx_params p, const int op) {
+  typedef typename DimsOf<ENC>::T D;
+  extern __shared__ __align__(128) uint32_t smem[];
+  const cbx_layout& L = p.lay;
+  const cbx_config& cfg = p.cfg;
+  const cbx_pipe_plan& Q = p.pipe;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool reset_only = op & CBX_OP_RESET, who_def = op & CBX_OP_DEFENDER, who_att = op & CBX_OP_ATTACKER;
+  const bool marlon = cfg.mode == CBX_MODE_MARLON;
+  const bool def_on = marlon && cfg.def_enabled && who_def;
+  const bool def_encode = def_on && !(op & CBX_OP_NOTIFY);
+  const bool dense = p.v.connect != nullptr;
+  const int DW = p.enc.desc_words;
+  const int AW = marlon ? 10 : 5;
+  uint32_t* s_tb = smem + Q.tables;
+  uint2* s_lut = reinterpret_cast<uint2*>(smem + Q.lut);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Q.bars);
+  uint64_t* bar_load = bars + 1;             // [wl]    state-tile loads, one per logic warp
+  uint64_t* bar_ready = bar_load + Q.wl;     // [nslot] logic -> encoders
+  uint64_t* bar_empty = bar_ready + Q.nslot; // [nslot] encoders -> logic
+  uint8_t* s_zero = reinterpret_cast<uint8_t*>(smem + Q.zero);
+  uint8_t* s_defst = reinterpret_cast<uint8_t*>(smem + Q.def_static);
+  const uint32_t* s_init = s_tb + p.table_words;
+  const uint32_t table_bytes = (uint32_t)(p.table_words + ((L.S + 3) & ~3)) * 4u;
+  const int nthreads = (Q.wl + Q.we) * 32;
+  constexpr uint32_t kRowBytes = CBX_TILE * 4u;
+
+  for (int k = tid; k < 256; k += nthreads) {
+    uint32_t lo = ((k & 0xF) * 0x00204081u) & 0x01010101u, hi = (((k >> 4) & 0xF) * 0x00204081u) & 0x01010101u;
+    s_lut[k] = make_uint2(lo, hi);
+  }
+  // zero row + encoder buffers (the zero halves of the row-pair templates stay zero for the whole kernel)
+  for (int k = Q.zero + tid; k < Q.def_static; k += nthreads) smem[k] = 0;
+  for (int k = Q.wbufs + tid; k < Q.wbufs + Q.we * Q.wbuf_words; k += nthreads) smem[k] = 0;
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    for (int w = 0; w < Q.wl; ++w) mbar_init(&bar_load[w], 1);
+    for (int s = 0; s < Q.nslot; ++s) { mbar_init(&bar_ready[s], 1); mbar_init(&bar_empty[s], Q.we); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&bars[0], table_bytes);
+    tma_load_1d(s_tb, p.tables, table_bytes, &bars[0]);
+  }
+  mbar_wait(&bars[0], 0);
+  if (def_encode) {  // static parts of the defender observation for a tile of 32 envs: [32][6n] in, [32][6n] out, [32][nsvc]
+    const int n6 = 6 * L.n;
+    for (int idx = tid; idx < CBX_TILE * n6; idx += nthreads) {
+      const int i = idx % n6, node = i / 6, r = i - node * 6;
+      const uint32_t dob = s_tb[s_tb[CBX_H_OFF_NODE] + node * CBX_NODE_WORDS + CBX_N_DEFOBS];
+      s_defst[idx] = (uint8_t)((dob >> r) & 1u);
+      s_defst[CBX_TILE * n6 + idx] = (uint8_t)((dob >> (8 + r)) & 1u);
+    }
+    for (int idx = tid; idx < CBX_TILE * L.nservices; idx += nthreads) s_defst[2 * CBX_TILE * n6 + idx] = 1;
+  }
+  fence_async_smem();
+  __syncthreads();
+
+  const int my_tiles = (int)blockIdx.x < p.n_tiles ? (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int spw = Q.nslot / Q.wl;  // slots per logic warp
+  long long prof_t = p.prof ? clock64() : 0;
+  long long pp[5] = {0, 0, 0, 0, 0};  // per-warp phase cycles (slots 8..12), flushed once at the end
+#define CBX_PPROF(slot)                                                        \
+  if (p.prof) {                                                                \
+    long long _now = clock64();                                                \
+    pp[(slot) - 8] += _now - prof_t;                                           \
+    prof_t = _now;                                                             \
+  }
+
+  if (warp < Q.wl) {
+    // =============================== game-logic warp ===============================
+    Acc acc;
+#pragma unroll
+    for (int k = 0; k < CBX_STAT_COUNT; ++k) acc.v[k] = 0.0;
+    int slice_of_kind[3] = {p.slice_of_kind[0], p.slice_of_kind[1], p.slice_of_kind[2]};
+    uint32_t load_phase = 0;
+    uint32_t* lb = smem + Q.lbufs + warp * Q.lbuf_words;  // state tile | staging | actions | field images
+    uint32_t* sg = lb + Q.l_stage;
+    int32_t* act = reinterpret_cast<int32_t*>(lb + Q.l_acts);
+    FieldImages im;
+    im.scal = reinterpret_cast<int32_t*>(lb + Q.i_scal); im.leak = reinterpret_cast<int32_t*>(lb + Q.i_leak);
+    im.cachem = reinterpret_cast<int32_t*>(lb + Q.i_cachem); im.props = reinterpret_cast<int32_t*>(lb + Q.i_props);
+    im.priv = reinterpret_cast<int32_t*>(lb + Q.i_priv); im.local = lb + Q.i_local;
+    const int wpe_leak = 4 * L.LEAK, wpe_cachem = 2 * L.C, wpe_props = L.N * L.nprops, wpe_priv = L.N, wpe_local = L.sz_local / 4;
+    int u = 0;  // my u-th tile
+    for (int j = warp; j < my_tiles; j += Q.wl, ++u) {
+      const int slot = warp + Q.wl * (u % spw), use = u / spw;
+      uint32_t* desc = smem + Q.slots + slot * Q.slot_words;
+      uint32_t* hdr = desc + Q.s_hdr;
+      const int tile = (int)blockIdx.x + j * (int)gridDim.x;
+      const int64_t e0 = (int64_t)tile * CBX_TILE;
+      const int n_valid = (int)min((int64_t)CBX_TILE, p.n_envs - e0);
+      // the previous tile's state store and field copies (issued by lanes 0..6) must be done reading this warp's buffer
+      tma_store_wait_read();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_expect_tx(&bar_load[warp], (uint32_t)L.S * kRowBytes);
+        tma_load_1d(lb, p.state + (int64_t)tile * L.S * CBX_TILE, (uint32_t)L.S * kRowBytes, &bar_load[warp]);
+      }
+      if (!reset_only) {
+        if (p.att_actions && (who_att || !marlon))
+          for (int q = lane; q < n_valid * AW; q += 32) act[q] = p.att_actions[e0 * AW + q];
+        if (def_on)
+          for (int q = lane; q < n_valid * 12; q += 32) act[CBX_TILE * 10 + q] = p.def_actions[e0 * 12 + q];
+      }
+      mbar_wait(&bar_load[warp], load_phase);
+      load_phase ^= 1;
+      __syncwarp();
+      CBX_PPROF(9)  // state tile + actions in
+      const bool active = lane < n_valid;
+      Ctx c;
+      c.st = lb + lane; c.sg = sg + lane; c.tb = s_tb; c.L = &L; c.cfg = &cfg; c.env = e0 + lane;
+      uint32_t att_done = 0, keep = 1;
+      if (active) {
+        logic_phase1(c, p, op, act + lane * AW, s_init, slice_of_kind, acc);
+        att_done = c.g(STG_ATT_DONE);
+        keep = c.g(STG_OBS_KIND) == OBS_KEEP;
+      }
+      const uint32_t att_done_mask = __ballot_sync(0xFFFFFFFFu, att_done != 0);
+      const uint32_t keep1 = __ballot_sync(0xFFFFFFFFu, keep != 0);
+      CBX_PPROF(10)  // game logic
+      if (use > 0) mbar_wait(&bar_empty[slot], (uint32_t)(use - 1) & 1u);  // the encoders are done with the slot's last tile
+      CBX_PPROF(8)  // waiting for a free descriptor slot
+      Tile t;
+      t.L = &L; t.tb = s_tb; t.st = lb; t.sg = sg; t.desc = desc; t.lut = s_lut; t.K = &p.enc; t.DW = DW;
+      // terminal observations of the envs that finished: encoded by this warp BEFORE the auto-reset (plain stores)
+      if (att_done_mask && cfg.auto_reset && cfg.emit_terminal_obs && !reset_only) {
+        if (active && ((att_done_mask >> lane) & 1u)) build_desc(c, desc + lane * DW, DW, nullptr);
+        __syncwarp();
+        Target tt = make_target(p.v, L, e0, true);
+        EnvMask m_enc, m_cp;
+#pragma unroll
+        for (int q = 0; q < kGroups; ++q) { m_enc.w[q] = 0; m_cp.w[q] = 0; }
+        m_enc.w[0] = att_done_mask & ~keep1;
+        m_cp.w[0] = att_done_mask & keep1;
+        encode_attacker<ENC>(t, tt, n_valid, m_enc, 0, 1);
+        if (m_cp.any()) {  // intercepted-and-truncated step: the terminal observation is the previous one
+          Target tm = make_target(p.v, L, e0, false);
+          copy_rows(tt.scalars, tm.scalars, 32, n_valid, m_cp, lane, 32);
+          copy_rows(tt.leaked, tm.leaked, 16 * L.LEAK, n_valid, m_cp, lane, 32);
+          copy_rows(tt.cachem, tm.cachem, 8 * L.C, n_valid, m_cp, lane, 32);
+          copy_rows(tt.props, tm.props, 4 * L.N * L.nprops, n_valid, m_cp, lane, 32);
+          copy_rows(tt.priv, tm.priv, 4 * L.N, n_valid, m_cp, lane, 32);
+          copy_rows(tt.local, tm.local, L.sz_local, n_valid, m_cp, lane, 32);
+          copy_rows(tt.remote, tm.remote, L.sz_remote, n_valid, m_cp, lane, 32);
+          copy_rows(tt.connect, tm.connect, L.sz_connect, n_valid, m_cp, lane, 32);
+        }
+        __syncwarp();
+      }
+      uint32_t def_done = 0;
+      keep = 1;
+      if (active) {
+        def_done = logic_phase2(c, p, op, act + CBX_TILE * 10 + lane * 12, s_init, desc + lane * DW, acc);
+        keep = c.g(STG_OBS_KIND) == OBS_KEEP;
+        if (def_done && cfg.emit_terminal_obs && p.v.term_def_infected_nodes) {
+          // terminal defender observation = infected nodes seen by the step that ended the episode
+          int8_t* ti = p.v.term_def_infected_nodes + c.env * L.n;
+          for (int i = 0; i < L.n; ++i) ti[i] = (int8_t)((c.g(STG_DEF_TERM_INST + (i >> 5)) >> (i & 31)) & 1u);
+        }
+      }
+      const uint32_t enc_mask = ~__ballot_sync(0xFFFFFFFFu, keep != 0);
+      // descriptors are complete: the encoder warps can start on the tile's action masks while this warp lays out the rest
+      if (lane == 0) { hdr[CBX_SH_ENC_MASK] = enc_mask; hdr[CBX_SH_TILE] = (uint32_t)tile; }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_ready[slot]);
+      CBX_PPROF(10)
+      // ---- the small observation fields of the tile: one thread per env, env-major images, one bulk copy per field ----
+      if (active && !keep) build_field_images<D>(c, desc + lane * DW, im, lane, dense);
+      // deferred defender auto-reset (DummyVecEnv resets after the step; the observations above were taken before it)
+      if (active && def_done) c.defender_reset(s_init);
+      fence_async_smem();
+      __syncwarp();
+      {
+        const Target tm = make_target(p.v, L, e0, false);
+        if (n_valid == CBX_TILE && enc_mask == 0xFFFFFFFFu) {
+          if (lane == 0) tma_store_1d(p.state + (int64_t)tile * L.S * CBX_TILE, lb, (uint32_t)L.S * kRowBytes);
+          if (lane == 1) tma_store_1d(tm.scalars, im.scal, CBX_TILE * 32u);
+          if (lane == 2) tma_store_1d(tm.leaked, im.leak, (uint32_t)(CBX_TILE * 4 * wpe_leak));
+          if (lane == 3) tma_store_1d(tm.cachem, im.cachem, (uint32_t)(CBX_TILE * 4 * wpe_cachem));
+          if (lane == 4) tma_store_1d(tm.props, im.props, (uint32_t)(CBX_TILE * 4 * wpe_props));
+          if (lane == 5) tma_store_1d(tm.priv, im.priv, (uint32_t)(CBX_TILE * 4 * wpe_priv));
+          if (lane == 6 && dense) tma_store_1d(tm.local, im.local, (uint32_t)(CBX_TILE * 4 * wpe_local));
+          if (lane < 7) tma_store_commit();
+        } else {
+          if (lane == 0) { tma_store_1d(p.state + (int64_t)tile * L.S * CBX_TILE, lb, (uint32_t)L.S * kRowBytes); tma_store_commit(); }
+          copy_field_rows(tm.scalars, im.scal, 8, n_valid, enc_mask, lane);
+          copy_field_rows(tm.leaked, im.leak, wpe_leak, n_valid, enc_mask, lane);
+          copy_field_rows(tm.cachem, im.cachem, wpe_cachem, n_valid, enc_mask, lane);
+          copy_field_rows(tm.props, im.props, wpe_props, n_valid, enc_mask, lane);
+          copy_field_rows(tm.priv, im.priv, wpe_priv, n_valid, enc_mask, lane);
+          if (dense) copy_field_rows(reinterpret_cast<int32_t*>(tm.local), reinterpret_cast<const int32_t*>(im.local), wpe_local, n_valid, enc_mask, lane);
+          __syncwarp();
+        }
+      }
+      CBX_PPROF(11)  // field images + state write-back
+    }
+    tma_store_wait_all();  // every lane that issued bulk copies waits for its own
+    // episode statistics: warp shuffle reduce, one atomic per slot per warp
+#pragma unroll
+    for (int k = 0; k < CBX_STAT_COUNT; ++k) {
+      double x = acc.v[k];
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xFFFFFFFFu, x, o);
+      if (lane == 0 && x != 0.0) atomicAdd(p.v.episode_stats + k, x);
+    }
+  } else if (warp < Q.wl + Q.we) {
+    // =============================== encoder warp ===============================
+    const int wid = warp - Q.wl;
+    uint8_t* wb = reinterpret_cast<uint8_t*>(smem + Q.wbufs + wid * Q.wbuf_words);
+    long long pacc[3] = {0, 0, 0};
+    for (int j = 0; j < my_tiles; ++j) {
+      const int lw = j % Q.wl, u = j / Q.wl;
+      const int slot = lw + Q.wl * (u % spw), use = u / spw;
+      const uint32_t* desc = smem + Q.slots + slot * Q.slot_words;
+      mbar_wait(&bar_ready[slot], (uint32_t)use & 1u);
+      CBX_PPROF(12)  // encoders waiting for a tile
+      const uint32_t enc_mask = desc[Q.s_hdr + CBX_SH_ENC_MASK];
+      const int tile = (int)blockIdx.x + j * (int)gridDim.x;
+      const int64_t e0 = (int64_t)tile * CBX_TILE;
+      const int n_valid = (int)min((int64_t)CBX_TILE, p.n_envs - e0);
+      if (def_encode && wid == j % Q.we) {
+        Tile t;
+        t.L = &L; t.tb = s_tb; t.st = nullptr; t.sg = nullptr; t.desc = desc; t.lut = s_lut; t.K = &p.enc; t.DW = DW;
+        const Target tm = make_target(p.v, L, e0, false);
+        encode_defender_tile<D>(t, tm, n_valid, wb, Q, s_defst, lane);
+      }
+      if (dense) {
+        for (int e = wid; e < n_valid; e += Q.we)
+          if ((enc_mask >> e) & 1u)
+            encode_masks_pipe<D>(desc + e * DW, s_lut, &L, p.enc, p.v.remote_vulnerability + (e0 + e) * L.sz_remote,
+                                 p.v.connect + (e0 + e) * (int64_t)L.sz_connect, wb, Q, s_zero, lane, p.prof != nullptr, pacc);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_empty[slot]);
+      prof_t = p.prof ? clock64() : 0;
+    }
+    tma_store_wait_all();
+    if (p.prof && lane == 0)
+      for (int k = 0; k < 3; ++k) atomicAdd(p.prof + 13 + k, (unsigned long long)pacc[k]);
+  }
+  if (p.prof && lane == 0)
+    for (int k = 0; k < 5; ++k)
+      if (pp[k]) atomicAdd(p.prof + 8 + k, (unsigned long long)pp[k]);
+#undef CBX_PPROF
+}
+
+}  // namespace cbx

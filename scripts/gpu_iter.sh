@@ -1,8 +1,8 @@
 #!/bin/bash
 # Quick iteration on a B200: smoke, the oracle-parity tests, a short bench (no CPU baseline).
 mkdir -p gpurun_out
-echo "== smoke"; timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "rc=$?"; tail -2 gpurun_out/smoke.log
-echo "== pytest gpu (vs oracle)"; timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x --no-header -p no:cacheprovider -k "${PYTEST_K:-oracle or roundtrip or fixture}" > gpurun_out/pytest_iter.log 2>&1; echo "rc=$?"; tail -15 gpurun_out/pytest_iter.log
+echo "== smoke"; timeout 120 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; rc=$?; echo "rc=$rc"; tail -4 gpurun_out/smoke.log; if [ $rc -ne 0 ]; then echo "smoke failed: stopping"; exit 1; fi
+echo "== pytest gpu"; timeout 1200 python -m pytest tests -m gpu -q -x --no-header -p no:cacheprovider ${PYTEST_K:+-k "$PYTEST_K"} > gpurun_out/pytest_iter.log 2>&1; echo "rc=$?"; tail -15 gpurun_out/pytest_iter.log
 echo "== bench"; timeout 600 python bench.py --steps ${STEPS:-30} --warmup 5 --no-cpu-baseline $BENCH_ARGS > gpurun_out/bench_iter.log 2> gpurun_out/bench_iter.err; echo "rc=$?"
 python - <<'PY'
 import json
@@ -13,4 +13,4 @@ try:
 except Exception as e:
     print("bench parse failed", e); print(open('gpurun_out/bench_iter.err').read()[-2000:])
 PY
-echo "== phases"; timeout 300 python scripts/gpu_phases.py 2>&1 | tee gpurun_out/phases.log | tail -9
+echo "== phases"; timeout 300 python scripts/gpu_phases.py 2>&1 | tee gpurun_out/phases.log | tail -14

@@ -20,6 +20,7 @@ for s in range(5, 25): b.step(*acts[s])
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 20
 pc = b.phase_cycles(False)
-tot = sum(pc.values())
+tot = max(sum(pc.values()), 1)
 print(f"kernel+launch {ms:.4f} ms/step; grid CTAs x tiles; phase share of CTA time:")
-for k, v in pc.items(): print(f"  {k:22s} {v/tot:6.3f}  ({v/20/1e6:8.2f} Mcycles/step summed over CTAs)")
+for k, v in pc.items():
+    if v: print(f"  {k:22s} {v/tot:6.3f}  ({v/20/1e6:8.2f} Mcycles/step summed over CTAs)")
