@@ -68,8 +68,9 @@ class ClockSampler:
         self.gpu, self.rows, self.proc = gpu_index, [], None
 
     def start(self):
+        """Start sampling (call well before the timed region: nvidia-smi needs ~0.1-0.3 s before its first row)."""
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "10",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -77,15 +78,33 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def wait_first(self, timeout=3.0):
+        t0 = time.perf_counter()
+        while self.proc and not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.01)
+
+    def mark_begin(self):
+        self.t_begin = time.perf_counter()
+
+    def mark_end(self):
+        self.t_end = time.perf_counter()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
+        t0, t1 = getattr(self, "t_begin", 0.0), getattr(self, "t_end", float("inf"))
+        inside = [r for t, r in self.rows if t0 <= t <= t1 + 0.012]  # a row describes the ~10 ms before it was printed
+        window = "timed region"
+        if not inside:  # region shorter than the sampling period: the rows right around it
+            before = [r for t, r in self.rows if t < t0][-1:]
+            after = [r for t, r in self.rows if t > t1][:2]
+            inside, window = before + after, "rows adjacent to the timed region (region shorter than the 10 ms sampling period)"
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in inside:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 9:
                 continue
@@ -98,7 +117,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def measured_peak_gbs():
@@ -246,24 +265,28 @@ def run_ours(args):
     b.reset()
     S_words = b.export_state(0, 1).shape[1]  # canonical words (not the packed layout); packed size comes from the library
     packed_state_words = int(os.environ.get("CBX_STATE_WORDS", "0")) or None
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
     for s in range(W):
         b.step(tape_a[s], tape_d[s])
     b.stats_reset()
     b.enable_timing(True)
     launches0 = b.launch_count
     torch.cuda.synchronize()
+    if rank == 0:
+        clocks.wait_first()
     if world > 1:
         dist.barrier()
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    clocks.mark_begin()
     ev0.record()
     for s in range(W, W + K):
         b.step(tape_a[s], tape_d[s])
     ev1.record()
     torch.cuda.synchronize()
+    clocks.mark_end()
     if world > 1:
         dist.barrier()
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
@@ -275,14 +298,15 @@ def run_ours(args):
     total_ms = float(ms.item())
     launches = b.launch_count - launches0
     kernel_ms, kernel_n = b.step_kernel_ms()
+    kinfo = b.kernel_info()
     b.enable_timing(False)
 
     # ---- e2e: the same step through the public API with HOST action buffers and host-side results ----
     # host action buffers in page-locked memory (what a host-side policy loop would hand over)
-    h_a = torch.empty((K, n, 10), dtype=torch.int32, pin_memory=True)
-    h_d = torch.empty((K, n, 12), dtype=torch.int32, pin_memory=True)
-    h_a.copy_(tape_a[W:W + K]); h_d.copy_(tape_d[W:W + K])
-    h_a, h_d = h_a.numpy(), h_d.numpy()
+    CH = min(K, 64)  # the tape reaches the host in chunks (bounded page-locked memory); only the step_host calls are timed
+    h_a = torch.empty((CH, n, 10), dtype=torch.int32, pin_memory=True)
+    h_d = torch.empty((CH, n, 12), dtype=torch.int32, pin_memory=True)
+    h_an, h_dn = h_a.numpy(), h_d.numpy()
     b2 = Batch(comp, cfg, n, device=local)
     b2.reset()
     for s in range(W):
@@ -290,10 +314,15 @@ def run_ours(args):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    t0 = time.perf_counter()
-    for s in range(K):
-        out = b2.step_host(h_a[s], h_d[s])
-    e2e_s = time.perf_counter() - t0
+    e2e_s = 0.0
+    for c0 in range(0, K, CH):
+        c1 = min(K, c0 + CH)
+        h_a[: c1 - c0].copy_(tape_a[W + c0:W + c1]); h_d[: c1 - c0].copy_(tape_d[W + c0:W + c1])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for s in range(c1 - c0):
+            out = b2.step_host(h_an[s], h_dn[s])
+        e2e_s += time.perf_counter() - t0
     e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
@@ -320,8 +349,9 @@ def run_ours(args):
                        "l2": "per-step output (%.0f MB/GPU) larger than the 126 MB L2; no flush needed" % (ab["total"] * n / 1e6),
                        "algorithmic_bytes_per_env_step": ab},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                         "traffic": None, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
-                         "kernel": "cbx_step_kernel", "kernel_ms": kernel_ms, "kernel_launches_timed": kernel_n},
+                         "traffic": ncu_traffic(kinfo["name"], n, args.factored),
+                         "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
+                         "kernel": kinfo["name"], "kernel_launch": kinfo, "kernel_ms": kernel_ms, "kernel_launches_timed": kernel_n},
             "e2e": {"value": total_envs * K / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": n * (10 + 12) * 4,
                     "d2h_bytes_per_step": n * 12,
                     "note": "cbx_batch_step_host per step: H2D of this step's actions from page-locked host memory, the step kernel, "
@@ -339,6 +369,18 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def ncu_traffic(kernel, envs, factored):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the step kernel from the committed `ncu --set full` capture
+    (profiles/ncu_traffic.json, written by scripts/ncu_summary.py); None when no capture matches this kernel and workload."""
+    try:
+        t = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")))
+        if t.get("kernel") == kernel and int(t.get("envs", -1)) == int(envs) and bool(t.get("factored", False)) == bool(factored):
+            return float(t["dram_bytes_per_launch"])
+    except Exception:
+        pass
+    return None
+
+
 def _packed_state_words(comp, cfg):
     """Words of the packed per-env state (mirrors compute_layout in csrc/cbx_api.cu)."""
     n = comp.n_nodes
@@ -354,7 +396,7 @@ def _packed_state_words(comp, cfg):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=65536)

@@ -200,6 +200,15 @@ class Batch:
         _lib.check(self._L.cbx_batch_phase_cycles(self._h, int(enable), out))
         return {k: int(out[i]) for i, k in enumerate(self.PHASES)}
 
+    def kernel_info(self) -> dict:
+        """Which kernel a step launches and its launch shape (cbx_batch_kernel_info)."""
+        out = (C.c_int32 * 8)()
+        _lib.check(self._L.cbx_batch_kernel_info(self._h, out))
+        keys = ["pipelined", "ctas", "threads", "smem_bytes", "logic_warps", "encoder_warps", "encoder_variant", "tma"]
+        d = {k: int(out[i]) for i, k in enumerate(keys)}
+        d["name"] = "cbx_pipe_kernel" if d["pipelined"] else "cbx_step_kernel"
+        return d
+
     @property
     def launch_count(self) -> int:
         return int(self._L.cbx_batch_launch_count(self._h))

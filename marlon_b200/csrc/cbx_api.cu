@@ -402,6 +402,7 @@ int cbx_batch_create(const cbx_scenario* s, int64_t n_envs, const cbx_config* cf
       for (int k = 0; k < 4 && !ok && !(ewl || ewe); ++k) ok = plan_pipe(b->p, cand[k][0], cand[k][1], &Q);
       if (ok && cbx_pipe_attrs(b->p.enc.warp_env, Q.total_bytes) == cudaSuccess) {
         Q.enabled = 1;
+        { const char* lt = getenv("CBX_PIPE_LOGIC_TMA"); Q.logic_tma = !(lt && lt[0] == '0'); }
         b->p.pipe = Q;
         int per_sm = ect ? atoi(ect) : 1;
         if (per_sm < 1) per_sm = 1;
@@ -461,9 +462,14 @@ int cbx_batch_create(const cbx_scenario* s, int64_t n_envs, const cbx_config* cf
     ALLOC(v.def_outgoing_firewall, int8_t, 6 * L.n);
     ALLOC(v.def_services_status, int8_t, L.nservices);
   }
-  ALLOC(v.att_reward, float, 1); ALLOC(v.def_reward, float, 1);
-  ALLOC(v.att_terminated, uint8_t, 1); ALLOC(v.att_truncated, uint8_t, 1);
-  ALLOC(v.def_terminated, uint8_t, 1); ALLOC(v.def_truncated, uint8_t, 1);
+  {  // rewards and done flags share one block so that the host-buffer step reads them back with a single copy
+    uint8_t* blk = nullptr;
+    ALLOC(blk, uint8_t, 12);
+    const size_t np = (size_t)b->p.n_pad;
+    v.att_reward = (float*)blk; v.def_reward = (float*)(blk + 4 * np);
+    v.att_terminated = blk + 8 * np; v.att_truncated = blk + 9 * np;
+    v.def_terminated = blk + 10 * np; v.def_truncated = blk + 11 * np;
+  }
   ALLOC(v.att_info, int32_t, 8);
   ALLOC(v.network_availability, double, 1);
   { void* ps = nullptr; cudaError_t e = dalloc(&ps, CBX_STAT_COUNT * sizeof(double));
@@ -613,12 +619,16 @@ int cbx_batch_step_host(cbx_batch* b, const int32_t* h_att, const int32_t* h_def
   const cbx_views& v = b->p.v;
   const bool out_pinned = is_pinned(host_out);
   uint8_t* o = out_pinned ? (uint8_t*)host_out : b->h_out;
-  CUDA_TRY(cudaMemcpyAsync(o, v.att_reward, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaMemcpyAsync(o + (size_t)n * 4, v.def_reward, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaMemcpyAsync(o + (size_t)n * 8, v.att_terminated, (size_t)n, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaMemcpyAsync(o + (size_t)n * 9, v.att_truncated, (size_t)n, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaMemcpyAsync(o + (size_t)n * 10, v.def_terminated, (size_t)n, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaMemcpyAsync(o + (size_t)n * 11, v.def_truncated, (size_t)n, cudaMemcpyDeviceToHost, st));
+  if (b->p.n_pad == n) {  // [att_reward | def_reward | att_terminated | att_truncated | def_terminated | def_truncated] is one block
+    CUDA_TRY(cudaMemcpyAsync(o, v.att_reward, out_bytes, cudaMemcpyDeviceToHost, st));
+  } else {
+    CUDA_TRY(cudaMemcpyAsync(o, v.att_reward, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(o + (size_t)n * 4, v.def_reward, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(o + (size_t)n * 8, v.att_terminated, (size_t)n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(o + (size_t)n * 9, v.att_truncated, (size_t)n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(o + (size_t)n * 10, v.def_terminated, (size_t)n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(o + (size_t)n * 11, v.def_truncated, (size_t)n, cudaMemcpyDeviceToHost, st));
+  }
   CUDA_TRY(cudaStreamSynchronize(st));
   if (!out_pinned) memcpy(host_out, o, out_bytes);
   return CBX_OK;
@@ -735,6 +745,20 @@ int cbx_batch_phase_cycles(cbx_batch* b, int enable, uint64_t* out16) {
     CUDA_TRY(cudaMemset(b->p.prof, 0, 16 * sizeof(unsigned long long)));
   }
   if (!enable) b->p.prof = nullptr;
+  return CBX_OK;
+}
+
+int cbx_batch_kernel_info(const cbx_batch* b, int32_t* out8) {
+  if (!b || !out8) return fail(CBX_ERR_INVALID, "null argument");
+  const cbx_pipe_plan& Q = b->p.pipe;
+  out8[0] = Q.enabled;
+  out8[1] = Q.enabled ? b->pipe_grid : b->grid;
+  out8[2] = Q.enabled ? (Q.wl + Q.we) * 32 : CBX_THREADS;
+  out8[3] = Q.enabled ? Q.total_bytes : b->smem_bytes;
+  out8[4] = Q.enabled ? Q.wl : 0;
+  out8[5] = Q.enabled ? Q.we : 0;
+  out8[6] = b->p.enc.warp_env;
+  out8[7] = b->use_tma;
   return CBX_OK;
 }
 

@@ -101,6 +101,9 @@ struct cbx_pipe_plan {
   int enabled;
   int wl, we, nslot;
   int gs;           // connect-mask rows per bulk copy: 1 when a row is a multiple of 16 bytes, 2 when it is 8 mod 16
+  int logic_tma;    // 1 (default): the logic warps move their state tile / field images with TMA bulk copies too;
+                    // 0 (CBX_PIPE_LOGIC_TMA=0): with plain 16-byte loads / stores (measured slower: HBM read latency
+                    // under the write stream is ~12 us, the TMA queue hides more of it)
   // shared-memory carve-up in 32-bit words
   int tables, lut, bars, zero, def_static;
   int lbufs, lbuf_words;    // per logic warp: state tile | staging | actions (aliased by the props image) | field images

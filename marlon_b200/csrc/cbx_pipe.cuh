@@ -311,12 +311,20 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
       const int tile = (int)blockIdx.x + j * (int)gridDim.x;
       const int64_t e0 = (int64_t)tile * CBX_TILE;
       const int n_valid = (int)min((int64_t)CBX_TILE, p.n_envs - e0);
-      // the previous tile's state store and field copies (issued by lanes 0..6) must be done reading this warp's buffer
-      tma_store_wait_read();
-      __syncwarp();
-      if (lane == 0) {
-        mbar_expect_tx(&bar_load[warp], (uint32_t)L.S * kRowBytes);
-        tma_load_1d(lb, p.state + (int64_t)tile * L.S * CBX_TILE, (uint32_t)L.S * kRowBytes, &bar_load[warp]);
+      const uint4* gstate = reinterpret_cast<const uint4*>(p.state + (int64_t)tile * L.S * CBX_TILE);
+      const int state_q = L.S * CBX_TILE / 4;  // 16-byte words of a state tile
+      if (Q.logic_tma) {
+        // the previous tile's state store and field copies (issued by lanes 0..6) must be done reading this warp's buffer
+        tma_store_wait_read();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_expect_tx(&bar_load[warp], (uint32_t)L.S * kRowBytes);
+          tma_load_1d(lb, gstate, (uint32_t)L.S * kRowBytes, &bar_load[warp]);
+        }
+      } else {
+        uint4* d = reinterpret_cast<uint4*>(lb);
+#pragma unroll 7
+        for (int q = lane; q < state_q; q += 32) d[q] = gstate[q];
       }
       if (!reset_only) {
         if (p.att_actions && (who_att || !marlon))
@@ -324,8 +332,10 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
         if (def_on)
           for (int q = lane; q < n_valid * 12; q += 32) act[CBX_TILE * 10 + q] = p.def_actions[e0 * 12 + q];
       }
-      mbar_wait(&bar_load[warp], load_phase);
-      load_phase ^= 1;
+      if (Q.logic_tma) {
+        mbar_wait(&bar_load[warp], load_phase);
+        load_phase ^= 1;
+      }
       __syncwarp();
       CBX_PPROF(9)  // state tile + actions in
       const bool active = lane < n_valid;
@@ -389,29 +399,49 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
       if (active && !keep) build_field_images<D>(c, desc + lane * DW, im, lane, dense);
       // deferred defender auto-reset (DummyVecEnv resets after the step; the observations above were taken before it)
       if (active && def_done) c.defender_reset(s_init);
-      fence_async_smem();
+      if (Q.logic_tma) fence_async_smem();
       __syncwarp();
       {
         const Target tm = make_target(p.v, L, e0, false);
-        if (n_valid == CBX_TILE && enc_mask == 0xFFFFFFFFu) {
+        const bool full = n_valid == CBX_TILE && enc_mask == 0xFFFFFFFFu;
+        if (Q.logic_tma) {
           if (lane == 0) tma_store_1d(p.state + (int64_t)tile * L.S * CBX_TILE, lb, (uint32_t)L.S * kRowBytes);
-          if (lane == 1) tma_store_1d(tm.scalars, im.scal, CBX_TILE * 32u);
-          if (lane == 2) tma_store_1d(tm.leaked, im.leak, (uint32_t)(CBX_TILE * 4 * wpe_leak));
-          if (lane == 3) tma_store_1d(tm.cachem, im.cachem, (uint32_t)(CBX_TILE * 4 * wpe_cachem));
-          if (lane == 4) tma_store_1d(tm.props, im.props, (uint32_t)(CBX_TILE * 4 * wpe_props));
-          if (lane == 5) tma_store_1d(tm.priv, im.priv, (uint32_t)(CBX_TILE * 4 * wpe_priv));
-          if (lane == 6 && dense) tma_store_1d(tm.local, im.local, (uint32_t)(CBX_TILE * 4 * wpe_local));
+          if (full) {
+            if (lane == 1) tma_store_1d(tm.scalars, im.scal, CBX_TILE * 32u);
+            if (lane == 2) tma_store_1d(tm.leaked, im.leak, (uint32_t)(CBX_TILE * 4 * wpe_leak));
+            if (lane == 3) tma_store_1d(tm.cachem, im.cachem, (uint32_t)(CBX_TILE * 4 * wpe_cachem));
+            if (lane == 4) tma_store_1d(tm.props, im.props, (uint32_t)(CBX_TILE * 4 * wpe_props));
+            if (lane == 5) tma_store_1d(tm.priv, im.priv, (uint32_t)(CBX_TILE * 4 * wpe_priv));
+            if (lane == 6 && dense) tma_store_1d(tm.local, im.local, (uint32_t)(CBX_TILE * 4 * wpe_local));
+          }
           if (lane < 7) tma_store_commit();
         } else {
-          if (lane == 0) { tma_store_1d(p.state + (int64_t)tile * L.S * CBX_TILE, lb, (uint32_t)L.S * kRowBytes); tma_store_commit(); }
+          // plain 16-byte copies: a tile's rows are contiguous in every tensor (fully coalesced 512-byte warp stores)
+          auto copy16 = [&](void* dst, const void* src, int n16) {
+            uint4* dd = reinterpret_cast<uint4*>(dst);
+            const uint4* ss = reinterpret_cast<const uint4*>(src);
+#pragma unroll 4
+            for (int q = lane; q < n16; q += 32) dd[q] = ss[q];
+          };
+          copy16(p.state + (int64_t)tile * L.S * CBX_TILE, lb, state_q);
+          if (full) {
+            copy16(tm.scalars, im.scal, CBX_TILE * 8 / 4);
+            copy16(tm.leaked, im.leak, CBX_TILE * wpe_leak / 4);
+            copy16(tm.cachem, im.cachem, CBX_TILE * wpe_cachem / 4);
+            copy16(tm.props, im.props, CBX_TILE * wpe_props / 4);
+            copy16(tm.priv, im.priv, CBX_TILE * wpe_priv / 4);
+            if (dense) copy16(tm.local, im.local, CBX_TILE * wpe_local / 4);
+          }
+        }
+        if (!full) {
           copy_field_rows(tm.scalars, im.scal, 8, n_valid, enc_mask, lane);
           copy_field_rows(tm.leaked, im.leak, wpe_leak, n_valid, enc_mask, lane);
           copy_field_rows(tm.cachem, im.cachem, wpe_cachem, n_valid, enc_mask, lane);
           copy_field_rows(tm.props, im.props, wpe_props, n_valid, enc_mask, lane);
           copy_field_rows(tm.priv, im.priv, wpe_priv, n_valid, enc_mask, lane);
           if (dense) copy_field_rows(reinterpret_cast<int32_t*>(tm.local), reinterpret_cast<const int32_t*>(im.local), wpe_local, n_valid, enc_mask, lane);
-          __syncwarp();
         }
+        __syncwarp();
       }
       CBX_PPROF(11)  // field images + state write-back
     }
