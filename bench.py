@@ -28,9 +28,27 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 
-def workload_config(mask_mode=0):
+WORKLOADS = {
+    "toyctf": "CyberBattleToyCtf-v0 (N=12,C=10) MARLon attacker+defender pair step (AttackerEnvWrapper + DefenderEnvWrapper, "
+              "reference_stale defender, SB3 auto-reset)",
+    "chain100": "CyberBattleChain-v0 size=100 (N=102,C=102) MARLon attacker+defender pair step (config 4: the 1M-env sharded case; "
+                "factored masks -- a dense connect mask would be 8.5 MB per env)",
+}
+
+
+def workload_config(mask_mode=0, workload="toyctf"):
     from marlon_b200 import _abi, config, scenario, scenarios
 
+    if workload == "chain100":
+        comp = scenario.compile_scenario(scenarios.chain_environment(100))
+        cfg = config.make_config(
+            _abi.MODE_MARLON, maximum_node_count=102, maximum_total_credentials=102, maximum_discoverable_credentials_per_action=5,
+            throws_on_invalid_actions=False, attacker_goal=config.AttackerGoal(own_atleast_percent=1.0),
+            defender_constraint=config.DefenderConstraint(0.60), losing_reward=-5000.0,
+            attacker_max_timesteps=2000, attacker_invalid_action_reward_modifier=-1.0,
+            defender_enabled=True, defender_max_timesteps=2000, defender_invalid_action_reward=-1,
+            defender_reset_on_constraint_broken=True, defender_loss_reward=-5000.0, mask_mode=1)
+        return comp, cfg
     comp = scenario.compile_scenario(scenarios.toyctf_environment())
     # MultiAgentUniverse.build defaults (multiagent_universe.py:78-95) with ppo/train_marl.py:12-14 bounds
     cfg = config.make_config(
@@ -244,7 +262,8 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
-    comp, cfg = workload_config(mask_mode=1 if args.factored else 0)
+    comp, cfg = workload_config(mask_mode=1 if args.factored else 0, workload=args.workload)
+    factored = bool(cfg.mask_mode)
     n = args.envs_per_gpu
     K, W = args.steps, args.warmup
 
@@ -342,14 +361,13 @@ def run_ours(args):
             "metric": "attacker+defender env-steps/sec", "value": total_envs * K / (total_ms * 1e-3), "unit": "env-steps/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "CyberBattleToyCtf-v0 (N=12,C=10) MARLon attacker+defender pair step (AttackerEnvWrapper + "
-                                   "DefenderEnvWrapper, reference_stale defender, SB3 auto-reset), "
-                                   + ("factored" if args.factored else "dense int8") + " action masks, random valid actions",
+            "config": {"workload": WORKLOADS[args.workload] + ", " + ("factored" if factored else "dense int8")
+                                   + " action masks, random valid actions",
                        "envs_per_gpu": n, "total_envs": total_envs, "parallelism": f"env-sharded x{world}, no data-path collective",
                        "l2": "per-step output (%.0f MB/GPU) larger than the 126 MB L2; no flush needed" % (ab["total"] * n / 1e6),
                        "algorithmic_bytes_per_env_step": ab},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                         "traffic": ncu_traffic(kinfo["name"], n, args.factored),
+                         "traffic": ncu_traffic(kinfo["name"], n, factored) if args.workload == "toyctf" else None,
                          "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
                          "kernel": kinfo["name"], "kernel_launch": kinfo, "kernel_ms": kernel_ms, "kernel_launches_timed": kernel_n},
             "e2e": {"value": total_envs * K / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": n * (10 + 12) * 4,
@@ -402,6 +420,7 @@ def main():
     ap.add_argument("--envs-per-gpu", type=int, default=65536)
     ap.add_argument("--seed", type=int, default=2026)
     ap.add_argument("--factored", action="store_true", help="factored masks instead of dense int8 masks")
+    ap.add_argument("--workload", default="toyctf", choices=sorted(WORKLOADS), help="toyctf = the headline configuration")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()

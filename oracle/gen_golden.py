@@ -291,7 +291,8 @@ def sample_raw_action(env, rng, p_valid):
     return a, out
 
 
-def record_raw(name, env_id, env_kwargs, n_tapes, steps, seed, p_valid=0.5, scripted=None, auto_reset=True):
+def record_raw(name, env_id, env_kwargs, n_tapes, steps, seed, p_valid=0.5, scripted=None, auto_reset=True, factory=None,
+               meta_kwargs=None):
     """One file, `n_tapes` independent envs x `steps` steps; arrays are [steps, n_tapes, ...]."""
     scan = env_kwargs.get("defender_agent")
     cap = scan.scan_capacity if scan else 0
@@ -305,7 +306,7 @@ def record_raw(name, env_id, env_kwargs, n_tapes, steps, seed, p_valid=0.5, scri
             d.tape = DrawTape(rng, cap)
             kw["defender_agent"] = d
             tapes.append(d.tape)
-        env = ref_loader.make(env_id, **kw)
+        env = factory(**kw) if factory else ref_loader.make(env_id, **kw)
         env.reset(seed=seed + t)
         envs.append(env)
         rngs.append(rng)
@@ -354,7 +355,7 @@ def record_raw(name, env_id, env_kwargs, n_tapes, steps, seed, p_valid=0.5, scri
             for k, v in r.items():
                 row.setdefault(k, []).append(v)
         rec.add(**{k: np.stack(v) for k, v in row.items()})
-    meta = dict(kind="raw", env_id=env_id, env_kwargs=env_kwargs_meta(env_kwargs), n_tapes=n_tapes, steps=steps,
+    meta = dict(kind="raw", env_id=env_id, env_kwargs=env_kwargs_meta(dict(env_kwargs, **(meta_kwargs or {}))), n_tapes=n_tapes, steps=steps,
                 auto_reset=auto_reset, N=N, C=C, LEAK=LEAK, fingerprint=comp.fingerprint(), node_ids=comp.node_ids,
                 scan_capacity=cap)
     save(name, meta, rec)
@@ -362,11 +363,11 @@ def record_raw(name, env_id, env_kwargs, n_tapes, steps, seed, p_valid=0.5, scri
 
 # ---- MARLon attacker+defender tapes ------------------------------------------------------------------------
 def record_marlon(name, env_id, env_kwargs, att_kwargs, def_kwargs, n_tapes, steps, seed, with_defender=True,
-                  p_att_valid=0.0, p_def_empty=0.0):
+                  p_att_valid=0.0, p_def_empty=0.0, factory=None, meta_kwargs=None):
     rec = Recorder()
     units = []
     for t in range(n_tapes):
-        env = ref_loader.make(env_id, **env_kwargs)
+        env = factory(**env_kwargs) if factory else ref_loader.make(env_id, **env_kwargs)
         es = EnvironmentEventSource()
         att = AttackerEnvWrapper(env, es, **att_kwargs)
         dfn = DefenderEnvWrapper(env, att, es, defender=True, **def_kwargs) if with_defender else None
@@ -443,7 +444,7 @@ def record_marlon(name, env_id, env_kwargs, att_kwargs, def_kwargs, n_tapes, ste
             for k, v in r.items():
                 row.setdefault(k, []).append(v)
         rec.add(**{k: np.stack(v) for k, v in row.items()})
-    meta = dict(kind="marlon", env_id=env_id, env_kwargs=env_kwargs_meta(env_kwargs), att_kwargs=att_kwargs,
+    meta = dict(kind="marlon", env_id=env_id, env_kwargs=env_kwargs_meta(dict(env_kwargs, **(meta_kwargs or {}))), att_kwargs=att_kwargs,
                 def_kwargs=def_kwargs, with_defender=with_defender, n_tapes=n_tapes, steps=steps, N=N, C=C, LEAK=LEAK,
                 fingerprint=comp.fingerprint(), node_ids=comp.node_ids, kind_of_index=kind_of_index,
                 att_nvec=att_nvec, def_nvec=def_nvec)
@@ -597,5 +598,57 @@ def main():
                   seed=52345, with_defender=False, p_att_valid=0.9)
 
 
+# ---- CyberBattleRandom: the reference's generator functions, seeded (configs[4]) ---------------------------------
+def ref_random_environment(seed):
+    """What ``generate_network.new_environment(15)`` builds (generate_network.py:266-294), with the seed it leaves out:
+    the reference's own two functions, its own parameter values, ``random.seed(seed)`` for the global stream they draw from."""
+    from cyberbattle.simulation import generate_network as gen
+    from cyberbattle.simulation import model as ref_model
+
+    random.seed(seed)
+    traffic = gen.generate_random_traffic_network(
+        seed=seed, n_clients=50, n_servers={"SMB": 15, "HTTP": 15, "RDP": 15},
+        alpha=np.array([(1, 1), (0.2, 0.5)], dtype=float), beta=np.array([(1000, 10), (10, 100)], dtype=float))
+    network = gen.cyberbattle_model_from_traffic_graph(
+        traffic, cached_rdp_password_probability=0.8, cached_smb_password_probability=0.7,
+        cached_accessed_network_shares_probability=0.8, cached_password_has_changed_probability=0.01,
+        probability_two_nodes_use_same_password_to_access_given_resource=0.9)
+    return ref_model.Environment(network=network, vulnerability_library=dict([]), identifiers=gen.ENV_IDENTIFIERS)
+
+
+def main_random():
+    """Only the CyberBattleRandom fixtures (the other tapes are left alone): table fingerprints of seeds 0..11 and tapes on
+    two of the networks."""
+    fp_path = os.path.join(GOLDEN, "scenario_fingerprints.json")
+    fps = json.load(open(fp_path))
+    for seed in range(12):
+        comp = scenario.compile_scenario(ref_random_environment(seed))
+        fps[f"CyberBattleRandom-v0:seed={seed}"] = comp.fingerprint()
+        print("seed", seed, "nodes", comp.n_nodes, "credentials", len(comp.triples), "services", comp.n_services)
+    json.dump(fps, open(fp_path, "w"), indent=1, sort_keys=True)
+    AG, DC = ref_env.AttackerGoal, ref_env.DefenderConstraint
+    Scan = ref_defender.ScanAndReimageCompromisedMachines
+
+    def factory(seed):
+        return lambda **kw: ref_env.CyberBattleEnv(initial_environment=ref_random_environment(seed), **kw)
+
+    # CyberBattleRandom fixes maximum_discoverable_credentials_per_action=32 (cyberbattle_random.py:14); 65 nodes,
+    # <= 100 credentials: bounds (72, 104) keep the dense masks of a tape small
+    r3 = dict(maximum_node_count=72, maximum_total_credentials=104, maximum_discoverable_credentials_per_action=32,
+              throws_on_invalid_actions=False, attacker_goal=AG(own_atleast_percent=1.0))
+    record_raw("raw_random3_valid", "CyberBattleRandom-v0", r3, 6, 400, seed=6000, p_valid=0.9, factory=factory(3), meta_kwargs=dict(seed=3))
+    r0 = dict(r3, defender_agent=Scan(probability=0.6, scan_capacity=2, scan_frequency=5), defender_constraint=DC(maintain_sla=0.80))
+    record_raw("raw_random0_scan", "CyberBattleRandom-v0", r0, 6, 400, seed=7000, p_valid=0.9, factory=factory(0), meta_kwargs=dict(seed=0))
+    akw = dict(max_timesteps=300, invalid_action_reward_modifier=-1.0, invalid_action_reward_multiplier=1.0, loss_reward=-5000.0)
+    dkw = dict(max_timesteps=300, invalid_action_reward=-1, reset_on_constraint_broken=True, loss_reward=-5000.0)
+    m3 = dict(maximum_node_count=72, maximum_total_credentials=104, maximum_discoverable_credentials_per_action=32,
+              throws_on_invalid_actions=False, defender_constraint=DC(maintain_sla=0.60), losing_reward=-5000.0)
+    record_marlon("marlon_random3_valid", "CyberBattleRandom-v0", m3, akw, dkw, 4, 400, seed=62345, p_att_valid=0.9, p_def_empty=0.5,
+                  factory=factory(3), meta_kwargs=dict(seed=3))
+
+
 if __name__ == "__main__":
-    main()
+    if "--random" in sys.argv:
+        main_random()
+    else:
+        main()
