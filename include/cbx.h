@@ -311,6 +311,16 @@ int cbx_scenario_destroy(cbx_scenario* s);
 
 int cbx_config_default(cbx_config* cfg);
 int cbx_batch_create(const cbx_scenario* s, int64_t n_envs, const cbx_config* cfg, int device, cbx_batch** out);
+
+/* One batch over SEVERAL scenarios of one Identifiers family (configs[4]: CyberBattleRandom networks generated by
+ * simulation/generate_network.py:266-294, a different network per group of envs).  Envs are grouped by scenario:
+ * envs_per_scenario[k] consecutive envs play scenarios[k]; every group but the last must be a multiple of 32 envs.
+ * The ports / vulnerability ids / properties must agree; node, credential and service counts may differ: the per-env
+ * state and the n-sized observation arrays (defender observation, cbx_batch_export_state) are laid out for the largest
+ * scenario and zero-padded, the game's arithmetic (availability, scan targets, ownership ratios) uses each scenario's
+ * own counts.  Bounds (maximum_node_count, ...) come from cfg and must hold the largest scenario. */
+int cbx_batch_create_multi(const cbx_scenario* const* scenarios, int n_scenarios, const int64_t* envs_per_scenario,
+                           const cbx_config* cfg, int device, cbx_batch** out);
 int cbx_batch_destroy(cbx_batch* b);
 
 /* Reset envs whose mask byte is non-zero (all when mask == NULL; device pointer [n]) and write their
@@ -353,6 +363,8 @@ int cbx_batch_stats_reset(cbx_batch* b, void* cuda_stream);
 
 int64_t cbx_export_words(const cbx_scenario* s, const cbx_config* cfg);
 /* Canonical state of envs [env_begin, env_end) into a HOST buffer; synchronises the stream. */
+/* words per env written by cbx_batch_export_state for this batch (multi-scenario batches: the largest scenario's) */
+int64_t cbx_batch_export_words(const cbx_batch* b);
 int cbx_batch_export_state(cbx_batch* b, int64_t env_begin, int64_t env_end, int32_t* host_out, void* cuda_stream);
 
 /* Number of kernels this library has launched on behalf of the batch so far (bench.py's gpu_launches). */

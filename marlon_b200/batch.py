@@ -24,27 +24,44 @@ class _DevArray:
 
 
 class Batch:
-    def __init__(self, compiled: CompiledScenario, cfg: _abi.Config, n_envs: int, device: int = 0):
+    def __init__(self, compiled, cfg: _abi.Config, n_envs, device: int = 0):
+        """`compiled`: one CompiledScenario, or a list of them with `n_envs` the list of envs per scenario (envs grouped by
+        scenario, every group but the last a multiple of 32: ``cbx_batch_create_multi``; e.g. CyberBattleRandom networks)."""
         import torch
 
         if not torch.cuda.is_available():
             raise RuntimeError("marlon_b200.Batch needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self._torch = torch
         self._L = _lib.load()
-        self.compiled, self.cfg, self.n_envs, self.device = compiled, cfg, int(n_envs), int(device)
+        multi = isinstance(compiled, (list, tuple))
+        self.scenarios = list(compiled) if multi else [compiled]
+        self.envs_per_scenario = [int(x) for x in n_envs] if multi else [int(n_envs)]
+        if len(self.scenarios) != len(self.envs_per_scenario):
+            raise ValueError("one env count per scenario")
+        self.compiled, self.cfg, self.n_envs, self.device = self.scenarios[0], cfg, sum(self.envs_per_scenario), int(device)
         self.torch_device = torch.device("cuda", self.device)
-        blob = compiled.tobytes()
-        self._scn = C.c_void_p()
-        _lib.check(self._L.cbx_scenario_create(blob, len(blob), C.byref(self._scn)))
+        self._scns = []
         self._h = C.c_void_p()
         try:
+            for comp in self.scenarios:
+                blob = comp.tobytes()
+                h = C.c_void_p()
+                _lib.check(self._L.cbx_scenario_create(blob, len(blob), C.byref(h)))
+                self._scns.append(h)
             with torch.cuda.device(self.device):
                 torch.cuda.init()
-                _lib.check(self._L.cbx_batch_create(self._scn, self.n_envs, C.byref(cfg), self.device, C.byref(self._h)))
+                if multi:
+                    arr = (C.c_void_p * len(self._scns))(*[h.value for h in self._scns])
+                    cnt = (C.c_int64 * len(self._scns))(*self.envs_per_scenario)
+                    _lib.check(self._L.cbx_batch_create_multi(arr, len(self._scns), cnt, C.byref(cfg), self.device, C.byref(self._h)))
+                else:
+                    _lib.check(self._L.cbx_batch_create(self._scns[0], self.n_envs, C.byref(cfg), self.device, C.byref(self._h)))
         except Exception:
-            self._L.cbx_scenario_destroy(self._scn)
-            self._scn = None
+            for h in self._scns:
+                self._L.cbx_scenario_destroy(h)
+            self._scns = []
             raise
+        self._scn = self._scns[0]
         v = _abi.Views()
         _lib.check(self._L.cbx_batch_views(self._h, C.byref(v)))
         self.views = v
@@ -70,9 +87,9 @@ class Batch:
             self.tensors.clear()
             self._L.cbx_batch_destroy(self._h)
             self._h = None
-        if getattr(self, "_scn", None):
-            self._L.cbx_scenario_destroy(self._scn)
-            self._scn = None
+        for h in getattr(self, "_scns", []):
+            self._L.cbx_scenario_destroy(h)
+        self._scns, self._scn = [], None
 
     def __del__(self):
         try:
@@ -168,7 +185,7 @@ class Batch:
 
     def export_state(self, begin: int = 0, end: Optional[int] = None) -> np.ndarray:
         end = self.n_envs if end is None else end
-        w = self._L.cbx_export_words(self._scn, C.byref(self.cfg))
+        w = self._L.cbx_batch_export_words(self._h)
         out = np.zeros((end - begin, w), dtype=np.int32)
         with self._torch.cuda.device(self.device):
             _lib.check(self._L.cbx_batch_export_state(self._h, begin, end, out.ctypes.data, self._stream()))

@@ -143,7 +143,9 @@ struct cbx_batch {
   size_t ev_used;
   double ms_sum;
   int64_t ms_count;
-  const cbx_scenario* scn;
+  const cbx_scenario* scn;       // dimensions the layout was computed from (== &vscn for a multi-scenario batch)
+  cbx_scenario vscn;             // multi-scenario batch: the element-wise maximum of the scenarios' dimensions (no blob)
+  int32_t* d_tile_scn;
   std::vector<uint32_t> init_state;
 };
 
@@ -272,7 +274,7 @@ static void build_init_state(const cbx_scenario* s, const cbx_layout& L, std::ve
   auto setbyte = [&](int off, int i, uint32_t v) { st[off + i / 4] = (st[off + i / 4] & ~(0xFFu << ((i & 3) * 8))) | (v << ((i & 3) * 8)); };
   for (int i = 0; i < ((L.n + 3) / 4) * 4; ++i) setbyte(L.o_disc_idx, i, 0xFFu);
   int nd = 0;
-  for (int i = 0; i < L.n; ++i) {
+  for (int i = 0; i < s->n; ++i) {  // the scenario's own nodes (L.n is the padded count in a multi-scenario batch)
     const uint32_t* r = node + (size_t)i * CBX_NODE_WORDS;
     uint32_t f = r[CBX_N_FLAGS];
     int priv = (f >> 2) & 3;
@@ -291,8 +293,38 @@ static void build_init_state(const cbx_scenario* s, const cbx_layout& L, std::ve
   st[L.o_hdr] = (uint32_t)nd;
 }
 
+static int create_impl(const cbx_scenario* const* scns, int n_scn, const int64_t* counts, int64_t n_envs, const cbx_config* cfg, int device,
+                       cbx_batch** out);
+
 int cbx_batch_create(const cbx_scenario* s, int64_t n_envs, const cbx_config* cfg, int device, cbx_batch** out) {
-  if (!s || !cfg || !out) return fail(CBX_ERR_INVALID, "null argument");
+  if (!s) return fail(CBX_ERR_INVALID, "null argument");
+  return create_impl(&s, 1, &n_envs, n_envs, cfg, device, out);
+}
+
+int cbx_batch_create_multi(const cbx_scenario* const* scenarios, int n_scenarios, const int64_t* envs_per_scenario, const cbx_config* cfg,
+                           int device, cbx_batch** out) {
+  if (!scenarios || !envs_per_scenario || n_scenarios < 1) return fail(CBX_ERR_INVALID, "null argument");
+  int64_t total = 0;
+  const cbx_scenario* s0 = scenarios[0];
+  for (int k = 0; k < n_scenarios; ++k) {
+    const cbx_scenario* s = scenarios[k];
+    if (!s) return fail(CBX_ERR_INVALID, "scenario %d is null", k);
+    if (envs_per_scenario[k] <= 0) return fail(CBX_ERR_INVALID, "scenario %d has no envs", k);
+    if (k + 1 < n_scenarios && envs_per_scenario[k] % CBX_TILE)
+      return fail(CBX_ERR_INVALID, "envs_per_scenario[%d] = %lld: every group but the last must be a multiple of %d envs (a tile shares one "
+                  "scenario's tables)", k, (long long)envs_per_scenario[k], CBX_TILE);
+    // one observation / action space for the whole batch: the identifier-derived dimensions must agree
+    if (s->P != s0->P || s->L != s0->L || s->R != s0->R || s->nprops != s0->nprops || s->flags != s0->flags)
+      return fail(CBX_ERR_INVALID, "scenario %d: ports / vulnerability ids / properties differ from scenario 0 (one batch, one Identifiers)", k);
+    total += envs_per_scenario[k];
+  }
+  return create_impl(scenarios, n_scenarios, envs_per_scenario, total, cfg, device, out);
+}
+
+static int create_impl(const cbx_scenario* const* scns, int n_scn, const int64_t* counts, int64_t n_envs, const cbx_config* cfg, int device,
+                       cbx_batch** out) {
+  if (!cfg || !out) return fail(CBX_ERR_INVALID, "null argument");
+  const cbx_scenario* s = scns[0];
   if (cfg->abi_version != CBX_ABI_VERSION) return fail(CBX_ERR_INVALID, "config abi_version %d, library %d", cfg->abi_version, CBX_ABI_VERSION);
   if (n_envs <= 0) return fail(CBX_ERR_INVALID, "n_envs must be positive");
   if (device < 0) return fail(CBX_ERR_NODEVICE, "device %d: this library has no CPU path", device);
@@ -308,7 +340,21 @@ int cbx_batch_create(const cbx_scenario* s, int64_t n_envs, const cbx_config* cf
   cbx_batch* b = new cbx_batch();
   memset(&b->p, 0, sizeof(b->p));
   b->device = device; b->launches = 0; b->sample_step = 0; b->timing = 0; b->ev_used = 0; b->ms_sum = 0; b->ms_count = 0;
-  b->h_att = b->h_def = b->d_att = b->d_def = nullptr; b->h_out = nullptr; b->scn = s;
+  b->h_att = b->h_def = b->d_att = b->d_def = nullptr; b->h_out = nullptr; b->scn = s; b->d_tile_scn = nullptr;
+  size_t max_blob = s->blob.size();
+  if (n_scn > 1) {  // padded layout: the maximum of every per-scenario dimension
+    cbx_scenario& v = b->vscn;
+    v.n = s->n; v.P = s->P; v.nprops = s->nprops; v.L = s->L; v.R = s->R; v.nsecrets = s->nsecrets; v.ntriples = s->ntriples;
+    v.nservices = s->nservices; v.max_leak = s->max_leak; v.flags = s->flags;
+    for (int k = 1; k < n_scn; ++k) {
+      const cbx_scenario* q = scns[k];
+      v.n = q->n > v.n ? q->n : v.n; v.nsecrets = q->nsecrets > v.nsecrets ? q->nsecrets : v.nsecrets;
+      v.ntriples = q->ntriples > v.ntriples ? q->ntriples : v.ntriples; v.nservices = q->nservices > v.nservices ? q->nservices : v.nservices;
+      v.max_leak = q->max_leak > v.max_leak ? q->max_leak : v.max_leak;
+      max_blob = q->blob.size() > max_blob ? q->blob.size() : max_blob;
+    }
+    b->scn = s = &b->vscn;
+  }
   int rc = compute_layout(s, cfg, n_envs, &b->p.lay);
   if (rc) { delete b; return rc; }
   cbx_layout& L = b->p.lay;
@@ -316,7 +362,10 @@ int cbx_batch_create(const cbx_scenario* s, int64_t n_envs, const cbx_config* cf
   b->p.n_envs = n_envs;
   b->p.n_pad = (n_envs + CBX_TILE - 1) / CBX_TILE * CBX_TILE;
   b->p.n_tiles = (int)(b->p.n_pad / CBX_TILE);
-  b->p.table_words = (int)s->blob.size();
+  b->p.table_words = (int)max_blob;
+  b->p.n_scenarios = n_scn;
+  b->p.table_stride = (int)max_blob + ((b->p.lay.S + 3) & ~3);
+  b->p.tile_scn = nullptr;
   int col = 1;
   for (int k = 0; k < 3; ++k) {
     int kind = cfg->kind_of_index[k];
@@ -393,7 +442,7 @@ int cbx_batch_create(const cbx_scenario* s, int64_t n_envs, const cbx_config* cf
   b->p.pipe.enabled = 0; b->pipe_grid = 0;
   {
     const char* pe = getenv("CBX_PIPE");
-    if (b->use_tma && !(pe && pe[0] == '0')) {
+    if (b->use_tma && n_scn == 1 && !(pe && pe[0] == '0')) {
       const char *ewl = getenv("CBX_PIPE_WL"), *ewe = getenv("CBX_PIPE_WE"), *ect = getenv("CBX_PIPE_CTAS");
       const int cand[4][2] = {{4, 8}, {3, 8}, {2, 8}, {2, 4}};
       cbx_pipe_plan Q;
@@ -427,10 +476,17 @@ int cbx_batch_create(const cbx_scenario* s, int64_t n_envs, const cbx_config* cf
       cbx_batch_destroy(b); return _rc; }                                                                          \
     field = (type*)_p;                                                                                             \
   } while (0)
-  build_init_state(s, L, b->init_state);
   {
-    std::vector<uint32_t> tab(s->blob);
-    tab.insert(tab.end(), b->init_state.begin(), b->init_state.end());
+    std::vector<uint32_t> tab;
+    tab.reserve((size_t)n_scn * b->p.table_stride);
+    for (int k = 0; k < n_scn; ++k) {  // per scenario: blob (zero-padded to the largest) then its initial per-env state
+      std::vector<uint32_t> init;
+      build_init_state(scns[k], L, init);
+      if (k == 0) b->init_state = init;
+      tab.insert(tab.end(), scns[k]->blob.begin(), scns[k]->blob.end());
+      tab.resize(tab.size() + (max_blob - scns[k]->blob.size()), 0u);
+      tab.insert(tab.end(), init.begin(), init.end());
+    }
     void* pt = nullptr;
     cudaError_t e = dalloc(&pt, tab.size() * 4);
     if (e != cudaSuccess) { int rc2 = fail(CBX_ERR_CUDA, "cudaMalloc(tables): %s", cudaGetErrorString(e)); cbx_batch_destroy(b); return rc2; }
@@ -438,6 +494,18 @@ int cbx_batch_create(const cbx_scenario* s, int64_t n_envs, const cbx_config* cf
     e = cudaMemcpy(pt, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { int rc2 = fail(CBX_ERR_CUDA, "upload tables: %s", cudaGetErrorString(e)); cbx_batch_destroy(b); return rc2; }
     b->p.tables = b->d_tables;
+    if (n_scn > 1) {
+      std::vector<int32_t> ts((size_t)b->p.n_tiles);
+      int64_t tile = 0;
+      for (int k = 0; k < n_scn; ++k)
+        for (int64_t q = 0; q < (counts[k] + CBX_TILE - 1) / CBX_TILE; ++q) ts[(size_t)tile++] = k;
+      void* pts = nullptr;
+      e = dalloc(&pts, ts.size() * 4);
+      if (e == cudaSuccess) e = cudaMemcpy(pts, ts.data(), ts.size() * 4, cudaMemcpyHostToDevice);
+      if (e != cudaSuccess) { int rc2 = fail(CBX_ERR_CUDA, "upload tile scenarios: %s", cudaGetErrorString(e)); cbx_batch_destroy(b); return rc2; }
+      b->d_tile_scn = (int32_t*)pts;
+      b->p.tile_scn = b->d_tile_scn;
+    }
   }
   cbx_views& v = b->p.v;
   v.n_envs = n_envs; v.N = L.N; v.L = L.L; v.R = L.R; v.P = L.P; v.C = L.C; v.LEAK = L.LEAK; v.n_props = L.nprops;
@@ -659,6 +727,8 @@ int64_t cbx_export_words(const cbx_scenario* s, const cbx_config* cfg) {
   if (!s || !cfg) return -1;
   return CBX_X_HEADER_WORDS + 10 * (int64_t)s->n + cfg->maximum_total_credentials + (s->nsecrets + 31) / 32;
 }
+
+int64_t cbx_batch_export_words(const cbx_batch* b) { return b ? cbx_export_words(b->scn, &b->p.cfg) : -1; }
 
 int cbx_batch_export_state(cbx_batch* b, int64_t begin, int64_t end, int32_t* out, void* cuda_stream) {
   if (!b || !out || begin < 0 || end > b->p.n_envs || begin >= end) return fail(CBX_ERR_INVALID, "bad export range");

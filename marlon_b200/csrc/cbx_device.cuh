@@ -98,6 +98,10 @@ struct Ctx {
   __device__ __forceinline__ void setf32(int off, float v) const { w(off) = __float_as_uint(v); }
 
   // ---- scenario tables --------------------------------------------------------------------------------
+  // Real dimensions of THIS env's scenario (the staged tables).  The layout (L->n, L->nsecrets, ...) is the maximum over the
+  // scenarios of a multi-scenario batch (cbx_batch_create_multi); the game's arithmetic uses the scenario's own counts.
+  __device__ __forceinline__ int n_nodes() const { return (int)tb[CBX_H_N_NODES]; }
+  __device__ __forceinline__ int n_secrets() const { return (int)tb[CBX_H_N_SECRETS]; }
   __device__ __forceinline__ const uint32_t* node_rec(int node) const { return tb + tb[CBX_H_OFF_NODE] + node * CBX_NODE_WORDS; }
   __device__ __forceinline__ const uint32_t* vuln_rec(int node, int v) const {
     return tb + tb[CBX_H_OFF_VULN] + (node * (L->L + L->R) + v) * CBX_VULN_WORDS;
@@ -243,7 +247,7 @@ struct Ctx {
     if (!((rt[CBX_N_FW_IN] >> port) & 1u)) { r.reward = -10.0; return r; }
     if (!((rt[CBX_N_LISTEN] >> port) & 1u)) { r.reward = -10.0; return r; }
     if (bit(L->o_notrunning, tgt)) { r.reward = 0.0; return r; }
-    const int Ws = (L->nsecrets + 31) >> 5;
+    const int Ws = (n_secrets() + 31) >> 5;
     const uint32_t* auth = tb + tb[CBX_H_OFF_AUTH] + (tgt * L->P + port) * Ws;
     if (!((auth[secret >> 5] >> (secret & 31)) & 1u)) { r.reward = -10.0; return r; }
     bool ever;
@@ -283,7 +287,7 @@ struct Ctx {
     }
     return down;
   }
-  __device__ double availability(int down) const { return (double)(L->n - down) / (double)L->n; }
+  __device__ double availability(int down) const { const int n = n_nodes(); return (double)(n - down) / (double)n; }
 
   __device__ void scan_and_reimage(int stepcount, const double* scan_u, const double* detect_u) const {  // DEF:42-55
     if (stepcount % cfg->scan_frequency != 0) return;
@@ -301,7 +305,7 @@ struct Ctx {
         us = u53(o[0], o[1]);
         ud = u53(o[2], o[3]);
       }
-      int node = (int)floor(us * (double)L->n);
+      int node = (int)floor(us * (double)n_nodes());
       if (!bit(L->o_notrunning, node) && bit(L->o_installed, node)) {
         bool detected = ud <= cfg->scan_probability;
         if (detected && (node_rec(node)[CBX_N_FLAGS] & 1u)) reimage_live(node);
@@ -325,7 +329,7 @@ struct Ctx {
     if ((double)f32(L->o_ep_sum) < cfg->goal_reward) return false;
     int oc = owned_count();
     if (oc < cfg->goal_own_atleast) return false;
-    if ((double)oc / (double)L->n < cfg->goal_own_atleast_percent) return false;
+    if ((double)oc / (double)n_nodes() < cfg->goal_own_atleast_percent) return false;
     if (cfg->builtin_defender != CBX_BUILTIN_NONE && live_availability() >= cfg->goal_low_availability) return false;
     return true;
   }
@@ -357,6 +361,10 @@ struct Ctx {
   // ENV:707-751 + 584-601; returns true on OutOfBoundIndexError
   __device__ bool execute_action(int kind, const int32_t* a, Result* out) const {
     const int ndisc = nd();
+    // coordinates outside the action space (vulnerability / port index beyond the Identifiers) cannot come out of the gym
+    // spaces; the reference would raise IndexError.  Here they take the OutOfBoundIndexError path instead of indexing tables.
+    if (kind == CBX_KIND_LOCAL ? (a[1] < 0 || a[1] >= L->L) : kind == CBX_KIND_REMOTE ? (a[2] < 0 || a[2] >= L->R) : (a[2] < 0 || a[2] >= L->P))
+      return true;
     if (kind == CBX_KIND_LOCAL) {
       if (a[0] < 0 || a[0] >= ndisc) return true;
       *out = exploit_local((int)byte(L->o_disc_order, a[0]), a[1]);
@@ -442,12 +450,13 @@ struct Ctx {
     setf32(L->o_def_return, 0.f);
   }
   __device__ bool defender_action_valid(const int32_t* a) const {  // DWR:329-412, on the LIVE env
+    const int n = n_nodes();  // node coordinates beyond the scenario's own nodes (padded action space) are invalid
     switch (a[0]) {
-      case 0: return !bit(L->o_notrunning, a[1]) && (node_rec(a[1])[CBX_N_FLAGS] & 1u);
-      case 1: return !bit(L->o_notrunning, a[2]) && ((node_rec(a[2])[CBX_N_DEFOBS] >> ((a[4] ? 0 : 8) + a[3])) & 1u);
-      case 2: return !bit(L->o_notrunning, a[5]);
-      case 3: return !bit(L->o_notrunning, a[8]) && a[9] < (int)((node_rec(a[8])[CBX_N_FLAGS] >> 8) & 0xFFu);
-      case 4: return !bit(L->o_notrunning, a[10]) && a[11] < (int)((node_rec(a[10])[CBX_N_FLAGS] >> 8) & 0xFFu);
+      case 0: return a[1] < n && !bit(L->o_notrunning, a[1]) && (node_rec(a[1])[CBX_N_FLAGS] & 1u);
+      case 1: return a[2] < n && !bit(L->o_notrunning, a[2]) && ((node_rec(a[2])[CBX_N_DEFOBS] >> ((a[4] ? 0 : 8) + a[3])) & 1u);
+      case 2: return a[5] < n && !bit(L->o_notrunning, a[5]);
+      case 3: return a[8] < n && !bit(L->o_notrunning, a[8]) && a[9] < (int)((node_rec(a[8])[CBX_N_FLAGS] >> 8) & 0xFFu);
+      case 4: return a[10] < n && !bit(L->o_notrunning, a[10]) && a[11] < (int)((node_rec(a[10])[CBX_N_FLAGS] >> 8) & 0xFFu);
       default: return false;
     }
   }

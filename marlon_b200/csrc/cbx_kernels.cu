@@ -536,6 +536,8 @@ __device__ __forceinline__ void encode_defender_by_warp(const Tile& t, const Tar
   const cbx_layout* L = t.L;
   const int lane = threadIdx.x & 31;
   const int n = CBX_DIM(D, NN, L->n), nsvc = CBX_DIM(D, NSVC, L->nservices);
+  // the scenario's own node / service counts (smaller than the layout's in a padded multi-scenario batch: zero fill)
+  const int n_own = D::kStatic ? n : (int)t.tb[CBX_H_N_NODES], nsvc_own = D::kStatic ? nsvc : (int)t.tb[CBX_H_N_SERVICES];
   const int OW = D::kStatic ? (D::N + 31) / 32 : L->OW;
   for (int e = wid; e < n_valid; e += nw) {
     if (!enc_mask.test((int)e)) continue;
@@ -547,12 +549,12 @@ __device__ __forceinline__ void encode_defender_by_warp(const Tile& t, const Tar
 #pragma unroll
     for (int i = lane; i < 6 * n; i += 32) {
       const int node = i / 6, r = i - node * 6;
-      const uint32_t dob = t.tb[t.tb[CBX_H_OFF_NODE] + node * CBX_NODE_WORDS + CBX_N_DEFOBS];
+      const uint32_t dob = node < n_own ? t.tb[t.tb[CBX_H_OFF_NODE] + node * CBX_NODE_WORDS + CBX_N_DEFOBS] : 0u;
       o.fw_in[(size_t)e * 6 * n + i] = (int8_t)((dob >> r) & 1u);
       o.fw_out[(size_t)e * 6 * n + i] = (int8_t)((dob >> (8 + r)) & 1u);
     }
 #pragma unroll
-    for (int i = lane; i < nsvc; i += 32) o.services[(size_t)e * nsvc + i] = 1;
+    for (int i = lane; i < nsvc; i += 32) o.services[(size_t)e * nsvc + i] = (int8_t)(i < nsvc_own);
   }
 }
 
@@ -608,15 +610,16 @@ __device__ __forceinline__ void encode_defender(const Tile& t, const Target& o, 
   write_i8(o.infected, L->n, K.d_n, n_valid, enc_mask,
            [&](int e, int i) -> uint32_t { return (t.d(e, D_OWNED + L->OW + (i >> 5)) >> (i & 31)) & 1u; });
   if (!static_too) return;
+  const int n_own = (int)t.tb[CBX_H_N_NODES], nsvc_own = (int)t.tb[CBX_H_N_SERVICES];
   write_i8(o.fw_in, 6 * L->n, K.d_6n, n_valid, enc_mask, [&](int, int i) -> uint32_t {
     int node = i / 6, r = i - node * 6;
-    return (t.tb[t.tb[CBX_H_OFF_NODE] + node * CBX_NODE_WORDS + CBX_N_DEFOBS] >> r) & 1u;
+    return node < n_own ? (t.tb[t.tb[CBX_H_OFF_NODE] + node * CBX_NODE_WORDS + CBX_N_DEFOBS] >> r) & 1u : 0u;
   });
   write_i8(o.fw_out, 6 * L->n, K.d_6n, n_valid, enc_mask, [&](int, int i) -> uint32_t {
     int node = i / 6, r = i - node * 6;
-    return (t.tb[t.tb[CBX_H_OFF_NODE] + node * CBX_NODE_WORDS + CBX_N_DEFOBS] >> (8 + r)) & 1u;
+    return node < n_own ? (t.tb[t.tb[CBX_H_OFF_NODE] + node * CBX_NODE_WORDS + CBX_N_DEFOBS] >> (8 + r)) & 1u : 0u;
   });
-  write_i8(o.services, L->nservices, K.d_svc, n_valid, enc_mask, [&](int, int) -> uint32_t { return 1u; });
+  write_i8(o.services, L->nservices, K.d_svc, n_valid, enc_mask, [&](int, int i) -> uint32_t { return i < nsvc_own ? 1u : 0u; });
 }
 
 // copy env rows main -> terminal buffers (terminal observation of an intercepted-and-truncated step is the previous one)
@@ -929,6 +932,28 @@ __global__ void __launch_bounds__(CBX_THREADS, CBX_MIN_CTAS) cbx_step_kernel(con
     uint32_t lo = ((k & 0xF) * 0x00204081u) & 0x01010101u, hi = (((k >> 4) & 0xF) * 0x00204081u) & 0x01010101u;
     s_lut[k] = make_uint2(lo, hi);
   }
+  // tiles of this CTA: strided for a single scenario (balance); one contiguous range for a multi-scenario batch, so that the
+  // staged scenario tables change rarely (envs are grouped by scenario, cbx_batch_create_multi)
+  const bool multi = p.n_scenarios > 1;
+  const int tile_begin = multi ? (int)((int64_t)blockIdx.x * p.n_tiles / gridDim.x) : (int)blockIdx.x;
+  const int tile_end = multi ? (int)((int64_t)(blockIdx.x + 1) * p.n_tiles / gridDim.x) : p.n_tiles;
+  const int tile_step = multi ? 1 : (int)gridDim.x;
+  int cur_scn = (multi && tile_begin < tile_end) ? p.tile_scn[tile_begin] : 0;
+  uint32_t tb_phase = 0;
+  auto stage_tables = [&](int scn) {  // all threads
+    const uint32_t* src = p.tables + (size_t)scn * p.table_stride;
+    if (USE_TMA) {
+      if (tid == 0) {
+        mbar_expect_tx(&bars[0], table_bytes);
+        tma_load_1d(s_tb, src, table_bytes, &bars[0]);
+      }
+      mbar_wait(&bars[0], tb_phase);
+      tb_phase ^= 1;
+    } else {
+      for (uint32_t k = tid; k < table_bytes / 4; k += CBX_THREADS) s_tb[k] = src[k];
+      __syncthreads();
+    }
+  };
   if (USE_TMA) {
     if (tid == 0) {
       mbar_init(&bars[0], 1);
@@ -936,15 +961,8 @@ __global__ void __launch_bounds__(CBX_THREADS, CBX_MIN_CTAS) cbx_step_kernel(con
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (tid == 0) {
-      mbar_expect_tx(&bars[0], table_bytes);
-      tma_load_1d(s_tb, p.tables, table_bytes, &bars[0]);
-    }
-    mbar_wait(&bars[0], 0);
-  } else {
-    for (uint32_t k = tid; k < table_bytes / 4; k += CBX_THREADS) s_tb[k] = p.tables[k];
-    __syncthreads();
   }
+  stage_tables(cur_scn);
 
   Acc acc;
 #pragma unroll
@@ -961,9 +979,14 @@ __global__ void __launch_bounds__(CBX_THREADS, CBX_MIN_CTAS) cbx_step_kernel(con
   int slice_of_kind[3] = {p.slice_of_kind[0], p.slice_of_kind[1], p.slice_of_kind[2]};
   constexpr uint32_t kRowBytes = CBX_TILE * 4u;
 
-  for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+  for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
     const int64_t e0 = (int64_t)tile * CBX_TILE;
     const int n_valid = (int)min((int64_t)CBX_TILE, p.n_envs - e0);
+    if (multi && p.tile_scn[tile] != cur_scn) {  // next scenario: restage its tables (every thread is past the last tile)
+      cur_scn = p.tile_scn[tile];
+      __syncthreads();
+      stage_tables(cur_scn);
+    }
     // ---- (0) stage the state tile (S rows of CBX_TILE words) and the tile's actions ----
     if (USE_TMA) {
       if (tid < 32) {
@@ -1118,6 +1141,7 @@ __global__ void cbx_sample_kernel(const __grid_constant__ cbx_params p, int32_t*
   const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= p.n_envs) return;
   const cbx_layout& L = p.lay;
+  const uint32_t* tables = p.tables + (size_t)(p.tile_scn ? p.tile_scn[env / CBX_TILE] : 0) * p.table_stride;
   auto W = [&](int off) { return p.state[((env / CBX_TILE) * L.S + off) * CBX_TILE + (env % CBX_TILE)]; };
   uint32_t r[4];
   philox4x32_10((uint32_t)env, (uint32_t)(env >> 32), step, 0x5A17u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
@@ -1141,7 +1165,7 @@ __global__ void cbx_sample_kernel(const __grid_constant__ cbx_params p, int32_t*
     int present[64];
     int np = 0;
     for (int v = 0; v < L.L && v < 64; ++v)
-      if (p.tables[p.tables[CBX_H_OFF_VULN] + (node * (L.L + L.R) + v) * CBX_VULN_WORDS] & 1u) present[np++] = v;
+      if (tables[tables[CBX_H_OFF_VULN] + (node * (L.L + L.R) + v) * CBX_VULN_WORDS] & 1u) present[np++] = v;
     if (np) a[1] = present[__umulhi(r[2], (uint32_t)np)];
     else { kind = CBX_KIND_REMOTE; }
   }
@@ -1164,7 +1188,7 @@ __global__ void cbx_sample_kernel(const __grid_constant__ cbx_params p, int32_t*
     for (int k = 0; k < width; ++k) o[p.slice_of_kind[kind] + k] = a[k];
     if (def) {
       int32_t* d = def + env * 12;
-      const uint32_t n = (uint32_t)L.n;
+      const uint32_t n = tables[CBX_H_N_NODES];  // the scenario's own node count
       d[0] = (int)__umulhi(r2[1], 5u);
       uint32_t x = r2[2], y = r2[3];
       d[1] = (int)__umulhi(x, n); x = x * 1664525u + 1013904223u;

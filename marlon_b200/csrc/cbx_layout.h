@@ -127,9 +127,12 @@ struct cbx_params {
   int64_t n_envs;
   int64_t n_pad;          // n_envs rounded up to CBX_TILE
   int n_tiles;
-  int table_words;        // scenario blob words (multiple of 4)
+  int table_words;        // scenario blob words (multiple of 4; the largest blob of a multi-scenario batch, others are padded)
   int slice_of_kind[3];
-  const uint32_t* tables; // scenario blob followed by the S-word initial state
+  int n_scenarios;        // > 1: cbx_batch_create_multi -- envs grouped by scenario in whole tiles
+  int table_stride;       // words between the tables of consecutive scenarios (table_words + padded S)
+  const int32_t* tile_scn;  // [n_tiles] scenario of each tile (NULL for a single scenario)
+  const uint32_t* tables; // per scenario: blob followed by the S-word initial state
   uint32_t* state;
   const int32_t* att_actions;
   const int32_t* def_actions;

@@ -173,3 +173,94 @@ def test_step_host_roundtrip():
         for k in ("att_reward", "def_reward", "att_terminated", "att_truncated", "def_terminated", "def_truncated"):
             assert np.array_equal(out[k], b.numpy(k)), k
     b.close()
+
+
+# ---- configs[4]: several generated CyberBattleRandom networks in ONE batch (padded layout, scenario per env group) ----
+def _slice_export(x, n_max, n_k, C, nsec_k):
+    """multi-scenario export (sections sized for the largest scenario) -> the layout a single-scenario export of n_k nodes has"""
+    H = _abi.X_HEADER_WORDS
+    parts = [x[:, :H]] + [x[:, H + sec * n_max: H + sec * n_max + n_k] for sec in range(10)]
+    base = H + 10 * n_max
+    parts += [x[:, base: base + C], x[:, base + C: base + C + (nsec_k + 31) // 32]]
+    return np.concatenate(parts, axis=1)
+
+
+@pytest.mark.parametrize("mask_mode", [_abi.MASK_FACTORED, _abi.MASK_DENSE])
+def test_random_networks_multi_scenario_batch_vs_oracle(mask_mode):
+    """Three generated networks (different node / credential / service counts) side by side in one batch: every group of envs
+    must behave exactly like a single-scenario oracle batch of its own network."""
+    from marlon_b200 import random_network
+    from marlon_b200.batch import Batch
+    from oracle import OracleBatch
+
+    seeds = [0, 3, 7]
+    counts = [64, 96, 45] if mask_mode == _abi.MASK_FACTORED else [32, 32, 13]
+    comps = [scenario.compile_scenario(random_network.random_environment(s)) for s in seeds]
+    assert len({c.n_services for c in comps}) > 1 and len({len(c.triples) for c in comps}) > 1
+    cfg = config.make_config(_abi.MODE_MARLON, maximum_node_count=72, maximum_total_credentials=136,
+                             maximum_discoverable_credentials_per_action=32, throws_on_invalid_actions=False,
+                             defender_constraint=config.DefenderConstraint(0.60), losing_reward=-5000.0, defender_enabled=True,
+                             defender_max_timesteps=200, attacker_max_timesteps=200, mask_mode=mask_mode, emit_terminal_obs=True)
+    b = Batch(comps, cfg, counts)
+    n_max, nsvc_max = b.views.n_nodes, b.views.n_services
+    assert n_max == max(c.n_nodes for c in comps) and nsvc_max == max(c.n_services for c in comps)
+    offs = np.concatenate([[0], np.cumsum(counts)])
+    oracles = []
+    for k, comp in enumerate(comps):
+        ck = _abi.Config.from_buffer_copy(bytes(cfg))
+        ck.env_index_base = int(offs[k])
+        oracles.append(OracleBatch(comp, ck, counts[k]))
+    b.reset()
+    for o in oracles:
+        o.reset()
+    rng = np.random.default_rng(5)
+
+    def compare(step):
+        x = b.export_state()
+        for k, (comp, o) in enumerate(zip(comps, oracles)):
+            sl = slice(int(offs[k]), int(offs[k + 1]))
+            n_k, nsvc_k = comp.n_nodes, comp.n_services
+            for name, t in b.tensors.items():
+                if name.startswith("term_"):
+                    continue
+                got, want = t[sl].cpu().numpy(), o.arrays[name]
+                if name == "def_infected_nodes":
+                    assert not got[:, n_k:].any(); got = got[:, :n_k]
+                elif name in ("def_incoming_firewall", "def_outgoing_firewall"):
+                    assert not got[:, 6 * n_k:].any(); got = got[:, :6 * n_k]
+                elif name == "def_services_status":
+                    assert not got[:, nsvc_k:].any(); got = got[:, :nsvc_k]
+                assert got.shape == want.shape, (name, got.shape, want.shape)
+                if got.dtype.kind == "f":
+                    assert np.allclose(got, want, rtol=helpers.REWARD_RTOL, atol=helpers.REWARD_RTOL), (step, k, name)
+                else:
+                    assert np.array_equal(got, want), (step, k, name, np.argwhere(got != want)[:4])
+            want_x = o.export_state()
+            got_x = _slice_export(x[sl], n_max, n_k, cfg.maximum_total_credentials, len(comp.secrets))
+            assert np.array_equal(got_x, want_x), (step, k, "state", np.argwhere(got_x != want_x)[:4])
+
+    compare(-1)
+    n = sum(counts)
+    for s in range(120):
+        att, dfn = b.sample_actions(seed=11)
+        att, dfn = att.cpu().numpy(), dfn.cpu().numpy()
+        if s % 3 == 0:  # uniform actions over the padded spaces: out-of-range nodes, invalid defender targets
+            pick = rng.random(n) < 0.5
+            nvec = np.array([3] + [cfg.maximum_node_count] * 9)
+            for kind, (a0, a1) in config.attacker_action_layout(cfg).items():
+                nvec[a0:a1] = {0: [b.views.N, b.views.L], 1: [b.views.N, b.views.N, b.views.R],
+                               2: [b.views.N, b.views.N, b.views.P, b.views.C]}[kind]
+            uni = (rng.random((n, 10)) * nvec).astype(np.int32)
+            att = np.where(pick[:, None], uni, att)
+            dfn[rng.random(n) < 0.3, 0] = -1
+        for k, o in enumerate(oracles):
+            sl = slice(int(offs[k]), int(offs[k + 1]))
+            dk = dfn[sl].copy()
+            # the sampler draws defender node coordinates below the scenario's own node count, so they are valid oracle inputs
+            o.step(att[sl], dk, None, None)
+        b.step(att, dfn, None, None)
+        if s % 6 == 0 or s == 119:
+            compare(s)
+    want_stats = sum(o.stats for o in oracles)
+    assert np.allclose(b.stats(), want_stats, rtol=1e-9, atol=1e-6)
+    b.close()
