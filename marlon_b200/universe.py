@@ -52,11 +52,13 @@ def attacker_spaces(cfg: _abi.Config, comp) -> Tuple[spaces.Dict, spaces.MultiDi
     return obs, spaces.MultiDiscrete(nvec)
 
 
-def defender_spaces(comp) -> Tuple[spaces.Dict, spaces.MultiDiscrete]:
-    """DefenderEnvWrapper observation / action spaces (defend_wrapper.py:162-195)."""
-    n = comp.n_nodes
+def defender_spaces(comp, n: Optional[int] = None, n_services: Optional[int] = None) -> Tuple[spaces.Dict, spaces.MultiDiscrete]:
+    """DefenderEnvWrapper observation / action spaces (defend_wrapper.py:162-195); `n` / `n_services` override the scenario's
+    own counts with the padded ones of a multi-scenario batch."""
+    n = comp.n_nodes if n is None else int(n)
+    n_services = comp.n_services if n_services is None else int(n_services)
     obs = spaces.Dict({"infected_nodes": spaces.MultiBinary(n), "incoming_firewall_status": spaces.MultiBinary(6 * n),
-                       "outgoing_firewall_status": spaces.MultiBinary(6 * n), "services_status": spaces.MultiBinary(comp.n_services)})
+                       "outgoing_firewall_status": spaces.MultiBinary(6 * n), "services_status": spaces.MultiBinary(n_services)})
     return obs, spaces.MultiDiscrete([5, n, n, 6, 2, n, 6, 2, n, 3, n, 3])
 
 
@@ -71,7 +73,11 @@ class MultiAgentUniversalEnv:
                  attacker_loss_reward: float = -5000.0, defender_loss_reward: float = -5000.0, defender_maintain_sla: float = 0.60,
                  defender_reset_on_constraint_broken: bool = True, defender_binding: str = "reference_stale",
                  action_kind_order="gymnasium029", mask_mode: str = "dense", emit_terminal_obs: bool = False, seed: int = 0,
-                 env_index_base: int = 0, **env_kwargs):
+                 env_index_base: int = 0, scenario_seeds=None, **env_kwargs):
+        """`scenario_seeds` (with ``env_id="CyberBattleRandom-v0"``): one generated network per seed, all in one batch
+        (configs[4]); `n_envs` is then the env count per network (an int, or one count per seed; every count but the last a
+        multiple of 32).  Node / credential / service counts differ between networks: the observation spaces are those of the
+        bounds and of the largest network, smaller ones are zero-padded."""
         if defender_binding != "reference_stale":
             raise NotImplementedError("only the reference's stale defender binding is on the batched path (SURVEY.md B.1); "
                                       "the 'live' semantics are a later row of the scope table (8f.4)")
@@ -85,10 +91,20 @@ class MultiAgentUniversalEnv:
         if defender:  # multiagent_universe.py:158-165
             kw.setdefault("defender_constraint", DefenderConstraint(maintain_sla=defender_maintain_sla))
             kw.setdefault("losing_reward", defender_loss_reward)
-        env, merged = registry.resolve(env_id, **kw)
+        if scenario_seeds is not None:
+            seeds = [int(x) for x in scenario_seeds]
+            resolved = [registry.resolve(env_id, seed=sd, **kw) for sd in seeds]
+            envs, merged = [r[0] for r in resolved], resolved[0][1]
+            comps = [scenario.compile_scenario(e) for e in envs]
+            counts = [int(n_envs)] * len(seeds) if np.isscalar(n_envs) else [int(x) for x in n_envs]
+            n_envs = sum(counts)
+            env = envs[0]
+        else:
+            env, merged = registry.resolve(env_id, **kw)
+            comps, counts = None, None
         merged.pop("observation_padding", None)
         self.env_id, self.environment = env_id, env
-        self.compiled = scenario.compile_scenario(env)
+        self.compiled = comps[0] if comps else scenario.compile_scenario(env)
         self.cfg = config.make_config(
             _abi.MODE_MARLON, attacker_max_timesteps=max_timesteps,
             attacker_invalid_action_reward_modifier=attacker_invalid_action_reward_modifier,
@@ -100,9 +116,10 @@ class MultiAgentUniversalEnv:
         from .batch import Batch
 
         self.n_envs, self.device, self.has_defender = int(n_envs), device, bool(defender)
-        self.batch = Batch(self.compiled, self.cfg, self.n_envs, device=device)
+        self.batch = Batch(comps, self.cfg, counts, device=device) if comps else Batch(self.compiled, self.cfg, self.n_envs, device=device)
         self.attacker_observation_space, self.attacker_action_space = attacker_spaces(self.cfg, self.compiled)
-        self.defender_observation_space, self.defender_action_space = defender_spaces(self.compiled)
+        self.defender_observation_space, self.defender_action_space = defender_spaces(
+            self.compiled, n=self.batch.views.n_nodes, n_services=self.batch.views.n_services)
         self.identifiers = env.identifiers
         self.logger = logging.getLogger("marlon")
 

@@ -205,3 +205,26 @@ def test_sharding_does_not_change_the_random_draws():
     assert np.array_equal(whole.numpy("connect")[128:], part.numpy("connect"))
     assert whole.export_state()[:, 13].sum() > 0  # some nodes are being re-imaged: the defender did act
     whole.close(); part.close()
+
+
+def test_universe_over_generated_random_networks():
+    """configs[4] through the Python face: one batch over several generated CyberBattleRandom networks (factored masks)."""
+    from marlon_b200.universe import MultiAgentUniversalEnv
+
+    u = MultiAgentUniversalEnv("CyberBattleRandom-v0", 64, scenario_seeds=[1, 2, 3], maximum_node_count=72, maximum_total_credentials=104,
+                               max_timesteps=50, mask_mode="factored")
+    assert u.n_envs == 192 and len(u.batch.scenarios) == 3
+    n_max = max(c.n_nodes for c in u.batch.scenarios)
+    assert u.defender_action_space.nvec.tolist() == [5, n_max, n_max, 6, 2, n_max, 6, 2, n_max, 3, n_max, 3]
+    assert u.attacker_action_space.nvec.tolist()[0] == 3
+    aobs, dobs = u.reset()
+    assert aobs["discovered_nodes_properties"].shape == (192, 72) and dobs["infected_nodes"].shape == (192, n_max)
+    assert "owned_bits" in aobs and "connect" not in aobs
+    assert (aobs["discovered_node_count"] == 1).all()  # one breach node per generated network (generate_network.py:205-219)
+    for s in range(80):
+        att, dfn = u.sample_actions(seed=9)
+        r = u.step(att, dfn)
+    st = u.episode_statistics(reduce=False)
+    assert st["env_steps"] == 192 * 80 and st["episodes"] >= 192 and st["att_invalid"] == 0
+    assert float(r["attacker_reward"].abs().sum()) >= 0
+    u.close()
