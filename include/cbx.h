@@ -375,7 +375,8 @@ int cbx_batch_enable_timing(cbx_batch* b, int enabled);
 int cbx_batch_step_kernel_ms(cbx_batch* b, double* mean_ms, int64_t* launches);
 
 /* Which kernel one step launches (reported by bench.py next to the roofline): out8[0] = 1 pipelined kernel (cbx_pipe_kernel:
- * logic warps ahead of TMA-storing encoder warps) / 0 fused kernel (cbx_step_kernel); [1] CTAs; [2] threads per CTA;
+ * logic warps ahead of TMA-storing encoder warps) / 2 warp-per-tile kernel for large state (cbx_wide_kernel) / 0 fused kernel
+ * (cbx_step_kernel); [1] CTAs; [2] threads per CTA;
  * [3] dynamic shared memory bytes per CTA; [4] logic warps; [5] encoder warps; [6] encoder variant (0 generic, 1 warp per
  * env, 2 ToyCtf(12,10) static, 3 Chain-10(12,12) static); [7] TMA staging enabled. */
 int cbx_batch_kernel_info(const cbx_batch* b, int32_t* out8);

@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libcbx.so")
 SOURCES = ["cbx_kernels.cu", "cbx_api.cu"]
-HEADERS = ["cbx_layout.h", "cbx_device.cuh", "cbx_pipe.cuh", os.path.join("..", "..", "include", "cbx.h")]
+HEADERS = ["cbx_layout.h", "cbx_device.cuh", "cbx_pipe.cuh", "cbx_wide.cuh", os.path.join("..", "..", "include", "cbx.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--extended-lambda",
               "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177"]
 

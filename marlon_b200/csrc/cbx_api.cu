@@ -19,6 +19,8 @@ cudaError_t cbx_launch_sample(const cbx_params* p, int32_t* att, int32_t* def, u
 cudaError_t cbx_kernel_attrs(int smem_bytes, int use_tma, int fast, int* blocks_per_sm);
 cudaError_t cbx_pipe_attrs(int enc, int smem_bytes);
 cudaError_t cbx_launch_pipe(const cbx_params* p, int op, int grid, cudaStream_t stream);
+cudaError_t cbx_wide_attrs(int smem_bytes);
+cudaError_t cbx_launch_wide(const cbx_params* p, int op, int grid, cudaStream_t stream);
 }
 
 namespace {
@@ -119,6 +121,32 @@ bool plan_pipe(const cbx_params& p, int wl, int we, cbx_pipe_plan* Q) {
   return true;
 }
 
+// Shared-memory plan of the warp-per-tile kernel (cbx_wide.cuh): factored masks, warp-per-env encoder available.
+bool plan_wide(const cbx_params& p, cbx_wide_plan* Q) {
+  const cbx_layout& L = p.lay;
+  memset(Q, 0, sizeof(*Q));
+  if (p.enc.warp_env < 1 || CBX_TILE != 32 || L.sz_connect > 0) return false;
+  int64_t o = 0;
+  Q->lut = (int)o; o += 512;
+  Q->warps = (int)o;
+  int64_t q = 0;
+  Q->w_stage = (int)q; q += (int64_t)L.G * CBX_TILE;
+  Q->w_desc = (int)q; q += (int64_t)p.enc.desc_words * CBX_TILE;
+  Q->w_acts = (int)q; q += 22 * CBX_TILE;
+  Q->w_img = (int)q; q += 33 * CBX_TILE;
+  Q->w_drows = (int)q; q += (2 * (6 * L.n + 4) + L.nservices + 4 + 3) / 4;
+  q = (q + 31) / 32 * 32;
+  Q->warp_words = (int)q;
+  // as many warps as fit while leaving L1 room for the scenario tables and the hot state lines
+  int nw = (int)((192 * 1024 / 4 - o) / q);
+  if (nw > CBX_WIDE_WARPS) nw = CBX_WIDE_WARPS;
+  if (nw < 4) return false;
+  Q->nwarps = nw;
+  o += nw * q;
+  Q->total_bytes = (int)(o * 4);
+  return true;
+}
+
 }  // namespace
 
 struct cbx_scenario {
@@ -130,6 +158,7 @@ struct cbx_batch {
   cbx_params p;
   int device, grid, smem_bytes, use_tma;
   int pipe_grid;  // pipelined kernel: CTAs (one per SM); the kernel is used when p.pipe.enabled
+  int wide_grid;  // warp-per-tile kernel (large state, factored masks); used when p.wide.enabled
   std::vector<void*> allocs;
   uint32_t* d_tables;
   int64_t launches;
@@ -462,6 +491,22 @@ static int create_impl(const cbx_scenario* const* scns, int n_scn, const int64_t
     }
   }
 
+  // warp-per-tile kernel: large per-env state (or several scenarios) with factored masks; CBX_WIDE=0/1 overrides the choice
+  b->p.wide.enabled = 0; b->wide_grid = 0;
+  if (!b->p.pipe.enabled && b->use_tma) {
+    const char* we = getenv("CBX_WIDE");
+    const bool want = we ? we[0] == '1' : (b->p.lay.S >= 128 || n_scn > 1);
+    cbx_wide_plan Q;
+    if (want && plan_wide(b->p, &Q) && cbx_wide_attrs(Q.total_bytes) == cudaSuccess) {
+      Q.enabled = 1;
+      b->p.wide = Q;
+      const int need = (b->p.n_tiles + Q.nwarps - 1) / Q.nwarps;
+      b->wide_grid = sms < need ? sms : need;
+    } else {
+      cudaGetLastError();
+    }
+  }
+
   auto dalloc = [&](void** ptr, size_t bytes) -> cudaError_t {
     if (bytes == 0) bytes = 16;
     cudaError_t e = cudaMalloc(ptr, bytes);
@@ -562,7 +607,8 @@ static int create_impl(const cbx_scenario* const* scns, int n_scn, const int64_t
     b->p.reset_mask = nullptr;
     const int op0 = CBX_OP_RESET | CBX_OP_ATTACKER | CBX_OP_DEFENDER;
     cudaError_t e = b->p.pipe.enabled ? cbx_launch_pipe(&b->p, op0, b->pipe_grid, 0)
-                                      : cbx_launch_step(&b->p, op0, b->grid, b->smem_bytes, b->use_tma, 0);
+                    : b->p.wide.enabled ? cbx_launch_wide(&b->p, op0, b->wide_grid, 0)
+                                        : cbx_launch_step(&b->p, op0, b->grid, b->smem_bytes, b->use_tma, 0);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { int rc2 = fail(CBX_ERR_CUDA, "initial reset: %s", cudaGetErrorString(e)); cbx_batch_destroy(b); return rc2; }
     b->launches++;
@@ -597,6 +643,7 @@ static int timed_launch(cbx_batch* b, int op, cudaStream_t st) {
     CUDA_TRY(cudaEventRecord(e0, st));
   }
   if (b->p.pipe.enabled) CUDA_TRY(cbx_launch_pipe(&b->p, op, b->pipe_grid, st));
+  else if (b->p.wide.enabled) CUDA_TRY(cbx_launch_wide(&b->p, op, b->wide_grid, st));
   else CUDA_TRY(cbx_launch_step(&b->p, op, b->grid, b->smem_bytes, b->use_tma, st));
   if (t) CUDA_TRY(cudaEventRecord(e1, st));
   b->launches++;
@@ -821,10 +868,11 @@ int cbx_batch_phase_cycles(cbx_batch* b, int enable, uint64_t* out16) {
 int cbx_batch_kernel_info(const cbx_batch* b, int32_t* out8) {
   if (!b || !out8) return fail(CBX_ERR_INVALID, "null argument");
   const cbx_pipe_plan& Q = b->p.pipe;
-  out8[0] = Q.enabled;
-  out8[1] = Q.enabled ? b->pipe_grid : b->grid;
-  out8[2] = Q.enabled ? (Q.wl + Q.we) * 32 : CBX_THREADS;
-  out8[3] = Q.enabled ? Q.total_bytes : b->smem_bytes;
+  const bool wide = b->p.wide.enabled;
+  out8[0] = Q.enabled ? 1 : wide ? 2 : 0;
+  out8[1] = Q.enabled ? b->pipe_grid : wide ? b->wide_grid : b->grid;
+  out8[2] = Q.enabled ? (Q.wl + Q.we) * 32 : wide ? b->p.wide.nwarps * 32 : CBX_THREADS;
+  out8[3] = Q.enabled ? Q.total_bytes : wide ? b->p.wide.total_bytes : b->smem_bytes;
   out8[4] = Q.enabled ? Q.wl : 0;
   out8[5] = Q.enabled ? Q.we : 0;
   out8[6] = b->p.enc.warp_env;

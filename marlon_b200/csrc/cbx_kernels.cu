@@ -1132,6 +1132,7 @@ __global__ void __launch_bounds__(CBX_THREADS, CBX_MIN_CTAS) cbx_step_kernel(con
 }  // namespace cbx
 
 #include "cbx_pipe.cuh"
+#include "cbx_wide.cuh"
 
 namespace cbx {
 
@@ -1249,6 +1250,14 @@ cudaError_t cbx_launch_pipe(const cbx_params* p, int op, int grid, cudaStream_t 
     case 2: cbx::cbx_pipe_kernel<2><<<grid, threads, p->pipe.total_bytes, stream>>>(*p, op); break;
     default: cbx::cbx_pipe_kernel<1><<<grid, threads, p->pipe.total_bytes, stream>>>(*p, op); break;
   }
+  return cudaGetLastError();
+}
+// warp-per-tile kernel for large per-env state (factored masks)
+cudaError_t cbx_wide_attrs(int smem_bytes) {
+  return cudaFuncSetAttribute(cbx::cbx_wide_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+}
+cudaError_t cbx_launch_wide(const cbx_params* p, int op, int grid, cudaStream_t stream) {
+  cbx::cbx_wide_kernel<1><<<grid, p->wide.nwarps * 32, p->wide.total_bytes, stream>>>(*p, op);
   return cudaGetLastError();
 }
 cudaError_t cbx_launch_sample(const cbx_params* p, int32_t* att, int32_t* def, uint64_t seed, uint32_t step, cudaStream_t stream) {

@@ -118,11 +118,23 @@ struct cbx_pipe_plan {
 // slot header words
 enum { CBX_SH_ENC_MASK = 0, CBX_SH_TILE = 1 };
 
+// Warp-per-tile kernel for large per-env state (cbx_wide.cuh): nothing big is staged; per warp a private area holds the
+// staging words, the encoder descriptors, the tile's actions, the 32 x 33 transpose square and the defender's static rows.
+#define CBX_WIDE_WARPS 12  // most warps per CTA (the kernel is compiled for 384 threads, one CTA per SM)
+struct cbx_wide_plan {
+  int enabled;
+  int nwarps;                                      // warps per CTA: as many as fit (<= CBX_WIDE_WARPS)
+  int lut, warps, warp_words;                      // shared-memory carve-up in 32-bit words
+  int w_stage, w_desc, w_acts, w_img, w_drows;     // inside a warp's area
+  int total_bytes;
+};
+
 struct cbx_params {
   cbx_layout lay;
   cbx_enc_consts enc;
   cbx_smem_plan plan;
   cbx_pipe_plan pipe;
+  cbx_wide_plan wide;
   cbx_config cfg;
   int64_t n_envs;
   int64_t n_pad;          // n_envs rounded up to CBX_TILE
