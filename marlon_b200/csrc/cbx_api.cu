@@ -134,7 +134,7 @@ bool plan_wide(const cbx_params& p, cbx_wide_plan* Q) {
   Q->w_desc = (int)q; q += (int64_t)p.enc.desc_words * CBX_TILE;
   Q->w_acts = (int)q; q += 22 * CBX_TILE;
   Q->w_img = (int)q; q += 33 * CBX_TILE;
-  Q->w_drows = (int)q; q += (2 * (6 * L.n + 4) + L.nservices + 4 + 3) / 4;
+  Q->w_drows = (int)q; q += 2 * ((6 * L.n + 4 + 3) / 4) + (L.nservices + 4 + 3) / 4 + 1;
   q = (q + 31) / 32 * 32;
   Q->warp_words = (int)q;
   // as many warps as fit while leaving L1 room for the scenario tables and the hot state lines

@@ -18,81 +18,50 @@ namespace cbx {
 
 constexpr int kImgStride = 33;  // padded row of the transpose square: conflict-free both ways
 
-// ---- thread-per-env word generators (same values as encode_attacker / build_field_images) -------------------------------
-struct GenStaging {  // k-th staging word from `base`
-  const Ctx& c; int base;
-  __device__ __forceinline__ uint32_t operator()(int k) { return c.g(base + k); }
-};
-struct GenCache {  // credential_cache_matrix [C][2]: (target discovery index, port) of every cached credential (ENV:920-922)
-  const Ctx& c; int nc; bool blank; uint32_t a, b;
-  __device__ __forceinline__ uint32_t operator()(int k) {
-    if (!(k & 1)) {
-      a = b = 0;
-      const int i = k >> 1;
-      if (!blank && i < nc) {
-        const uint32_t* rec = c.triple((int)c.half(c.L->o_cache, i));
-        a = c.byte(c.L->o_disc_idx, (int)rec[0]);
-        b = rec[1];
-      }
-      return a;
-    }
-    return b;
-  }
-};
-struct GenProps {  // discovered_nodes_properties [N][props] (ENV:811-830; 2 = unknown only in blank observations, ENV:765)
-  const Ctx& c; int nd, nprops; bool blank; int kk, pi; uint32_t lo, hi;
-  __device__ __forceinline__ uint32_t operator()(int) {
-    if (pi == 0) {
-      lo = hi = 0;
-      if (!blank && kk < nd) {
-        const int node = (int)c.byte(c.L->o_disc_order, kk);
-        lo = c.w(c.L->o_props + node * c.L->PW);
-        if (c.L->PW > 1) hi = c.w(c.L->o_props + node * c.L->PW + 1);
-      }
-    }
-    const uint32_t v = blank ? 2u : (((pi < 32 ? lo : hi) >> (pi & 31)) & 1u);
-    if (++pi == nprops) { pi = 0; ++kk; }
-    return v;
-  }
-};
-struct GenPriv {  // nodes_privilegelevel [N] in discovery order (ENV:840-857), as the observation saw it (staging snapshot)
-  const Ctx& c; int nd; bool blank;
-  __device__ __forceinline__ uint32_t operator()(int k) {
-    if (blank || k >= nd) return 0u;
-    const uint32_t node = c.byte(c.L->o_disc_order, k);
-    return (c.g(c.L->g_priv + (node >> 4)) >> ((node & 15) * 2)) & 3u;
-  }
-};
-
-// One int32 field of a tile: every thread generates ITS env's words 32 at a time into the padded square, then the warp
-// stores the square transposed -- env e's 32 words are 128 contiguous bytes of dst.
-template <class Gen>
-__device__ __forceinline__ void emit_field_rows(int32_t* dst, const int wpe, const int n_valid, const uint32_t mask, uint32_t* img,
-                                                const int lane, const bool mine, Gen gen) {
-  if (!dst) return;
-  for (int k0 = 0; k0 < wpe; k0 += 32) {
-    const int m = min(32, wpe - k0);
-    if (mine)
-      for (int j = 0; j < m; ++j) img[lane * kImgStride + j] = gen(k0 + j);
+// Streaming writer of one int32 field of a tile: every thread `put`s ITS env's words in order; after every 32 words the warp
+// stores the padded square transposed -- env e's 32 words are 128 contiguous bytes of the output tensor.  All lanes call
+// put() the same number of times (the field has the same length for every env), so the flushes are warp-uniform.
+struct FieldWriter {
+  int32_t* dst;     // the tile's first row of the output tensor (nullptr: field not materialised)
+  uint32_t* img;    // this warp's 32 x kImgStride square
+  int wpe, n_valid, lane, j, k0;
+  uint32_t mask;    // envs whose observation is (re)written
+  bool mine;        // this lane's env is one of them
+  __device__ __forceinline__ void flush(const int m) {  // the square holds words [k0, k0 + m) of every env
     __syncwarp();
     if (lane < m) {
       int32_t* d = dst + k0 + lane;
-#pragma unroll 4
-      for (int e = 0; e < n_valid; ++e)
-        if ((mask >> e) & 1u) d[(size_t)e * wpe] = (int32_t)img[e * kImgStride + lane];
+      const uint32_t* s = img + lane;
+      if (mask == 0xFFFFFFFFu && n_valid == CBX_TILE) {
+#pragma unroll 8
+        for (int e = 0; e < CBX_TILE; ++e) d[(size_t)e * wpe] = (int32_t)s[e * kImgStride];
+      } else {
+        for (int e = 0; e < n_valid; ++e)
+          if ((mask >> e) & 1u) d[(size_t)e * wpe] = (int32_t)s[e * kImgStride];
+      }
     }
     __syncwarp();
+    k0 += m;
+    j = 0;
   }
-}
+  __device__ __forceinline__ void put(const uint32_t v) {
+    if (mine) img[lane * kImgStride + j] = v;
+    if (++j == 32) flush(32);
+  }
+  __device__ __forceinline__ void finish() {
+    if (j) flush(j);
+  }
+};
 
-// Static rows of the defender observation for ONE env of the scenario `tb`: [6n incoming | 6n outgoing | nsvc services],
-// followed by the first 4 bytes again (word reads wrap around the end of a row).  n / nsvc: layout sizes (zero padded).
+// Static rows of the defender observation for ONE env of the scenario `tb`: incoming [6n] | outgoing [6n] | services [nsvc],
+// each followed by its first 4 bytes again (reads wrap around the end of a row) and padded to a multiple of 4 bytes.
+__device__ __forceinline__ int defender_row_stride(const int len) { return (len + 4 + 3) & ~3; }
 __device__ __forceinline__ void build_defender_rows(const uint32_t* tb, uint8_t* rows, const int n, const int nsvc, const int lane) {
   const int n_own = (int)tb[CBX_H_N_NODES], nsvc_own = (int)tb[CBX_H_N_SERVICES];
   const int n6 = 6 * n;
   uint8_t* rin = rows;
-  uint8_t* rout = rows + n6 + 4;
-  uint8_t* rsvc = rout + n6 + 4;
+  uint8_t* rout = rows + defender_row_stride(n6);
+  uint8_t* rsvc = rout + defender_row_stride(n6);
   for (int i = lane; i < n6 + 4; i += 32) {
     const int q = i < n6 ? i : i - n6;
     const int node = q / 6, r = q - node * 6;
@@ -100,20 +69,21 @@ __device__ __forceinline__ void build_defender_rows(const uint32_t* tb, uint8_t*
     rin[i] = (uint8_t)((dob >> r) & 1u);
     rout[i] = (uint8_t)((dob >> (8 + r)) & 1u);
   }
-  for (int i = lane; i < nsvc + 4; i += 32) rsvc[i] = (uint8_t)((nsvc > 0 ? (i < nsvc ? i : i - nsvc) : 0) < nsvc_own);
+  for (int i = lane; i < nsvc + 4; i += 32) rsvc[i] = (uint8_t)((nsvc > 0 ? i % nsvc : 0) < nsvc_own);
 }
 
-// a tile's worth (32 envs) of a byte field whose rows all equal `row` (period `len` bytes): coalesced word stores
+// a tile's worth (32 envs) of a byte field whose rows all equal `row` (period `len` >= 4 bytes, wrap copy behind it):
+// coalesced word stores, each word = 4 bytes of the periodic string = two aligned shared-memory words funnel-shifted
 __device__ __forceinline__ void emit_periodic_bytes(int8_t* dst, const uint8_t* row, const int len, const int lane) {
   if (!dst || len == 0) return;
   uint32_t* d = reinterpret_cast<uint32_t*>(dst);  // 32 * len bytes from a 128-byte aligned tile base: whole words
+  const uint32_t* r32 = reinterpret_cast<const uint32_t*>(row);
   const int words = CBX_TILE * len / 4;
   int i = (lane * 4) % len;              // byte offset within the row of this lane's first word
   const int step = 128 % len;            // advance per iteration (32 lanes x 4 bytes)
   for (int w = lane; w < words; w += 32) {
-    const uint32_t v = (uint32_t)row[i] | ((uint32_t)row[i + 1 < len ? i + 1 : i + 1 - len] << 8) |
-                       ((uint32_t)row[i + 2 < len ? i + 2 : i + 2 - len] << 16) | ((uint32_t)row[i + 3 < len ? i + 3 : i + 3 - len] << 24);
-    d[w] = v;
+    const uint32_t lo = r32[i >> 2], hi = r32[(i >> 2) + 1];
+    d[w] = __funnelshift_r(lo, hi, (i & 3) * 8);
     i += step;
     if (i >= len) i -= len;
   }
@@ -220,11 +190,52 @@ __global__ void __launch_bounds__(CBX_WIDE_WARPS * 32, 1) cbx_wide_kernel(const 
       const bool mine = active && !keep;
       const int nd = mine ? (int)de[D_ND] : 0, nc = mine ? (int)de[D_NC] : 0;
       const bool blank = mine && de[D_KIND] == OBS_BLANK;
-      emit_field_rows(tm.scalars, 8, n_valid, enc_mask, img, lane, mine, GenStaging{c, STG_SCALARS});
-      emit_field_rows(tm.leaked, 4 * L.LEAK, n_valid, enc_mask, img, lane, mine, GenStaging{c, L.g_leaked});
-      emit_field_rows(tm.cachem, 2 * L.C, n_valid, enc_mask, img, lane, mine, GenCache{c, nc, blank, 0u, 0u});
-      emit_field_rows(tm.props, L.N * L.nprops, n_valid, enc_mask, img, lane, mine, GenProps{c, nd, L.nprops, blank, 0, 0, 0u, 0u});
-      emit_field_rows(tm.priv, L.N, n_valid, enc_mask, img, lane, mine, GenPriv{c, nd, blank});
+      FieldWriter fw;
+      fw.img = img; fw.n_valid = n_valid; fw.lane = lane; fw.mask = enc_mask; fw.mine = mine;
+      auto begin = [&](int32_t* dst, int wpe) { fw.dst = dst; fw.wpe = wpe; fw.j = 0; fw.k0 = 0; };
+      begin(tm.scalars, 8);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) fw.put(mine ? c.g(STG_SCALARS + k) : 0u);
+      fw.finish();
+      begin(tm.leaked, 4 * L.LEAK);
+      for (int k = 0; k < 4 * L.LEAK; ++k) fw.put(mine ? c.g(L.g_leaked + k) : 0u);
+      fw.finish();
+      begin(tm.cachem, 2 * L.C);  // credential_cache_matrix [C][2]: (target discovery index, port) per cached credential
+      for (int i = 0; i < L.C; ++i) {
+        uint32_t a = 0, b = 0;
+        if (!blank && i < nc) {
+          const uint32_t* rec = c.triple((int)c.half(L.o_cache, i));
+          a = c.byte(L.o_disc_idx, (int)rec[0]);
+          b = rec[1];
+        }
+        fw.put(a);
+        fw.put(b);
+      }
+      fw.finish();
+      begin(tm.props, L.N * L.nprops);  // discovered_nodes_properties [N][props]; 2 = unknown only in blank observations
+      for (int kk = 0; kk < L.N; ++kk) {
+        uint32_t lo = 0, hi = 0;
+        if (!blank && kk < nd) {
+          const int node = (int)c.byte(L.o_disc_order, kk);
+          lo = c.w(L.o_props + node * L.PW);
+          if (L.PW > 1) hi = c.w(L.o_props + node * L.PW + 1);
+        }
+        if (blank) lo = hi = 0;
+        const int np_lo = min(L.nprops, 32);
+        for (int pi = 0; pi < np_lo; ++pi) fw.put(blank ? 2u : ((lo >> pi) & 1u));
+        for (int pi = 32; pi < L.nprops; ++pi) fw.put(blank ? 2u : ((hi >> (pi - 32)) & 1u));
+      }
+      fw.finish();
+      begin(tm.priv, L.N);  // nodes_privilegelevel [N] in discovery order, as the observation saw it (staging snapshot)
+      for (int k = 0; k < L.N; ++k) {
+        uint32_t val = 0;
+        if (!blank && k < nd) {
+          const uint32_t node = c.byte(L.o_disc_order, k);
+          val = (c.g(L.g_priv + (node >> 4)) >> ((node & 15) * 2)) & 3u;
+        }
+        fw.put(val);
+      }
+      fw.finish();
       // ---- the defender's observation of the tile ----
       if (def_encode) {
         if (n_valid == CBX_TILE) {
@@ -243,8 +254,8 @@ __global__ void __launch_bounds__(CBX_WIDE_WARPS * 32, 1) cbx_wide_kernel(const 
             di32[w] = v;
           }
           emit_periodic_bytes(tm.fw_in, drows, n6, lane);
-          emit_periodic_bytes(tm.fw_out, drows + n6 + 4, n6, lane);
-          emit_periodic_bytes(tm.services, drows + 2 * (n6 + 4), L.nservices, lane);
+          emit_periodic_bytes(tm.fw_out, drows + defender_row_stride(n6), n6, lane);
+          emit_periodic_bytes(tm.services, drows + 2 * defender_row_stride(n6), L.nservices, lane);
         } else {
           encode_defender_by_warp<DimsDyn>(t, tm, n_valid, mask_all(), true, 0, 1);  // ragged last tile
         }

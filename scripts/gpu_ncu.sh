@@ -2,7 +2,7 @@
 # ncu evidence for the step kernel (B200_PROFILING.md recipe): launch list, then one full capture of the top kernel.
 # Run only after the plain command exited 0; numbers printed under ncu are never bench values.
 mkdir -p gpurun_out
-CMD="python bench.py --steps 5 --warmup 3 --no-cpu-baseline"
+CMD=${CMD:-"python bench.py --steps 5 --warmup 3 --no-cpu-baseline"}
 KERNEL=${KERNEL:-cbx_pipe_kernel}
 $CMD > gpurun_out/plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
