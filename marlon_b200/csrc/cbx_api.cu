@@ -128,12 +128,13 @@ bool plan_wide(const cbx_params& p, cbx_wide_plan* Q) {
   if (p.enc.warp_env < 1 || CBX_TILE != 32 || L.sz_connect > 0) return false;
   int64_t o = 0;
   Q->lut = (int)o; o += 512;
+  Q->lut4 = (int)o; o += 17 * 4 + 28;  // 17 x uint4, padded to 32 words
   Q->warps = (int)o;
   int64_t q = 0;
   Q->w_stage = (int)q; q += (int64_t)L.G * CBX_TILE;
   Q->w_desc = (int)q; q += (int64_t)p.enc.desc_words * CBX_TILE;
   Q->w_acts = (int)q; q += 22 * CBX_TILE;
-  Q->w_img = (int)q; q += 33 * CBX_TILE;
+  Q->w_img = (int)q; q += 36 * CBX_TILE;
   Q->w_drows = (int)q; q += 2 * ((6 * L.n + 4 + 3) / 4) + (L.nservices + 4 + 3) / 4 + 1;
   q = (q + 31) / 32 * 32;
   Q->warp_words = (int)q;

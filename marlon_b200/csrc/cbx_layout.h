@@ -124,7 +124,7 @@ enum { CBX_SH_ENC_MASK = 0, CBX_SH_TILE = 1 };
 struct cbx_wide_plan {
   int enabled;
   int nwarps;                                      // warps per CTA: as many as fit (<= CBX_WIDE_WARPS)
-  int lut, warps, warp_words;                      // shared-memory carve-up in 32-bit words
+  int lut, lut4, warps, warp_words;                // shared-memory carve-up in 32-bit words
   int w_stage, w_desc, w_acts, w_img, w_drows;     // inside a warp's area
   int total_bytes;
 };

@@ -16,7 +16,7 @@
 // Factored masks only (what these configurations use: a dense Chain-100 connect mask is 8.5 MB per env).
 namespace cbx {
 
-constexpr int kImgStride = 33;  // padded row of the transpose square: conflict-free both ways
+constexpr int kImgStride = 36;  // padded row of the transpose square: 16-byte aligned, conflict-free for 128-bit accesses both ways
 
 // Streaming writer of one int32 field of a tile: every thread `put`s ITS env's words in order; after every 32 words the warp
 // stores the padded square transposed -- env e's 32 words are 128 contiguous bytes of the output tensor.  All lanes call
@@ -24,21 +24,27 @@ constexpr int kImgStride = 33;  // padded row of the transpose square: conflict-
 struct FieldWriter {
   int32_t* dst;     // the tile's first row of the output tensor (nullptr: field not materialised)
   uint32_t* img;    // this warp's 32 x kImgStride square
+  const uint4* lut4;  // 17 entries: the 4 bits of a nibble as 4 int32 words; entry 16 = {2,2,2,2} ("unknown", blank observations)
   int wpe, n_valid, lane, j, k0;
   uint32_t mask;    // envs whose observation is (re)written
   bool mine;        // this lane's env is one of them
   __device__ __forceinline__ void flush(const int m) {  // the square holds words [k0, k0 + m) of every env
     __syncwarp();
-    if (lane < m) {
+    if ((wpe & 3) == 0) {  // env rows are 16-byte aligned: 4 envs x 128 bytes per store instruction
+      const int sub = lane >> 3, c4 = (lane & 7) * 4;
+      if (c4 < m) {
+#pragma unroll
+        for (int it = 0; it < CBX_TILE / 4; ++it) {
+          const int e = it * 4 + sub;
+          if (e < n_valid && ((mask >> e) & 1u))
+            *reinterpret_cast<uint4*>(dst + (size_t)e * wpe + k0 + c4) = *reinterpret_cast<const uint4*>(img + e * kImgStride + c4);
+        }
+      }
+    } else if (lane < m) {
       int32_t* d = dst + k0 + lane;
       const uint32_t* s = img + lane;
-      if (mask == 0xFFFFFFFFu && n_valid == CBX_TILE) {
-#pragma unroll 8
-        for (int e = 0; e < CBX_TILE; ++e) d[(size_t)e * wpe] = (int32_t)s[e * kImgStride];
-      } else {
-        for (int e = 0; e < n_valid; ++e)
-          if ((mask >> e) & 1u) d[(size_t)e * wpe] = (int32_t)s[e * kImgStride];
-      }
+      for (int e = 0; e < n_valid; ++e)
+        if ((mask >> e) & 1u) d[(size_t)e * wpe] = (int32_t)s[e * kImgStride];
     }
     __syncwarp();
     k0 += m;
@@ -48,8 +54,35 @@ struct FieldWriter {
     if (mine) img[lane * kImgStride + j] = v;
     if (++j == 32) flush(32);
   }
+  __device__ __forceinline__ void put4(const uint4 v) {  // j is a multiple of 4
+    if (mine) *reinterpret_cast<uint4*>(img + lane * kImgStride + j) = v;
+    j += 4;
+    if (j == 32) flush(32);
+  }
   __device__ __forceinline__ void finish() {
     if (j) flush(j);
+  }
+};
+
+// Bits -> int32 words, four at a time: the property matrix of an env is one long bit stream (props bits per discovered node).
+struct BitStream {
+  FieldWriter& fw;
+  uint64_t acc;
+  int nb;
+  bool blank;  // this env's observation is blank: every word is 2 (same control flow as the other lanes: flushes are collective)
+  __device__ __forceinline__ void append(const uint32_t lo, const uint32_t hi, const int nbits) {  // nbits <= 64 - 3
+    const uint64_t v = ((uint64_t)hi << 32) | lo;
+    acc |= v << nb;
+    nb += nbits;
+    while (nb >= 4) {
+      fw.put4(fw.lut4[blank ? 16u : ((uint32_t)acc & 15u)]);
+      acc >>= 4;
+      nb -= 4;
+    }
+  }
+  __device__ __forceinline__ void finish() {  // trailing bits (field length not a multiple of 4): word by word
+    for (int k = 0; k < nb; ++k) fw.put(blank ? 2u : ((uint32_t)(acc >> k) & 1u));
+    nb = 0;
   }
 };
 
@@ -113,6 +146,10 @@ __global__ void __launch_bounds__(CBX_WIDE_WARPS * 32, 1) cbx_wide_kernel(const 
     uint32_t lo = ((k & 0xF) * 0x00204081u) & 0x01010101u, hi = (((k >> 4) & 0xF) * 0x00204081u) & 0x01010101u;
     s_lut[k] = make_uint2(lo, hi);
   }
+  if (tid < 17) {
+    uint4* l4 = reinterpret_cast<uint4*>(smem + Q.lut4);
+    l4[tid] = tid == 16 ? make_uint4(2u, 2u, 2u, 2u) : make_uint4(tid & 1u, (tid >> 1) & 1u, (tid >> 2) & 1u, (tid >> 3) & 1u);
+  }
   __syncthreads();  // the only CTA-wide barrier
 
   Acc acc;
@@ -120,6 +157,14 @@ __global__ void __launch_bounds__(CBX_WIDE_WARPS * 32, 1) cbx_wide_kernel(const 
   for (int k = 0; k < CBX_STAT_COUNT; ++k) acc.v[k] = 0.0;
   int slice_of_kind[3] = {p.slice_of_kind[0], p.slice_of_kind[1], p.slice_of_kind[2]};
   int rows_scn = -1;  // scenario the defender rows in `drows` were built for
+  long long prof_t = p.prof ? clock64() : 0;
+  long long pp[6] = {0, 0, 0, 0, 0, 0};  // per-warp phase cycles (instrumentation slots 1..6), flushed once at the end
+#define CBX_WPROF(slot)                    \
+  if (p.prof) {                            \
+    long long _now = clock64();            \
+    pp[(slot) - 1] += _now - prof_t;       \
+    prof_t = _now;                         \
+  }
   const int n6 = 6 * L.n;
   const int nw = (int)blockDim.x >> 5;  // warps per CTA (<= CBX_WIDE_WARPS)
   const int gw = (int)gridDim.x * nw;
@@ -130,6 +175,8 @@ __global__ void __launch_bounds__(CBX_WIDE_WARPS * 32, 1) cbx_wide_kernel(const 
     const uint32_t* tb = p.tables + (size_t)scn * p.table_stride;  // global memory, L1-resident
     const uint32_t* s_init = tb + p.table_words;
     uint32_t* gst = p.state + (int64_t)tile * L.S * CBX_TILE;        // the tile's state, in place
+    // pull the tile's S lines towards L2 now, all at once: the game logic's dependent accesses then pay L2 latency, not HBM's
+    for (int r = lane; r < L.S; r += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(gst + (size_t)r * CBX_TILE));
     if (!reset_only) {
       if (p.att_actions && (who_att || !marlon))
         for (int q = lane; q < n_valid * AW; q += 32) act[q] = p.att_actions[e0 * AW + q];
@@ -137,6 +184,7 @@ __global__ void __launch_bounds__(CBX_WIDE_WARPS * 32, 1) cbx_wide_kernel(const 
         for (int q = lane; q < n_valid * 12; q += 32) act[CBX_TILE * 10 + q] = p.def_actions[e0 * 12 + q];
     }
     __syncwarp();
+    CBX_WPROF(1)  // actions in
     const bool active = lane < n_valid;
     Ctx c;
     c.st = gst + lane; c.sg = sg + lane; c.tb = tb; c.L = &L; c.cfg = &cfg; c.env = e0 + lane;
@@ -148,6 +196,7 @@ __global__ void __launch_bounds__(CBX_WIDE_WARPS * 32, 1) cbx_wide_kernel(const 
     }
     const uint32_t att_done_mask = __ballot_sync(0xFFFFFFFFu, att_done != 0);
     const uint32_t keep1 = __ballot_sync(0xFFFFFFFFu, keep != 0);
+    CBX_WPROF(2)  // attacker logic
     Tile t;
     t.L = &L; t.tb = tb; t.st = gst; t.sg = sg; t.desc = desc; t.lut = s_lut; t.K = &p.enc; t.DW = DW;
     // terminal observations of the envs that finished: BEFORE the auto-reset (rare; element-wise encoder)
@@ -183,6 +232,7 @@ __global__ void __launch_bounds__(CBX_WIDE_WARPS * 32, 1) cbx_wide_kernel(const 
     }
     const uint32_t enc_mask = ~__ballot_sync(0xFFFFFFFFu, keep != 0);
     __syncwarp();
+    CBX_WPROF(4)  // auto-reset, defender logic, descriptors
     // ---- the attacker's observation fields, transposed through the padded square ----
     {
       const Target tm = make_target(p.v, L, e0, false);
@@ -192,6 +242,7 @@ __global__ void __launch_bounds__(CBX_WIDE_WARPS * 32, 1) cbx_wide_kernel(const 
       const bool blank = mine && de[D_KIND] == OBS_BLANK;
       FieldWriter fw;
       fw.img = img; fw.n_valid = n_valid; fw.lane = lane; fw.mask = enc_mask; fw.mine = mine;
+      fw.lut4 = reinterpret_cast<const uint4*>(smem + Q.lut4);
       auto begin = [&](int32_t* dst, int wpe) { fw.dst = dst; fw.wpe = wpe; fw.j = 0; fw.k0 = 0; };
       begin(tm.scalars, 8);
 #pragma unroll
@@ -213,17 +264,30 @@ __global__ void __launch_bounds__(CBX_WIDE_WARPS * 32, 1) cbx_wide_kernel(const 
       }
       fw.finish();
       begin(tm.props, L.N * L.nprops);  // discovered_nodes_properties [N][props]; 2 = unknown only in blank observations
-      for (int kk = 0; kk < L.N; ++kk) {
-        uint32_t lo = 0, hi = 0;
-        if (!blank && kk < nd) {
-          const int node = (int)c.byte(L.o_disc_order, kk);
-          lo = c.w(L.o_props + node * L.PW);
-          if (L.PW > 1) hi = c.w(L.o_props + node * L.PW + 1);
+      if (L.nprops > 60) {  // word by word (warp-uniform choice: the flushes inside are collective)
+        for (int kk = 0; kk < L.N; ++kk) {
+          uint32_t lo = 0, hi = 0;
+          if (!blank && kk < nd) {
+            const int node = (int)c.byte(L.o_disc_order, kk);
+            lo = c.w(L.o_props + node * L.PW);
+            if (L.PW > 1) hi = c.w(L.o_props + node * L.PW + 1);
+          }
+          for (int pi = 0; pi < L.nprops; ++pi) fw.put(blank ? 2u : (((pi < 32 ? lo : hi) >> (pi & 31)) & 1u));
         }
-        if (blank) lo = hi = 0;
-        const int np_lo = min(L.nprops, 32);
-        for (int pi = 0; pi < np_lo; ++pi) fw.put(blank ? 2u : ((lo >> pi) & 1u));
-        for (int pi = 32; pi < L.nprops; ++pi) fw.put(blank ? 2u : ((hi >> (pi - 32)) & 1u));
+      } else {
+        BitStream bs{fw, 0ull, 0, blank};
+        const uint32_t keep_lo = L.nprops >= 32 ? 0xFFFFFFFFu : ((1u << L.nprops) - 1u);
+        const uint32_t keep_hi = L.nprops > 32 ? ((1u << (L.nprops - 32)) - 1u) : 0u;
+        for (int kk = 0; kk < L.N; ++kk) {
+          uint32_t lo = 0, hi = 0;
+          if (kk < nd) {
+            const int node = (int)c.byte(L.o_disc_order, kk);
+            lo = c.w(L.o_props + node * L.PW) & keep_lo;
+            if (L.PW > 1) hi = c.w(L.o_props + node * L.PW + 1) & keep_hi;
+          }
+          bs.append(lo, hi, L.nprops);
+        }
+        bs.finish();
       }
       fw.finish();
       begin(tm.priv, L.N);  // nodes_privilegelevel [N] in discovery order, as the observation saw it (staging snapshot)
@@ -236,6 +300,7 @@ __global__ void __launch_bounds__(CBX_WIDE_WARPS * 32, 1) cbx_wide_kernel(const 
         fw.put(val);
       }
       fw.finish();
+      CBX_WPROF(5)  // attacker observation fields
       // ---- the defender's observation of the tile ----
       if (def_encode) {
         if (n_valid == CBX_TILE) {
@@ -264,7 +329,12 @@ __global__ void __launch_bounds__(CBX_WIDE_WARPS * 32, 1) cbx_wide_kernel(const 
     // deferred defender auto-reset (DummyVecEnv resets after the step; the observations above were taken before it)
     if (active && def_done) c.defender_reset(s_init);
     __syncwarp();
+    CBX_WPROF(6)  // defender observation + deferred reset
   }
+  if (p.prof && lane == 0)
+    for (int k = 0; k < 6; ++k)
+      if (pp[k]) atomicAdd(p.prof + 1 + k, (unsigned long long)pp[k]);
+#undef CBX_WPROF
   // episode statistics: warp shuffle reduce, one atomic per slot per warp
 #pragma unroll
   for (int k = 0; k < CBX_STAT_COUNT; ++k) {

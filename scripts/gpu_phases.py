@@ -3,7 +3,7 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, bench
 from marlon_b200.batch import Batch
-comp, cfg = bench.workload_config()
+comp, cfg = bench.workload_config(workload=os.environ.get("WORKLOAD", "toyctf"))
 n = int(os.environ.get("ENVS", 65536))
 b = Batch(comp, cfg, n); b.reset()
 acts = []
