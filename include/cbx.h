@@ -374,6 +374,16 @@ int64_t cbx_batch_launch_count(const cbx_batch* b);
 int cbx_batch_enable_timing(cbx_batch* b, int enabled);
 int cbx_batch_step_kernel_ms(cbx_batch* b, double* mean_ms, int64_t* launches);
 
+/* Generalised advantage estimation over a device-resident rollout: what stable-baselines3's
+ * RolloutBuffer.compute_returns_and_advantage computes when MARLon's on_rollout_end calls it
+ * (marlon/baseline_models/multiagent/baseline_marlon_agent.py:276-284).  All pointers are DEVICE pointers; rewards / values /
+ * episode_starts / advantages / returns are [n_steps, n_envs] row-major, last_values / last_dones are [n_envs].
+ * advantages[t] = delta_t + gamma * lambda * (1 - start_{t+1}) * advantages[t+1],
+ * delta_t = r_t + gamma * V_{t+1} * (1 - start_{t+1}) - V_t, with V_T = last_values and start_T = last_dones. */
+int cbx_gae(const float* rewards, const float* values, const uint8_t* episode_starts, const float* last_values,
+            const uint8_t* last_dones, double gamma, double gae_lambda, int n_steps, int64_t n_envs, float* advantages,
+            float* returns, void* cuda_stream);
+
 /* Which kernel one step launches (reported by bench.py next to the roofline): out8[0] = 1 pipelined kernel (cbx_pipe_kernel:
  * logic warps ahead of TMA-storing encoder warps) / 2 warp-per-tile kernel for large state (cbx_wide_kernel) / 0 fused kernel
  * (cbx_step_kernel); [1] CTAs; [2] threads per CTA;

@@ -18,7 +18,7 @@ SYMBOLS = [
     "cbx_batch_create", "cbx_batch_destroy", "cbx_batch_reset", "cbx_batch_step", "cbx_batch_step_host",
     "cbx_batch_sample_actions", "cbx_batch_views", "cbx_batch_stats_reset", "cbx_export_words",
     "cbx_batch_export_state", "cbx_batch_launch_count", "cbx_batch_enable_timing", "cbx_batch_step_kernel_ms",
-    "cbx_abi_sizeof", "cbx_batch_step_ex", "cbx_batch_reset_ex", "cbx_batch_phase_cycles", "cbx_batch_notify_reset", "cbx_batch_kernel_info", "cbx_batch_create_multi", "cbx_batch_export_words",
+    "cbx_abi_sizeof", "cbx_batch_step_ex", "cbx_batch_reset_ex", "cbx_batch_phase_cycles", "cbx_batch_notify_reset", "cbx_batch_kernel_info", "cbx_batch_create_multi", "cbx_batch_export_words", "cbx_gae",
 ]
 
 
@@ -67,6 +67,7 @@ def load():
     L.cbx_batch_create_multi.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp]
     L.cbx_batch_export_words.restype = C.c_int64
     L.cbx_batch_export_words.argtypes = [vp]
+    L.cbx_gae.argtypes = [vp, vp, vp, vp, vp, C.c_double, C.c_double, C.c_int, i64, vp, vp, vp]
     L.cbx_abi_sizeof.restype = C.c_size_t
     L.cbx_abi_sizeof.argtypes = [C.c_int]
     if L.cbx_abi_version() != _abi.ABI_VERSION:

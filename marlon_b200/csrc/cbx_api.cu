@@ -19,6 +19,9 @@ cudaError_t cbx_launch_sample(const cbx_params* p, int32_t* att, int32_t* def, u
 cudaError_t cbx_kernel_attrs(int smem_bytes, int use_tma, int fast, int* blocks_per_sm);
 cudaError_t cbx_pipe_attrs(int enc, int smem_bytes);
 cudaError_t cbx_launch_pipe(const cbx_params* p, int op, int grid, cudaStream_t stream);
+cudaError_t cbx_launch_gae(const float* rewards, const float* values, const uint8_t* episode_starts, const float* last_values,
+                           const uint8_t* last_dones, float gamma, float lam, int T, int64_t n, float* advantages, float* returns,
+                           cudaStream_t stream);
 cudaError_t cbx_wide_attrs(int smem_bytes);
 cudaError_t cbx_launch_wide(const cbx_params* p, int op, int grid, cudaStream_t stream);
 }
@@ -842,6 +845,15 @@ int cbx_batch_export_state(cbx_batch* b, int64_t begin, int64_t end, int32_t* ou
     p += L.C;
     for (int k = 0; k < (L.nsecrets + 31) / 32; ++k) p[k] = (int32_t)w(L.o_gathered + k);
   }
+  return CBX_OK;
+}
+
+int cbx_gae(const float* rewards, const float* values, const uint8_t* episode_starts, const float* last_values, const uint8_t* last_dones,
+            double gamma, double gae_lambda, int n_steps, int64_t n_envs, float* advantages, float* returns, void* cuda_stream) {
+  if (!rewards || !values || !episode_starts || !last_values || !last_dones || !advantages || !returns) return fail(CBX_ERR_INVALID, "null argument");
+  if (n_steps <= 0 || n_envs <= 0) return fail(CBX_ERR_INVALID, "empty rollout");
+  CUDA_TRY(cbx_launch_gae(rewards, values, episode_starts, last_values, last_dones, (float)gamma, (float)gae_lambda, n_steps, n_envs,
+                          advantages, returns, (cudaStream_t)cuda_stream));
   return CBX_OK;
 }
 

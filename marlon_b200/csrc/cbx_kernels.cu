@@ -1212,6 +1212,31 @@ __global__ void cbx_sample_kernel(const __grid_constant__ cbx_params p, int32_t*
 
 }  // namespace cbx
 
+namespace cbx {
+// ---- generalised advantage estimation over a device-resident rollout --------------------------------
+// stable-baselines3 RolloutBuffer.compute_returns_and_advantage, the routine MARLon's on_rollout_end reaches through
+// baseline_marlon_agent.py:276-284: a backward scan per env over [T, n] arrays (one thread per env, coalesced rows).
+__global__ void cbx_gae_kernel(const float* __restrict__ rewards, const float* __restrict__ values, const uint8_t* __restrict__ episode_starts,
+                               const float* __restrict__ last_values, const uint8_t* __restrict__ last_dones, const float gamma,
+                               const float lam, const int T, const int64_t n, float* __restrict__ advantages, float* __restrict__ returns) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  float next_value = last_values[e];
+  float next_non_terminal = 1.0f - (float)(last_dones[e] != 0);
+  float gae = 0.0f;
+  for (int t = T - 1; t >= 0; --t) {
+    const int64_t i = (int64_t)t * n + e;
+    const float v = values[i];
+    const float delta = rewards[i] + gamma * next_value * next_non_terminal - v;
+    gae = delta + gamma * lam * next_non_terminal * gae;
+    advantages[i] = gae;
+    returns[i] = gae + v;
+    next_value = v;
+    next_non_terminal = 1.0f - (float)(episode_starts[i] != 0);
+  }
+}
+}  // namespace cbx
+
 // ---- launch helpers used by cbx_api.cu ------------------------------------------------------------------------------------
 template <bool A, int B>
 static cudaError_t attrs_of(int smem_bytes, int* blocks_per_sm) {
@@ -1258,6 +1283,14 @@ cudaError_t cbx_wide_attrs(int smem_bytes) {
 }
 cudaError_t cbx_launch_wide(const cbx_params* p, int op, int grid, cudaStream_t stream) {
   cbx::cbx_wide_kernel<1><<<grid, p->wide.nwarps * 32, p->wide.total_bytes, stream>>>(*p, op);
+  return cudaGetLastError();
+}
+cudaError_t cbx_launch_gae(const float* rewards, const float* values, const uint8_t* episode_starts, const float* last_values,
+                           const uint8_t* last_dones, float gamma, float lam, int T, int64_t n, float* advantages, float* returns,
+                           cudaStream_t stream) {
+  const int threads = 128;
+  cbx::cbx_gae_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, stream>>>(rewards, values, episode_starts, last_values, last_dones,
+                                                                                     gamma, lam, T, n, advantages, returns);
   return cudaGetLastError();
 }
 cudaError_t cbx_launch_sample(const cbx_params* p, int32_t* att, int32_t* def, uint64_t seed, uint32_t step, cudaStream_t stream) {

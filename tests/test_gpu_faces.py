@@ -228,3 +228,67 @@ def test_universe_over_generated_random_networks():
     assert st["env_steps"] == 192 * 80 and st["episodes"] >= 192 and st["att_invalid"] == 0
     assert float(r["attacker_reward"].abs().sum()) >= 0
     u.close()
+
+
+def _gae_numpy(rewards, values, starts, last_values, last_dones, gamma, lam):
+    """stable-baselines3 RolloutBuffer.compute_returns_and_advantage, restated (float32 like SB3's numpy buffers)."""
+    T = rewards.shape[0]
+    adv = np.zeros_like(rewards)
+    last = np.zeros(rewards.shape[1], dtype=np.float32)
+    for t in reversed(range(T)):
+        if t == T - 1:
+            nnt, nv = 1.0 - last_dones.astype(np.float32), last_values
+        else:
+            nnt, nv = 1.0 - starts[t + 1].astype(np.float32), values[t + 1]
+        delta = rewards[t] + np.float32(gamma) * nv * nnt - values[t]
+        last = delta + np.float32(gamma) * np.float32(lam) * nnt * last
+        adv[t] = last
+    return adv, adv + values
+
+
+def test_device_rollout_and_gae():
+    """collect_rollouts with everything on the device; GAE kernel against the SB3 formula."""
+    import torch
+
+    from marlon_b200.rollout import DeviceRolloutBuffer, collect_rollouts
+    from marlon_b200.universe import MultiAgentUniversalEnv
+
+    n, T = 300, 24
+    u = MultiAgentUniversalEnv("CyberBattleToyCtf-v0", n, maximum_node_count=12, maximum_total_credentials=10, max_timesteps=9)
+    u.reset()
+    dev = u.batch.torch_device
+    calls = {"k": 0}
+
+    def attacker_policy(obs, masks):
+        calls["k"] += 1
+        att, _ = u.sample_actions(seed=calls["k"])
+        value = obs["discovered_node_count"].to(torch.float32) * 0.5 + obs["credential_cache_length"].to(torch.float32)
+        return att, value, torch.full((n,), -1.25, device=dev)
+
+    def defender_policy(obs, masks):
+        _, dfn = u.sample_actions(seed=1000 + calls["k"])
+        return dfn, obs["infected_nodes"].to(torch.float32).sum(dim=1), torch.full((n,), -2.5, device=dev)
+
+    ab = DeviceRolloutBuffer(T, n, 10, dev, gamma=0.99, gae_lambda=0.95, obs_spec={"discovered_node_count": ((), torch.int32)})
+    db = DeviceRolloutBuffer(T, n, 12, dev, gamma=0.9, gae_lambda=0.8)
+    assert collect_rollouts(u, attacker_policy, ab, defender_policy, db)
+    assert ab.full and db.full
+    for buf, gamma, lam, last_starts in ((ab, 0.99, 0.95, u._att_starts), (db, 0.9, 0.8, u._def_starts)):
+        r, v, s = buf.rewards.cpu().numpy(), buf.values.cpu().numpy(), buf.episode_starts.cpu().numpy()
+        assert s[0].all()  # _last_episode_starts right after reset
+        adv, ret = buf.advantages.cpu().numpy(), buf.returns.cpu().numpy()
+        # the kernel's bootstrap inputs are recomputed here the way collect_rollouts produced them
+        if buf is ab:
+            o = u.attacker_observation()
+            lv = (o["discovered_node_count"].to(torch.float32) * 0.5 + o["credential_cache_length"].to(torch.float32)).cpu().numpy()
+        else:
+            lv = u.defender_observation()["infected_nodes"].to(torch.float32).sum(dim=1).cpu().numpy()
+        want_adv, want_ret = _gae_numpy(r, v, s, lv, last_starts.cpu().numpy(), gamma, lam)
+        assert np.allclose(adv, want_adv, rtol=1e-5, atol=1e-3) and np.allclose(ret, want_ret, rtol=1e-5, atol=1e-3)
+    # episode starts after step 0 are the done flags of the step before: as many as episodes finished (minus those of the last step)
+    st = u.episode_statistics(reduce=False)
+    assert int(ab.episode_starts[1:].sum().item()) + int(u._att_starts.sum().item()) == int(st["episodes"])
+    assert st["env_steps"] == n * T
+    assert (ab.observations["discovered_node_count"][0] == 1).all()  # the observation the first action was chosen on
+    assert ab.actions.shape == (T, n, 10) and db.actions.shape == (T, n, 12)
+    u.close()
