@@ -33,12 +33,26 @@ WORKLOADS = {
               "reference_stale defender, SB3 auto-reset)",
     "chain100": "CyberBattleChain-v0 size=100 (N=102,C=102) MARLon attacker+defender pair step (config 4: the 1M-env sharded case; "
                 "factored masks -- a dense connect mask would be 8.5 MB per env)",
+    "random16": "CyberBattleRandom-v0, 16 generated 65-node networks (seeds 0-15) side by side in one batch (config 5: padded layout, "
+                "N=72, C=192, 32 leak slots), MARLon attacker+defender pair step",
 }
 
 
 def workload_config(mask_mode=0, workload="toyctf"):
     from marlon_b200 import _abi, config, scenario, scenarios
 
+    if workload == "random16":
+        from marlon_b200 import random_network
+
+        comps = [scenario.compile_scenario(random_network.random_environment(sd)) for sd in range(16)]
+        cfg = config.make_config(
+            _abi.MODE_MARLON, maximum_node_count=72, maximum_total_credentials=192, maximum_discoverable_credentials_per_action=32,
+            throws_on_invalid_actions=False, attacker_goal=config.AttackerGoal(own_atleast_percent=1.0),
+            defender_constraint=config.DefenderConstraint(0.60), losing_reward=-5000.0,
+            attacker_max_timesteps=2000, attacker_invalid_action_reward_modifier=-1.0,
+            defender_enabled=True, defender_max_timesteps=2000, defender_invalid_action_reward=-1,
+            defender_reset_on_constraint_broken=True, defender_loss_reward=-5000.0, mask_mode=1)
+        return comps, cfg
     if workload == "chain100":
         comp = scenario.compile_scenario(scenarios.chain_environment(100))
         cfg = config.make_config(
@@ -268,7 +282,11 @@ def run_ours(args):
     K, W = args.steps, args.warmup
 
     # ---- record the synthetic action tape (valid attacker actions for the evolving state), untimed ----
-    rec = Batch(comp, cfg, n, device=local)
+    multi = isinstance(comp, list)
+    counts = [n // len(comp)] * len(comp) if multi else n  # envs per scenario (multiples of 32 for the default sizes)
+    if multi:
+        n = sum(counts)
+    rec = Batch(comp, cfg, counts, device=local)
     rec.reset()
     tape_a = torch.empty((W + K, n, 10), dtype=torch.int32, device=dev)
     tape_d = torch.empty((W + K, n, 12), dtype=torch.int32, device=dev)
@@ -280,7 +298,7 @@ def run_ours(args):
     rec.close()
     del rec
 
-    b = Batch(comp, cfg, n, device=local)
+    b = Batch(comp, cfg, counts, device=local)
     b.reset()
     S_words = b.export_state(0, 1).shape[1]  # canonical words (not the packed layout); packed size comes from the library
     packed_state_words = int(os.environ.get("CBX_STATE_WORDS", "0")) or None
@@ -326,7 +344,7 @@ def run_ours(args):
     h_a = torch.empty((CH, n, 10), dtype=torch.int32, pin_memory=True)
     h_d = torch.empty((CH, n, 12), dtype=torch.int32, pin_memory=True)
     h_an, h_dn = h_a.numpy(), h_d.numpy()
-    b2 = Batch(comp, cfg, n, device=local)
+    b2 = Batch(comp, cfg, counts, device=local)
     b2.reset()
     for s in range(W):
         b2.step(tape_a[s], tape_d[s])
@@ -353,8 +371,16 @@ def run_ours(args):
 
         peak, peak_kind = measured_peak_gbs()
         # packed per-env state words: ask the library through the export of the layout (S) -- state array bytes / n_pad
-        S_packed = packed_state_words or _packed_state_words(comp, cfg)
-        ab = algorithmic_bytes_per_env_step(comp, cfg, S_packed)
+        if multi:  # padded layout: the largest scenario's dimensions, as the library lays the batch out
+            import copy
+
+            big = copy.copy(max(comp, key=lambda c: c.n_nodes))
+            big.n_services = max(c.n_services for c in comp)
+            S_packed = packed_state_words or max(_packed_state_words(c, cfg) for c in comp)
+            ab = algorithmic_bytes_per_env_step(big, cfg, S_packed)
+        else:
+            S_packed = packed_state_words or _packed_state_words(comp, cfg)
+            ab = algorithmic_bytes_per_env_step(comp, cfg, S_packed)
         achieved = ab["total"] * n / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else None
         total_envs = n * world
         line = {
