@@ -398,8 +398,10 @@ def run_ours(args):
                          "kernel": kinfo["name"], "kernel_launch": kinfo, "kernel_ms": kernel_ms, "kernel_launches_timed": kernel_n},
             "e2e": {"value": total_envs * K / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": n * (10 + 12) * 4,
                     "d2h_bytes_per_step": n * 12,
-                    "note": "cbx_batch_step_host per step: H2D of this step's actions from page-locked host memory, the step kernel, "
-                            "D2H of rewards + done flags, stream sync; observations stay in HBM as torch tensors (consumers are GPU policies)"},
+                    "note": "cbx_batch_step_host per step with HOST action buffers in page-locked memory: the step kernel reads each "
+                            "tile's actions over PCIe in place (TMA bulk loads from the mapped host buffers; h2d_bytes_per_step is what "
+                            "crosses the link), then D2H of rewards + done flags as one block, stream sync, results copied out of the "
+                            "reused pinned buffer; observations stay in HBM as torch tensors (consumers are GPU policies)"},
             "gpu_launches": launches,
             "clocks": clk,
             "episode_stats": {k: float(v) for k, v in zip(_abi.STAT_NAMES, stats.cpu().numpy())},

@@ -725,15 +725,32 @@ int cbx_batch_step_host(cbx_batch* b, const int32_t* h_att, const int32_t* h_def
     if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
     return at.type == cudaMemoryTypeHost;
   };
+  // Page-locked action buffers are read by the step kernel IN PLACE over PCIe (pinned allocations are mapped into the device
+  // address space under unified addressing): the transfer of a tile's actions overlaps the other tiles' work instead of
+  // preceding the launch.  Pageable buffers go through the library's pinned staging first.  CBX_HOST_ZEROCOPY=0 restores
+  // the explicit H2D copies.
+  static const bool zero_copy = [] { const char* e = getenv("CBX_HOST_ZEROCOPY"); return !(e && e[0] == '0'); }();
+  auto device_view = [](const void* pinned) -> const int32_t* {
+    void* d = nullptr;
+    if (cudaHostGetDevicePointer(&d, const_cast<void*>(pinned), 0) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return (const int32_t*)d;
+  };
   const int32_t* src_att = h_att;
   if (!is_pinned(h_att)) { memcpy(b->h_att, h_att, (size_t)n * aw * 4); src_att = b->h_att; }
-  CUDA_TRY(cudaMemcpyAsync(b->d_att, src_att, (size_t)n * aw * 4, cudaMemcpyHostToDevice, st));
+  const int32_t* src_def = nullptr;
   if (need_def) {
-    const int32_t* src_def = h_def;
+    src_def = h_def;
     if (!is_pinned(h_def)) { memcpy(b->h_def, h_def, (size_t)n * 12 * 4); src_def = b->h_def; }
-    CUDA_TRY(cudaMemcpyAsync(b->d_def, src_def, (size_t)n * 12 * 4, cudaMemcpyHostToDevice, st));
   }
-  int rc = cbx_batch_step(b, b->d_att, need_def ? b->d_def : nullptr, nullptr, cuda_stream);
+  const int32_t* k_att = zero_copy ? device_view(src_att) : nullptr;
+  const int32_t* k_def = (zero_copy && need_def) ? device_view(src_def) : nullptr;
+  if (!k_att || (need_def && !k_def)) {  // explicit copies
+    CUDA_TRY(cudaMemcpyAsync(b->d_att, src_att, (size_t)n * aw * 4, cudaMemcpyHostToDevice, st));
+    if (need_def) CUDA_TRY(cudaMemcpyAsync(b->d_def, src_def, (size_t)n * 12 * 4, cudaMemcpyHostToDevice, st));
+    k_att = b->d_att;
+    k_def = need_def ? b->d_def : nullptr;
+  }
+  int rc = cbx_batch_step(b, k_att, k_def, nullptr, cuda_stream);
   if (rc) return rc;
   const cbx_views& v = b->p.v;
   const bool out_pinned = is_pinned(host_out);

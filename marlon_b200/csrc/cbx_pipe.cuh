@@ -313,23 +313,32 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
       const int n_valid = (int)min((int64_t)CBX_TILE, p.n_envs - e0);
       const uint4* gstate = reinterpret_cast<const uint4*>(p.state + (int64_t)tile * L.S * CBX_TILE);
       const int state_q = L.S * CBX_TILE / 4;  // 16-byte words of a state tile
+      const bool need_att = !reset_only && p.att_actions && (who_att || !marlon);
+      const bool need_def = !reset_only && def_on;
+      // a full tile's actions are one contiguous 16-byte aligned block per agent: they ride the same mbarrier as the state
+      // tile (bulk copies also read page-locked HOST memory efficiently: cbx_batch_step_host hands host pointers over)
+      const bool bulk_acts = Q.logic_tma && n_valid == CBX_TILE && ((((uintptr_t)p.att_actions) | ((uintptr_t)p.def_actions)) & 15u) == 0;
       if (Q.logic_tma) {
         // the previous tile's state store and field copies (issued by lanes 0..6) must be done reading this warp's buffer
         tma_store_wait_read();
         __syncwarp();
         if (lane == 0) {
-          mbar_expect_tx(&bar_load[warp], (uint32_t)L.S * kRowBytes);
+          const uint32_t att_bytes = (bulk_acts && need_att) ? (uint32_t)(CBX_TILE * AW * 4) : 0u;
+          const uint32_t def_bytes = (bulk_acts && need_def) ? (uint32_t)(CBX_TILE * 12 * 4) : 0u;
+          mbar_expect_tx(&bar_load[warp], (uint32_t)L.S * kRowBytes + att_bytes + def_bytes);
           tma_load_1d(lb, gstate, (uint32_t)L.S * kRowBytes, &bar_load[warp]);
+          if (att_bytes) tma_load_1d(act, p.att_actions + e0 * AW, att_bytes, &bar_load[warp]);
+          if (def_bytes) tma_load_1d(act + CBX_TILE * 10, p.def_actions + e0 * 12, def_bytes, &bar_load[warp]);
         }
       } else {
         uint4* d = reinterpret_cast<uint4*>(lb);
 #pragma unroll 7
         for (int q = lane; q < state_q; q += 32) d[q] = gstate[q];
       }
-      if (!reset_only) {
-        if (p.att_actions && (who_att || !marlon))
+      if (!bulk_acts) {
+        if (need_att)
           for (int q = lane; q < n_valid * AW; q += 32) act[q] = p.att_actions[e0 * AW + q];
-        if (def_on)
+        if (need_def)
           for (int q = lane; q < n_valid * 12; q += 32) act[CBX_TILE * 10 + q] = p.def_actions[e0 * 12 + q];
       }
       if (Q.logic_tma) {
