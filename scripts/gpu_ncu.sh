@@ -12,5 +12,5 @@ ncu --set full --clock-control none --import-source on -k regex:$KERNEL -s 16 -c
 echo "full capture rc=$?"
 tail -3 gpurun_out/ncu_full.log
 ncu -i gpurun_out/prof.ncu-rep --page raw --csv > gpurun_out/prof_raw.csv 2>/dev/null
-ncu -i gpurun_out/prof.ncu-rep --page source --csv --print-source cuda,sass > gpurun_out/prof_src.csv 2>/dev/null
+ncu -i gpurun_out/prof.ncu-rep --page source --csv --print-source cuda,sass > gpurun_out/prof_src.csv 2>/dev/null; python scripts/ncu_lines.py gpurun_out/prof_src.csv 40 | cut -c1-200 > gpurun_out/prof_lines.txt
 ls -la gpurun_out/ | tail -12

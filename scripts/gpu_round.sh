@@ -15,3 +15,14 @@ print("value %.4g env-steps/s  ms/step %.4f  kernel %s %.4f ms  achieved %.1f GB
     d["e2e"]["value"], d.get("cpu_baseline"), d["clocks"]))
 PY
 bash scripts/gpu_ncu.sh
+echo "== 1M envs on one GPU (index-width sanity + large-batch throughput)"
+timeout 600 python bench.py --envs-per-gpu 1048576 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_1m.log 2> gpurun_out/bench_1m.err; echo "rc=$?"
+python - <<'PY'
+import json
+try:
+    d = json.loads(open('gpurun_out/bench_1m.log').read().strip().splitlines()[-1])
+    print("1M envs: value %.4g  kernel %.4f ms  achieved %.1f GB/s  frac %.3f  env_steps %s" % (d["value"], d["roofline"]["kernel_ms"], d["roofline"]["achieved"], d["roofline"]["frac"], d["episode_stats"]["env_steps"]))
+except Exception as e:
+    print("1M run failed", e); print(open('gpurun_out/bench_1m.err').read()[-1500:])
+PY
+rm -f gpurun_out/prof.ncu-rep gpurun_out/prof_src.csv
