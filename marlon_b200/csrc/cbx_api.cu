@@ -125,7 +125,7 @@ bool plan_pipe(const cbx_params& p, int wl, int we, cbx_pipe_plan* Q) {
 }
 
 // Shared-memory plan of the warp-per-tile kernel (cbx_wide.cuh): factored masks, warp-per-env encoder available.
-bool plan_wide(const cbx_params& p, cbx_wide_plan* Q) {
+bool plan_wide(const cbx_params& p, int sms, cbx_wide_plan* Q) {
   const cbx_layout& L = p.lay;
   memset(Q, 0, sizeof(*Q));
   if (p.enc.warp_env < 1 || CBX_TILE != 32 || L.sz_connect > 0) return false;
@@ -141,10 +141,16 @@ bool plan_wide(const cbx_params& p, cbx_wide_plan* Q) {
   Q->w_drows = (int)q; q += 2 * ((6 * L.n + 4 + 3) / 4) + (L.nservices + 4 + 3) / 4 + 1;
   q = (q + 31) / 32 * 32;
   Q->warp_words = (int)q;
-  // as many warps as fit while leaving L1 room for the scenario tables and the hot state lines
-  int nw = (int)((192 * 1024 / 4 - o) / q);
+  // as many warps as fit while leaving L1 room for the scenario tables and the hot state lines; then the FEWEST warps that
+  // still need the same number of rounds over the tiles (each warp takes whole tiles: with 4096 tiles, 11 to 13 warps per SM
+  // all need three rounds and the extra warps only add contention, 14 need two)
+  int nw = (int)((212 * 1024 / 4 - o) / q);
   if (nw > CBX_WIDE_WARPS) nw = CBX_WIDE_WARPS;
   if (nw < 4) return false;
+  if (sms > 0 && p.n_tiles > 0) {
+    const int64_t rounds = (p.n_tiles + (int64_t)sms * nw - 1) / ((int64_t)sms * nw);
+    while (nw > 4 && (p.n_tiles + (int64_t)sms * (nw - 1) - 1) / ((int64_t)sms * (nw - 1)) == rounds) --nw;
+  }
   Q->nwarps = nw;
   o += nw * q;
   Q->total_bytes = (int)(o * 4);
@@ -287,7 +293,8 @@ static int compute_layout(const cbx_scenario* s, const cbx_config* cfg, int64_t 
   L->o_cache = o; o += (L->ntriples + 1 + 1) / 2;
   L->S = o;
   int g = 11 + L->Wn;
-  L->g_leaked = g; g += 4 * L->LEAK;
+  L->LEAKS = s->max_leak < L->LEAK ? s->max_leak : L->LEAK;
+  L->g_leaked = g; g += 4 * L->LEAKS;
   L->g_inst = g; g += L->Wn;
   L->g_priv = g; g += (L->n + 15) / 16;
   L->G = g;
@@ -501,7 +508,7 @@ static int create_impl(const cbx_scenario* const* scns, int n_scn, const int64_t
     const char* we = getenv("CBX_WIDE");
     const bool want = we ? we[0] == '1' : (b->p.lay.S >= 128 || n_scn > 1);
     cbx_wide_plan Q;
-    if (want && plan_wide(b->p, &Q) && cbx_wide_attrs(Q.total_bytes) == cudaSuccess) {
+    if (want && plan_wide(b->p, sms, &Q) && cbx_wide_attrs(Q.total_bytes) == cudaSuccess) {
       Q.enabled = 1;
       b->p.wide = Q;
       const int need = (b->p.n_tiles + Q.nwarps - 1) / Q.nwarps;

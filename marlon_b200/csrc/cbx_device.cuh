@@ -202,7 +202,7 @@ struct Ctx {
           int c = nc();
           sethalf(L->o_cache, c, (uint32_t)t);
           w(L->o_hdr) = (w(L->o_hdr) & ~0xFFFF00u) | ((uint32_t)(c + 1) << 8);
-          if (slot < L->LEAK) {     // ENV:890-907 (target index is final: a node keeps its discovery index)
+          if (slot < L->LEAKS) {    // ENV:890-907; a list never has more than LEAKS entries (target index is final: a node keeps its discovery index)
             g(L->g_leaked + 4 * slot + 0) = 1;
             g(L->g_leaked + 4 * slot + 1) = (uint32_t)c;
             g(L->g_leaked + 4 * slot + 2) = byte(L->o_disc_idx, (int)tr[0]);
@@ -353,7 +353,7 @@ struct Ctx {
   __device__ void stage_reset_obs() const {  // blank observation + masks/properties of the fresh state (ENV:1197-1200)
     for (int k = 0; k < 8; ++k) g(STG_SCALARS + k) = 0;
     g(STG_SCALARS + 6) = (uint32_t)nd();
-    for (int k = 0; k < 4 * L->LEAK; ++k) g(L->g_leaked + k) = 0;
+    for (int k = 0; k < 4 * L->LEAKS; ++k) g(L->g_leaked + k) = 0;
     g(STG_OBS_KIND) = OBS_NORMAL;
     snapshot_for_obs();
   }
@@ -388,7 +388,7 @@ struct Ctx {
     if (flag(HDR_DONE)) { so.error = CBX_E_STEP_AFTER_DONE; so.terminated = 1; g(STG_OBS_KIND) = OBS_KEEP; return so; }
     w(L->o_stepcount) += 1;
     for (int k = 0; k < 8; ++k) g(STG_SCALARS + k) = 0;
-    for (int k = 0; k < 4 * L->LEAK; ++k) g(L->g_leaked + k) = 0;
+    for (int k = 0; k < 4 * L->LEAKS; ++k) g(L->g_leaked + k) = 0;
     Result r;
     if (execute_action(kind, a, &r)) {  // blank observation, reward 0, the built-in defender does not move
       g(STG_SCALARS + 6) = (uint32_t)nd();

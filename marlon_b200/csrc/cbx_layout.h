@@ -33,6 +33,8 @@
 struct cbx_layout {
   // dimensions
   int n, N, C, LEAK, P, L, R, nprops, nsecrets, ntriples, nservices;
+  int LEAKS;   // leaked-credential slots actually staged: min(LEAK, longest LeakedCredentials list of the scenario); the rest of
+               // the LEAK slots of an observation are always zero
   int Wn;      // words of a node bitset
   int PW;      // words of a property bitset (1 or 2)
   int AW;      // words of the attacked bits of one node: 2 bits per vulnerability
@@ -66,7 +68,7 @@ struct cbx_layout {
   int S;              // words per env
   // per-env staging words written by the game-logic thread for the encoder (word-major like the state tile):
   //   [0,8) scalars | 8 obs kind | 9 attacker done | 10 defender done | [11, 11+Wn) installed bits at defender done
-  int g_leaked;       // 4*LEAK leaked-credential slots
+  int g_leaked;       // 4*LEAKS leaked-credential slots
   int g_inst;         // Wn: agent_installed bits as the observation sees them (before the built-in defender moves)
   int g_priv;         // ceil(n/16): privilege levels as the observation sees them
   int G;              // staging words per env
@@ -120,7 +122,7 @@ enum { CBX_SH_ENC_MASK = 0, CBX_SH_TILE = 1 };
 
 // Warp-per-tile kernel for large per-env state (cbx_wide.cuh): nothing big is staged; per warp a private area holds the
 // staging words, the encoder descriptors, the tile's actions, the 32 x 33 transpose square and the defender's static rows.
-#define CBX_WIDE_WARPS 12  // most warps per CTA (the kernel is compiled for 384 threads, one CTA per SM)
+#define CBX_WIDE_WARPS 14  // most warps per CTA (the kernel is compiled for 448 threads, one CTA per SM)
 struct cbx_wide_plan {
   int enabled;
   int nwarps;                                      // warps per CTA: as many as fit (<= CBX_WIDE_WARPS)

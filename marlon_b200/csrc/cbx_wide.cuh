@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(CBX_WIDE_WARPS * 32, 1) cbx_wide_kernel(const 
       for (int k = 0; k < 8; ++k) fw.put(mine ? c.g(STG_SCALARS + k) : 0u);
       fw.finish();
       begin(tm.leaked, 4 * L.LEAK);
-      for (int k = 0; k < 4 * L.LEAK; ++k) fw.put(mine ? c.g(L.g_leaked + k) : 0u);
+      for (int k = 0; k < 4 * L.LEAK; ++k) fw.put((mine && k < 4 * L.LEAKS) ? c.g(L.g_leaked + k) : 0u);
       fw.finish();
       begin(tm.cachem, 2 * L.C);  // credential_cache_matrix [C][2]: (target discovery index, port) per cached credential
       for (int i = 0; i < L.C; ++i) {
