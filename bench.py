@@ -222,6 +222,16 @@ def _cpu_worker(args):
     return steps * n_envs, spent
 
 
+def _cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.lower().startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def cpu_baseline(seconds=12.0, n_envs=256, cores=None):
     """Oracle (C port of the reference step) on every host core at once; only the step call is timed."""
     import multiprocessing as mp
@@ -234,7 +244,7 @@ def cpu_baseline(seconds=12.0, n_envs=256, cores=None):
     with mp.get_context("fork").Pool(cores) as pool:
         res = pool.map(_cpu_worker, [(1000 + i, n_envs, seconds) for i in range(cores)])
     value = sum(s / t for s, t in res if t > 0)
-    return {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
+    return {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "cpu_model": _cpu_model(), "per_core": value / cores,
             "sample": f"{cores} processes x {n_envs} envs, ToyCtf(12,10) MARLon attacker+defender pair step, random valid actions, "
                       f"{seconds:.0f} s wall each, only oracle step() timed ({sum(s for s, _ in res)} env-steps)"}
 

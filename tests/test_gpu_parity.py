@@ -127,6 +127,17 @@ def test_toyctf_marlon_pair_vs_oracle():
     _run_against_oracle(comp, cfg, 4099, 300, seed=17)  # 4099: a ragged last tile
 
 
+def test_toyctf_marlon_pair_full_bench_size_vs_oracle():
+    """configs[2] at its full size: 65 536 envs on one GPU (what bench.py times), every array of every env against the oracle."""
+    comp = scenario.compile_scenario(scenarios.toyctf_environment())
+    cfg = config.make_config(_abi.MODE_MARLON, maximum_node_count=12, maximum_total_credentials=10,
+                             maximum_discoverable_credentials_per_action=5, throws_on_invalid_actions=False,
+                             attacker_goal=config.AttackerGoal(own_atleast=6), defender_constraint=config.DefenderConstraint(0.60),
+                             losing_reward=-5000.0, defender_enabled=True, defender_max_timesteps=2000,
+                             defender_invalid_action_reward=-1, attacker_max_timesteps=2000)
+    _run_against_oracle(comp, cfg, 65536, 24, seed=23, check_every=12)
+
+
 def test_chain100_factored_masks_vs_oracle():
     """configs[3] shape: Chain-100 (102,102) attacker+defender, factored masks (dense would be 8.5 MB/env)."""
     comp = scenario.compile_scenario(scenarios.chain_environment(100))
