@@ -82,7 +82,7 @@ bool plan_pipe(const cbx_params& p, int wl, int we, cbx_pipe_plan* Q) {
   auto up = [](int64_t x, int a) { return (x + a - 1) / a * a; };
   Q->tables = (int)o; o = up(o + p.table_words + ((L.S + 3) & ~3), 32);
   Q->lut = (int)o; o += 512;
-  Q->bars = (int)o; o = up(o + 2 * (1 + wl + 2 * Q->nslot), 32);
+  Q->bars = (int)o; o = up(o + 2 * (1 + wl + 3 * Q->nslot), 32);
   Q->zero = (int)o; o = up(o + (dense ? gs * ROWC / 4 : 0), 32);
   Q->def_static = (int)o; o = up(o + (defobs ? CBX_TILE * (12 * L.n + L.nservices) / 4 : 0), 32);
   // logic buffers: state tile | staging | field images [32][words per env] | actions (aliasing the property image when it

@@ -238,6 +238,7 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
   uint64_t* bar_load = bars + 1;             // [wl]    state-tile loads, one per logic warp
   uint64_t* bar_ready = bar_load + Q.wl;     // [nslot] logic -> encoders
   uint64_t* bar_empty = bar_ready + Q.nslot; // [nslot] encoders -> logic
+  uint64_t* bar_rdef = bar_empty + Q.nslot;  // [nslot] logic -> the encoder of the tile's defender observation
   uint8_t* s_zero = reinterpret_cast<uint8_t*>(smem + Q.zero);
   uint8_t* s_defst = reinterpret_cast<uint8_t*>(smem + Q.def_static);
   const uint32_t* s_init = s_tb + p.table_words;
@@ -255,7 +256,7 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     for (int w = 0; w < Q.wl; ++w) mbar_init(&bar_load[w], 1);
-    for (int s = 0; s < Q.nslot; ++s) { mbar_init(&bar_ready[s], 1); mbar_init(&bar_empty[s], Q.we); }
+    for (int s = 0; s < Q.nslot; ++s) { mbar_init(&bar_ready[s], 1); mbar_init(&bar_empty[s], Q.we); mbar_init(&bar_rdef[s], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -387,22 +388,43 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
         }
         __syncwarp();
       }
-      uint32_t def_done = 0;
+      // ---- phase 2a: the attacker's auto-reset and the encoder descriptors.  The action masks depend on nothing the defender
+      //      does (it acts on its stale copy), so the encoder warps are released BEFORE the defender moves.
       keep = 1;
       if (active) {
-        def_done = logic_phase2(c, p, op, act + CBX_TILE * 10 + lane * 12, s_init, desc + lane * DW, acc);
+        if (!reset_only && c.g(STG_ATT_DONE) && cfg.auto_reset) {
+          if (marlon) c.attacker_reset(s_init);
+          else { c.cyber_reset(s_init); c.setf32(L.o_att_return, 0.f); }
+          c.stage_reset_obs();
+        }
         keep = c.g(STG_OBS_KIND) == OBS_KEEP;
-        if (def_done && cfg.emit_terminal_obs && p.v.term_def_infected_nodes) {
-          // terminal defender observation = infected nodes seen by the step that ended the episode
-          int8_t* ti = p.v.term_def_infected_nodes + c.env * L.n;
-          for (int i = 0; i < L.n; ++i) ti[i] = (int8_t)((c.g(STG_DEF_TERM_INST + (i >> 5)) >> (i & 31)) & 1u);
+        build_desc(c, desc + lane * DW, DW, nullptr);
+        if (!keep) {
+          uint32_t* ob = p.v.owned_bits + c.env * L.OW;
+          for (int k = 0; k < L.OW; ++k) ob[k] = desc[lane * DW + D_OWNED + k];
         }
       }
       const uint32_t enc_mask = ~__ballot_sync(0xFFFFFFFFu, keep != 0);
-      // descriptors are complete: the encoder warps can start on the tile's action masks while this warp lays out the rest
       if (lane == 0) { hdr[CBX_SH_ENC_MASK] = enc_mask; hdr[CBX_SH_TILE] = (uint32_t)tile; }
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_ready[slot]);
+      // ---- phase 2b: the defender's move; its observation of the tile is released separately ----
+      uint32_t def_done = 0;
+      if (active) {
+        if (!reset_only && def_on) defender_wrapper_step(c, p, act + CBX_TILE * 10 + lane * 12, acc);
+        def_done = c.g(STG_DEF_DONE) && cfg.auto_reset;
+        if (def_done) {
+          // main defender observation after an auto-reset shows the fresh environment (DWR:477)
+          for (int k = 0; k < L.Wn; ++k) desc[lane * DW + D_OWNED + L.OW + k] = s_init[L.o_installed + k];
+          if (cfg.emit_terminal_obs && p.v.term_def_infected_nodes) {
+            // terminal defender observation = infected nodes seen by the step that ended the episode
+            int8_t* ti = p.v.term_def_infected_nodes + c.env * L.n;
+            for (int i = 0; i < L.n; ++i) ti[i] = (int8_t)((c.g(STG_DEF_TERM_INST + (i >> 5)) >> (i & 31)) & 1u);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_rdef[slot]);
       CBX_PPROF(10)
       // ---- the small observation fields of the tile: one thread per env, env-major images, one bulk copy per field ----
       if (active && !keep) build_field_images<D>(c, desc + lane * DW, im, lane, dense);
@@ -477,17 +499,18 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
       const int tile = (int)blockIdx.x + j * (int)gridDim.x;
       const int64_t e0 = (int64_t)tile * CBX_TILE;
       const int n_valid = (int)min((int64_t)CBX_TILE, p.n_envs - e0);
-      if (def_encode && wid == j % Q.we) {
-        Tile t;
-        t.L = &L; t.tb = s_tb; t.st = nullptr; t.sg = nullptr; t.desc = desc; t.lut = s_lut; t.K = &p.enc; t.DW = DW;
-        const Target tm = make_target(p.v, L, e0, false);
-        encode_defender_tile<D>(t, tm, n_valid, wb, Q, s_defst, lane);
-      }
       if (dense) {
         for (int e = wid; e < n_valid; e += Q.we)
           if ((enc_mask >> e) & 1u)
             encode_masks_pipe<D>(desc + e * DW, s_lut, &L, p.enc, p.v.remote_vulnerability + (e0 + e) * L.sz_remote,
                                  p.v.connect + (e0 + e) * (int64_t)L.sz_connect, wb, Q, s_zero, lane, p.prof != nullptr, pacc);
+      }
+      if (def_encode && wid == j % Q.we) {  // the defender has moved by now (it is released after the action masks)
+        mbar_wait(&bar_rdef[slot], (uint32_t)use & 1u);
+        Tile t;
+        t.L = &L; t.tb = s_tb; t.st = nullptr; t.sg = nullptr; t.desc = desc; t.lut = s_lut; t.K = &p.enc; t.DW = DW;
+        const Target tm = make_target(p.v, L, e0, false);
+        encode_defender_tile<D>(t, tm, n_valid, wb, Q, s_defst, lane);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_empty[slot]);
