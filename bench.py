@@ -410,8 +410,8 @@ def run_ours(args):
                     "d2h_bytes_per_step": n * 12,
                     "note": "cbx_batch_step_host per step with HOST action buffers in page-locked memory: the step kernel reads each "
                             "tile's actions over PCIe in place (TMA bulk loads from the mapped host buffers; h2d_bytes_per_step is what "
-                            "crosses the link), then D2H of rewards + done flags as one block, stream sync, results copied out of the "
-                            "reused pinned buffer; observations stay in HBM as torch tensors (consumers are GPU policies)"},
+                            "crosses the link), then D2H of rewards + done flags as one block into a rotating page-locked result buffer, "
+                            "stream sync; observations stay in HBM as torch tensors (consumers are GPU policies)"},
             "gpu_launches": launches,
             "clocks": clk,
             "episode_stats": {k: float(v) for k, v in zip(_abi.STAT_NAMES, stats.cpu().numpy())},

@@ -152,17 +152,21 @@ class Batch:
         self._keep = [a, d, su, du]  # keep inputs alive until the next call (stream-ordered use)
 
     def step_host(self, attacker_actions: np.ndarray, defender_actions: Optional[np.ndarray] = None):
-        """The same step through HOST buffers (pinned staging + H2D of actions, D2H of rewards/flags); synchronous."""
+        """The same step through HOST buffers; synchronous.  Page-locked action arrays (``torch.empty(..., pin_memory=True)``)
+        are read by the kernel in place over PCIe; pageable ones go through the library's pinned staging.  The rewards and
+        done flags land in one of three page-locked result buffers used in rotation: the returned arrays are views of it and
+        stay valid until the third call after this one (copy them to keep them longer)."""
         a = np.ascontiguousarray(attacker_actions, dtype=np.int32)
         d = None if defender_actions is None else np.ascontiguousarray(defender_actions, dtype=np.int32)
         n = self.n_envs
-        if getattr(self, "_host_out", None) is None:  # page-locked result buffer, reused: D2H lands in it directly
-            self._host_out = self._torch.empty(n * 12, dtype=self._torch.uint8, pin_memory=True).numpy()
-        out = self._host_out
+        if getattr(self, "_host_out", None) is None:
+            self._host_out = [self._torch.empty(n * 12, dtype=self._torch.uint8, pin_memory=True).numpy() for _ in range(3)]
+            self._host_turn = 0
+        out = self._host_out[self._host_turn]
+        self._host_turn = (self._host_turn + 1) % 3
         with self._torch.cuda.device(self.device):
             _lib.check(self._L.cbx_batch_step_host(self._h, a.ctypes.data, None if d is None else d.ctypes.data,
                                                    out.ctypes.data, out.nbytes, self._stream()))
-        out = out.copy()
         return {
             "att_reward": out[: 4 * n].view(np.float32), "def_reward": out[4 * n: 8 * n].view(np.float32),
             "att_terminated": out[8 * n: 9 * n], "att_truncated": out[9 * n: 10 * n],

@@ -138,6 +138,16 @@ def test_toyctf_marlon_pair_full_bench_size_vs_oracle():
     _run_against_oracle(comp, cfg, 65536, 24, seed=23, check_every=12)
 
 
+def test_toyctf_factored_masks_vs_oracle():
+    """ToyCtf with factored masks: the pipelined kernel without any dense-mask work (encoder warps only emit the defender tile)."""
+    comp = scenario.compile_scenario(scenarios.toyctf_environment())
+    cfg = config.make_config(_abi.MODE_MARLON, maximum_node_count=12, maximum_total_credentials=10,
+                             throws_on_invalid_actions=False, defender_constraint=config.DefenderConstraint(0.60),
+                             losing_reward=-5000.0, defender_enabled=True, defender_max_timesteps=60,
+                             attacker_max_timesteps=60, mask_mode=_abi.MASK_FACTORED, emit_terminal_obs=True)
+    _run_against_oracle(comp, cfg, 1000, 150, seed=29)
+
+
 def test_chain100_factored_masks_vs_oracle():
     """configs[3] shape: Chain-100 (102,102) attacker+defender, factored masks (dense would be 8.5 MB/env)."""
     comp = scenario.compile_scenario(scenarios.chain_environment(100))
