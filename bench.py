@@ -33,6 +33,9 @@ WORKLOADS = {
               "reference_stale defender, SB3 auto-reset)",
     "chain100": "CyberBattleChain-v0 size=100 (N=102,C=102) MARLon attacker+defender pair step (config 4: the 1M-env sharded case; "
                 "factored masks -- a dense connect mask would be 8.5 MB per env)",
+    "toyctf_scan": "CyberBattleToyCtf-v0 (N=12,C=10) CyberBattleEnv step with the built-in ScanAndReimageCompromisedMachines(0.6, 2, 5) "
+                   "defender (configs[2] to the letter: notebook_withdefender.py:57-63 parameters, SLA 0.80, Philox detection draws, "
+                   "auto-reset as under the SB3 VecEnv adapter)",
     "random16": "CyberBattleRandom-v0, 16 generated 65-node networks (seeds 0-15) side by side in one batch (config 5: padded layout, "
                 "N=72, C=192, 32 leak slots), MARLon attacker+defender pair step",
 }
@@ -41,6 +44,14 @@ WORKLOADS = {
 def workload_config(mask_mode=0, workload="toyctf"):
     from marlon_b200 import _abi, config, scenario, scenarios
 
+    if workload == "toyctf_scan":
+        comp = scenario.compile_scenario(scenarios.toyctf_environment())
+        cfg = config.make_config(
+            _abi.MODE_CYBERBATTLE, maximum_node_count=12, maximum_total_credentials=10, maximum_discoverable_credentials_per_action=5,
+            throws_on_invalid_actions=False, attacker_goal=config.AttackerGoal(own_atleast=6),
+            defender_agent=config.ScanAndReimageCompromisedMachines(0.6, 2, 5), defender_constraint=config.DefenderConstraint(0.80),
+            auto_reset=True, mask_mode=mask_mode, seed=2026)
+        return comp, cfg
     if workload == "random16":
         from marlon_b200 import random_network
 
@@ -85,7 +96,7 @@ def algorithmic_bytes_per_env_step(comp, cfg, S_words):
     masks = (N * L + N * N * R + N * N * P * C) if cfg.mask_mode == 0 else 4 * ((N + 31) // 32)
     defender = (n + 12 * n + comp.n_services) if cfg.def_enabled else 0
     state = 2 * 4 * S_words
-    io = 40 + (48 if cfg.def_enabled else 0) + 4 + 4 + 4
+    io = (40 if cfg.mode == 1 else 20) + (48 if cfg.def_enabled else 0) + 4 + 4 + 4  # actions (MARLon 10 / CyberBattleEnv 5 words), rewards, flags
     return dict(attacker_obs=att_small, masks=masks, defender_obs=defender, state_rw=state, actions_rewards_flags=io,
                 total=att_small + masks + defender + state + io)
 
@@ -298,10 +309,12 @@ def run_ours(args):
         n = sum(counts)
     rec = Batch(comp, cfg, counts, device=local)
     rec.reset()
-    tape_a = torch.empty((W + K, n, 10), dtype=torch.int32, device=dev)
-    tape_d = torch.empty((W + K, n, 12), dtype=torch.int32, device=dev)
+    aw = rec.att_width  # 10: MARLon MultiDiscrete attacker action; 5: CyberBattleEnv [kind, 4 coordinates]
+    has_def = bool(cfg.mode == _abi.MODE_MARLON and cfg.def_enabled)
+    tape_a = torch.empty((W + K, n, aw), dtype=torch.int32, device=dev)
+    tape_d = torch.empty((W + K, n, 12), dtype=torch.int32, device=dev) if has_def else [None] * (W + K)
     for s in range(W + K):
-        rec.sample_actions(seed=args.seed + rank, attacker_out=tape_a[s], defender_out=tape_d[s])
+        rec.sample_actions(seed=args.seed + rank, attacker_out=tape_a[s], defender_out=tape_d[s] if has_def else None)
         rec.step(tape_a[s], tape_d[s])
     torch.cuda.synchronize()
     S_words = None
@@ -351,9 +364,9 @@ def run_ours(args):
     # ---- e2e: the same step through the public API with HOST action buffers and host-side results ----
     # host action buffers in page-locked memory (what a host-side policy loop would hand over)
     CH = min(K, 64)  # the tape reaches the host in chunks (bounded page-locked memory); only the step_host calls are timed
-    h_a = torch.empty((CH, n, 10), dtype=torch.int32, pin_memory=True)
-    h_d = torch.empty((CH, n, 12), dtype=torch.int32, pin_memory=True)
-    h_an, h_dn = h_a.numpy(), h_d.numpy()
+    h_a = torch.empty((CH, n, aw), dtype=torch.int32, pin_memory=True)
+    h_d = torch.empty((CH, n, 12), dtype=torch.int32, pin_memory=True) if has_def else None
+    h_an, h_dn = h_a.numpy(), (h_d.numpy() if has_def else [None] * CH)
     b2 = Batch(comp, cfg, counts, device=local)
     b2.reset()
     for s in range(W):
@@ -364,7 +377,9 @@ def run_ours(args):
     e2e_s = 0.0
     for c0 in range(0, K, CH):
         c1 = min(K, c0 + CH)
-        h_a[: c1 - c0].copy_(tape_a[W + c0:W + c1]); h_d[: c1 - c0].copy_(tape_d[W + c0:W + c1])
+        h_a[: c1 - c0].copy_(tape_a[W + c0:W + c1])
+        if has_def:
+            h_d[: c1 - c0].copy_(tape_d[W + c0:W + c1])
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for s in range(c1 - c0):
@@ -406,7 +421,7 @@ def run_ours(args):
                          "traffic": ncu_traffic(kinfo["name"], n, factored) if args.workload == "toyctf" else None,
                          "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
                          "kernel": kinfo["name"], "kernel_launch": kinfo, "kernel_ms": kernel_ms, "kernel_launches_timed": kernel_n},
-            "e2e": {"value": total_envs * K / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": n * (10 + 12) * 4,
+            "e2e": {"value": total_envs * K / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": n * (aw + (12 if has_def else 0)) * 4,
                     "d2h_bytes_per_step": n * 12,
                     "note": "cbx_batch_step_host per step with HOST action buffers in page-locked memory: the step kernel reads each "
                             "tile's actions over PCIe in place (TMA bulk loads from the mapped host buffers; h2d_bytes_per_step is what "
