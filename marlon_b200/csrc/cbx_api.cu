@@ -452,13 +452,10 @@ static int create_impl(const cbx_scenario* const* scns, int n_scn, const int64_t
   pl.tables = o; o = align_up(o + b->p.table_words + ((L.S + 3) & ~3), 32);
   pl.lut = o; o = align_up(o + 512, 32);
   pl.bars = o; o = align_up(o + 8, 32);
-  // one buffer set = {state tile, staging, descriptors, actions}; the pipelined loop uses two of them
-  const int set0 = o;
   pl.state = o; o = align_up(o + L.S * CBX_TILE, 32);
   pl.stage = o; o = align_up(o + L.G * CBX_TILE, 32);
   pl.desc = o; o = align_up(o + K.desc_words * CBX_TILE, 32);
   pl.acts = o; o = align_up(o + 22 * CBX_TILE, 32);
-  pl.buf_stride = o - set0;
   pl.total_bytes = o * 4;
   b->smem_bytes = pl.total_bytes;
   if (b->smem_bytes > 227 * 1024) {

@@ -1,13 +1,19 @@
-// cbx_kernels.cu -- fused env-step kernel (game logic + observation / action-mask encoder) for sm_100a.
+// cbx_kernels.cu -- the step kernels for sm_100a and what they share.
 //
-// One persistent CTA per resident slot loops over tiles of 32 envs:
+// This file: the encoder building blocks, the MARLon wrapper steps, the two game-logic phases of one env (logic_phase1 / 2,
+// over the rules in cbx_device.cuh), the FUSED step kernel (general path: any bounds, dense masks of any size), the
+// on-device valid-action sampler, the GAE kernel and the launch helpers.  Included below:
+//   cbx_pipe.cuh -- pipelined, warp-specialised kernel (small state, dense masks: the bench workload): logic warps ahead of
+//                   encoder warps that hand mask rows to the TMA engine;
+//   cbx_wide.cuh -- warp-per-tile kernel for large per-env state with factored masks (Chain-100, generated networks).
+// All three produce identical bytes; cbx_batch_create (cbx_api.cu) picks one per batch.
+//
+// Fused kernel: one persistent CTA per resident slot loops over tiles of 32 envs:
 //   (0) TMA bulk copies stage the scenario tables (once per CTA) and the tile's S x 32 state words into shared memory;
 //   (1) warp 0 plays the step, one thread per env, on the shared-memory tile (cbx_device.cuh);
-//   (2) all 128 threads encode the tile's observations and action masks straight into the output tensors with
-//       16-byte streaming stores -- the dense masks are >90 % of the bytes of a step, so this is the part that runs
-//       against the HBM roofline;
-//   (3) the state tile is streamed back with TMA bulk stores.
-// Algorithmic bytes per env-step and the roofline are stated in DESIGN.md.
+//   (2) all 128 threads encode the tile's observations and action masks straight into the output tensors;
+//   (3) the state tile is streamed back with a TMA bulk store.
+// Algorithmic bytes per env-step and the rooflines are stated in DESIGN.md.
 #include <cuda_runtime.h>
 #include <stdint.h>
 

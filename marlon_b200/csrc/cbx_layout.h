@@ -93,7 +93,6 @@ struct cbx_enc_consts {  // divisors of the encoder, fixed per batch
 
 struct cbx_smem_plan {  // shared-memory carve-up in 32-bit words
   int tables, state, stage, desc, acts, lut, bars, total_bytes;
-  int buf_stride;  // words between the two buffer sets {state, stage, desc, acts} of the pipelined tile loop
 };
 
 // Pipelined step kernel (cbx_pipe.cuh): per CTA `wl` game-logic warps (one thread per env; they also lay out the small
@@ -121,7 +120,7 @@ struct cbx_pipe_plan {
 enum { CBX_SH_ENC_MASK = 0, CBX_SH_TILE = 1 };
 
 // Warp-per-tile kernel for large per-env state (cbx_wide.cuh): nothing big is staged; per warp a private area holds the
-// staging words, the encoder descriptors, the tile's actions, the 32 x 33 transpose square and the defender's static rows.
+// staging words, the encoder descriptors, the tile's actions, the 32 x 36 transpose square and the defender's static rows.
 #define CBX_WIDE_WARPS 14  // most warps per CTA (the kernel is compiled for 448 threads, one CTA per SM)
 struct cbx_wide_plan {
   int enabled;

@@ -9,10 +9,10 @@
 //     of a tile is one 128-byte line (tiled structure of arrays), so every access of a warp is one coalesced transaction;
 //   * the scenario tables are read through L1 from global memory (30 KB at Chain-100, hot), which also makes a batch over
 //     several scenarios (cbx_batch_create_multi) free: a tile just points at its scenario's tables;
-//   * each warp owns a tile end to end -- no CTA-wide barrier in the loop, 12 tiles in flight per SM instead of 2;
-//   * the int32 observation fields are produced by the env's own thread, 32 words at a time, into a padded 32 x 33 shared-
-//     memory square and leave transposed: one fully coalesced 128-byte store per env and chunk (0.1 instructions per word
-//     where the element-wise encoder needed ~20).
+//   * each warp owns a tile end to end -- no CTA-wide barrier in the loop, up to 14 tiles in flight per SM instead of 2;
+//   * the int32 observation fields are produced by the env's own thread, 32 words at a time, into a padded 32 x 36 shared-
+//     memory square and leave transposed with 16-byte stores (4 envs x 128 contiguous bytes per instruction); the property
+//     matrix is a bit stream expanded four words at a time through a 16-entry uint4 table.
 // Factored masks only (what these configurations use: a dense Chain-100 connect mask is 8.5 MB per env).
 namespace cbx {
 
