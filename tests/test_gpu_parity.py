@@ -285,3 +285,29 @@ def test_random_networks_multi_scenario_batch_vs_oracle(mask_mode):
     want_stats = sum(o.stats for o in oracles)
     assert np.allclose(b.stats(), want_stats, rtol=1e-9, atol=1e-6)
     b.close()
+
+
+def test_full_size_runs_are_reproducible():
+    """Two independent batches at the bench size fed the same actions for 120 steps end in identical states, statistics and
+    observations (a data race between the logic and encoder warps of the pipelined kernel would show up here)."""
+    import torch
+
+    comp = scenario.compile_scenario(scenarios.toyctf_environment())
+    cfg = config.make_config(_abi.MODE_MARLON, maximum_node_count=12, maximum_total_credentials=10,
+                             maximum_discoverable_credentials_per_action=5, throws_on_invalid_actions=False,
+                             attacker_goal=config.AttackerGoal(own_atleast=6), defender_constraint=config.DefenderConstraint(0.60),
+                             losing_reward=-5000.0, defender_enabled=True, defender_max_timesteps=2000,
+                             defender_invalid_action_reward=-1, attacker_max_timesteps=2000)
+    n = 65536
+    a, b = _batch(comp, cfg, n), _batch(comp, cfg, n)
+    a.reset(); b.reset()
+    for s in range(120):
+        att, dfn = a.sample_actions(seed=31)
+        a.step(att, dfn)
+        b.step(att, dfn)
+        if s % 40 == 39:
+            for k in a.tensors:
+                assert torch.equal(a.tensors[k], b.tensors[k]), (s, k)
+    assert np.array_equal(a.export_state(), b.export_state())
+    assert np.array_equal(a.stats(), b.stats()) and a.stats()[_abi.STAT_ENV_STEPS] == n * 120
+    a.close(); b.close()
