@@ -353,6 +353,13 @@ int cbx_batch_notify_reset(cbx_batch* b, const uint8_t* mask_or_null, int who, d
 int cbx_batch_step_host(cbx_batch* b, const int32_t* host_attacker_actions, const int32_t* host_defender_actions,
                         void* host_out, size_t host_out_bytes, void* cuda_stream);
 
+/* The same two calls with int16 action elements (every component of both MultiDiscrete spaces is far below 32768):
+ * half the bytes over PCIe, which is what bounds cbx_batch_step_host.  The reference hands int64 numpy arrays from the
+ * policy to env.step (baseline_marlon_agent.py:118-131), so an adapter narrows them either way. */
+int cbx_batch_step_i16(cbx_batch* b, const int16_t* attacker_actions, const int16_t* defender_actions, void* cuda_stream);
+int cbx_batch_step_host_i16(cbx_batch* b, const int16_t* host_attacker_actions, const int16_t* host_defender_actions,
+                            void* host_out, size_t host_out_bytes, void* cuda_stream);
+
 /* Fill device action buffers with uniformly sampled VALID actions for the current state (benchmark load;
  * cyberbattle_env.py:1041-1047 semantics: resample until the mask admits the action), Philox keyed by (seed, env, step). */
 int cbx_batch_sample_actions(cbx_batch* b, int32_t* attacker_actions, int32_t* defender_actions, uint64_t seed,

@@ -15,7 +15,7 @@ _LIB = None
 # every symbol declared in include/cbx.h
 SYMBOLS = [
     "cbx_last_error", "cbx_abi_version", "cbx_scenario_create", "cbx_scenario_destroy", "cbx_config_default",
-    "cbx_batch_create", "cbx_batch_destroy", "cbx_batch_reset", "cbx_batch_step", "cbx_batch_step_host",
+    "cbx_batch_create", "cbx_batch_destroy", "cbx_batch_reset", "cbx_batch_step", "cbx_batch_step_host", "cbx_batch_step_i16", "cbx_batch_step_host_i16",
     "cbx_batch_sample_actions", "cbx_batch_views", "cbx_batch_stats_reset", "cbx_export_words",
     "cbx_batch_export_state", "cbx_batch_launch_count", "cbx_batch_enable_timing", "cbx_batch_step_kernel_ms",
     "cbx_abi_sizeof", "cbx_batch_step_ex", "cbx_batch_reset_ex", "cbx_batch_phase_cycles", "cbx_batch_notify_reset", "cbx_batch_kernel_info", "cbx_batch_create_multi", "cbx_batch_export_words", "cbx_gae",
@@ -51,6 +51,8 @@ def load():
     L.cbx_batch_reset_ex.argtypes = [vp, vp, C.c_int, vp]
     L.cbx_batch_step_ex.argtypes = [vp, i32p, i32p, C.POINTER(_abi.Tape), C.c_int, vp]
     L.cbx_batch_step_host.argtypes = [vp, i32p, i32p, vp, C.c_size_t, vp]
+    L.cbx_batch_step_i16.argtypes = [vp, vp, vp, vp]
+    L.cbx_batch_step_host_i16.argtypes = [vp, vp, vp, vp, C.c_size_t, vp]
     L.cbx_batch_sample_actions.argtypes = [vp, i32p, i32p, C.c_uint64, vp]
     L.cbx_batch_views.argtypes = [vp, C.POINTER(_abi.Views)]
     L.cbx_batch_stats_reset.argtypes = [vp, vp]

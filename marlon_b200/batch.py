@@ -137,6 +137,15 @@ class Batch:
         """One env-step for every env. Actions: int32 [n,10] (MARLon) or [n,5] (CyberBattleEnv), defender [n,12].
         `who`: both halves of the MARLon pair step (3), only the attacker's (1) or only the defender's (2)."""
         torch = self._torch
+        if (who == 3 and scan_u is None and torch.is_tensor(attacker_actions) and attacker_actions.dtype == torch.int16
+                and (defender_actions is None or (torch.is_tensor(defender_actions) and defender_actions.dtype == torch.int16))):
+            a = self._dev(attacker_actions, torch.int16, self.att_width)  # compact action elements
+            d = self._dev(defender_actions, torch.int16, 12) if defender_actions is not None else None
+            with torch.cuda.device(self.device):
+                _lib.check(self._L.cbx_batch_step_i16(self._h, C.c_void_p(a.data_ptr()),
+                                                      C.c_void_p(d.data_ptr()) if d is not None else None, self._stream()))
+            self._keep = [a, d]
+            return
         a = self._dev(attacker_actions, torch.int32, self.att_width) if attacker_actions is not None else None
         d = self._dev(defender_actions, torch.int32, 12) if defender_actions is not None else None
         tape = None
@@ -155,23 +164,28 @@ class Batch:
         """The same step through HOST buffers; synchronous.  Page-locked action arrays (``torch.empty(..., pin_memory=True)``)
         are read by the kernel in place over PCIe; pageable ones go through the library's pinned staging.  The rewards and
         done flags land in one of three page-locked result buffers used in rotation: the returned arrays are views of it and
-        stay valid until the third call after this one (copy them to keep them longer)."""
-        a = np.ascontiguousarray(attacker_actions, dtype=np.int32)
-        d = None if defender_actions is None else np.ascontiguousarray(defender_actions, dtype=np.int32)
+        stay valid until the third call after this one (copy them to keep them longer).  With both agents stepping and
+        page-locked actions the kernel writes the results into that buffer itself (no copy back).  int16 action arrays
+        are taken as they are (``cbx_batch_step_host_i16``: half the PCIe bytes); anything else is converted to int32."""
+        i16 = (getattr(attacker_actions, "dtype", None) == np.int16
+               and (defender_actions is None or getattr(defender_actions, "dtype", None) == np.int16))
+        dt = np.int16 if i16 else np.int32
+        a = np.ascontiguousarray(attacker_actions, dtype=dt)
+        d = None if defender_actions is None else np.ascontiguousarray(defender_actions, dtype=dt)
         n = self.n_envs
         if getattr(self, "_host_out", None) is None:
             self._host_out = [self._torch.empty(n * 12, dtype=self._torch.uint8, pin_memory=True).numpy() for _ in range(3)]
+            self._host_views = [{
+                "att_reward": o[: 4 * n].view(np.float32), "def_reward": o[4 * n: 8 * n].view(np.float32),
+                "att_terminated": o[8 * n: 9 * n], "att_truncated": o[9 * n: 10 * n],
+                "def_terminated": o[10 * n: 11 * n], "def_truncated": o[11 * n: 12 * n]} for o in self._host_out]
             self._host_turn = 0
-        out = self._host_out[self._host_turn]
+        out, views = self._host_out[self._host_turn], self._host_views[self._host_turn]
         self._host_turn = (self._host_turn + 1) % 3
         with self._torch.cuda.device(self.device):
-            _lib.check(self._L.cbx_batch_step_host(self._h, a.ctypes.data, None if d is None else d.ctypes.data,
-                                                   out.ctypes.data, out.nbytes, self._stream()))
-        return {
-            "att_reward": out[: 4 * n].view(np.float32), "def_reward": out[4 * n: 8 * n].view(np.float32),
-            "att_terminated": out[8 * n: 9 * n], "att_truncated": out[9 * n: 10 * n],
-            "def_terminated": out[10 * n: 11 * n], "def_truncated": out[11 * n: 12 * n],
-        }
+            fn = self._L.cbx_batch_step_host_i16 if i16 else self._L.cbx_batch_step_host
+            _lib.check(fn(self._h, a.ctypes.data, None if d is None else d.ctypes.data, out.ctypes.data, out.nbytes, self._stream()))
+        return dict(views)
 
     def sample_actions(self, seed: int = 0, attacker_out=None, defender_out=None):
         """Uniformly sampled VALID attacker actions (and uniform defender actions) for the current state, on device."""

@@ -489,6 +489,8 @@ static int create_impl(const cbx_scenario* const* scns, int n_scn, const int64_t
       if (ok && cbx_pipe_attrs(b->p.enc.warp_env, Q.total_bytes) == cudaSuccess) {
         Q.enabled = 1;
         { const char* lt = getenv("CBX_PIPE_LOGIC_TMA"); Q.logic_tma = !(lt && lt[0] == '0'); }
+        { const char* dy = getenv("CBX_PIPE_DYNAMIC"); Q.dynamic = dy ? atoi(dy) : 0; }
+        { const char* la = getenv("CBX_PIPE_LOOKAHEAD"); Q.lookahead = la ? atoi(la) : 0; }
         b->p.pipe = Q;
         int per_sm = ect ? atoi(ect) : 1;
         if (per_sm < 1) per_sm = 1;
@@ -559,6 +561,12 @@ static int create_impl(const cbx_scenario* const* scns, int n_scn, const int64_t
       b->d_tile_scn = (int32_t*)pts;
       b->p.tile_scn = b->d_tile_scn;
     }
+  }
+  if (b->p.pipe.enabled) {
+    void* pc = nullptr;
+    cudaError_t e = dalloc(&pc, 64);
+    if (e != cudaSuccess) { int rc2 = fail(CBX_ERR_CUDA, "cudaMalloc(tile counter): %s", cudaGetErrorString(e)); cbx_batch_destroy(b); return rc2; }
+    b->p.tile_counter = (int*)pc;
   }
   cbx_views& v = b->p.v;
   v.n_envs = n_envs; v.N = L.N; v.L = L.L; v.R = L.R; v.P = L.P; v.C = L.C; v.LEAK = L.LEAK; v.n_props = L.nprops;
@@ -687,6 +695,14 @@ int cbx_batch_step(cbx_batch* b, const int32_t* att, const int32_t* def, const c
   return cbx_batch_step_ex(b, att, def, tape, CBX_WHO_ATTACKER | CBX_WHO_DEFENDER, cuda_stream);
 }
 
+int cbx_batch_step_i16(cbx_batch* b, const int16_t* att, const int16_t* def, void* cuda_stream) {
+  if (!b) return fail(CBX_ERR_INVALID, "null batch");
+  b->p.act_i16 = 1;
+  const int rc = cbx_batch_step_ex(b, (const int32_t*)att, (const int32_t*)def, nullptr, CBX_WHO_ATTACKER | CBX_WHO_DEFENDER, cuda_stream);
+  b->p.act_i16 = 0;  // the launch took its copy of the parameters
+  return rc;
+}
+
 int cbx_batch_step_ex(cbx_batch* b, const int32_t* att, const int32_t* def, const cbx_tape* tape, int who, void* cuda_stream) {
   if (!b) return fail(CBX_ERR_INVALID, "null batch");
   const cbx_config& c = b->p.cfg;
@@ -705,7 +721,20 @@ int cbx_batch_step_ex(cbx_batch* b, const int32_t* att, const int32_t* def, cons
   return timed_launch(b, op, (cudaStream_t)cuda_stream);
 }
 
+static int step_host_impl(cbx_batch* b, const void* h_att, const void* h_def, size_t esz, void* host_out, size_t host_out_bytes,
+                          void* cuda_stream);
+
 int cbx_batch_step_host(cbx_batch* b, const int32_t* h_att, const int32_t* h_def, void* host_out, size_t host_out_bytes, void* cuda_stream) {
+  return step_host_impl(b, h_att, h_def, 4, host_out, host_out_bytes, cuda_stream);
+}
+
+int cbx_batch_step_host_i16(cbx_batch* b, const int16_t* h_att, const int16_t* h_def, void* host_out, size_t host_out_bytes,
+                            void* cuda_stream) {
+  return step_host_impl(b, h_att, h_def, 2, host_out, host_out_bytes, cuda_stream);
+}
+
+static int step_host_impl(cbx_batch* b, const void* h_att, const void* h_def, const size_t esz, void* host_out, size_t host_out_bytes,
+                          void* cuda_stream) {
   if (!b || !h_att || !host_out) return fail(CBX_ERR_INVALID, "null argument");
   const cbx_config& c = b->p.cfg;
   const int64_t n = b->p.n_envs;
@@ -724,42 +753,51 @@ int cbx_batch_step_host(cbx_batch* b, const int32_t* h_att, const int32_t* h_def
     CUDA_TRY(cudaMalloc((void**)&b->d_def, (size_t)n * 12 * 4));
   }
   // caller buffers that are already page-locked go to the device directly; pageable ones through the pinned staging
-  auto is_pinned = [](const void* ptr) {
+  // one query per buffer: page-locked or not, and the address the device sees it at
+  auto pinned_view = [](const void* ptr) -> void* {
     cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
-    return at.type == cudaMemoryTypeHost;
+    if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
   };
   // Page-locked action buffers are read by the step kernel IN PLACE over PCIe (pinned allocations are mapped into the device
   // address space under unified addressing): the transfer of a tile's actions overlaps the other tiles' work instead of
   // preceding the launch.  Pageable buffers go through the library's pinned staging first.  CBX_HOST_ZEROCOPY=0 restores
   // the explicit H2D copies.
   static const bool zero_copy = [] { const char* e = getenv("CBX_HOST_ZEROCOPY"); return !(e && e[0] == '0'); }();
-  auto device_view = [](const void* pinned) -> const int32_t* {
-    void* d = nullptr;
-    if (cudaHostGetDevicePointer(&d, const_cast<void*>(pinned), 0) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    return (const int32_t*)d;
-  };
-  const int32_t* src_att = h_att;
-  if (!is_pinned(h_att)) { memcpy(b->h_att, h_att, (size_t)n * aw * 4); src_att = b->h_att; }
-  const int32_t* src_def = nullptr;
+  const void* src_att = h_att;
+  const void* k_att = pinned_view(h_att);
+  if (!k_att) { memcpy(b->h_att, h_att, (size_t)n * aw * esz); src_att = b->h_att; k_att = pinned_view(b->h_att); }
+  const void *src_def = nullptr, *k_def = nullptr;
   if (need_def) {
     src_def = h_def;
-    if (!is_pinned(h_def)) { memcpy(b->h_def, h_def, (size_t)n * 12 * 4); src_def = b->h_def; }
+    k_def = pinned_view(h_def);
+    if (!k_def) { memcpy(b->h_def, h_def, (size_t)n * 12 * esz); src_def = b->h_def; k_def = pinned_view(b->h_def); }
   }
-  const int32_t* k_att = zero_copy ? device_view(src_att) : nullptr;
-  const int32_t* k_def = (zero_copy && need_def) ? device_view(src_def) : nullptr;
+  if (!zero_copy) k_att = k_def = nullptr;
   if (!k_att || (need_def && !k_def)) {  // explicit copies
-    CUDA_TRY(cudaMemcpyAsync(b->d_att, src_att, (size_t)n * aw * 4, cudaMemcpyHostToDevice, st));
-    if (need_def) CUDA_TRY(cudaMemcpyAsync(b->d_def, src_def, (size_t)n * 12 * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(b->d_att, src_att, (size_t)n * aw * esz, cudaMemcpyHostToDevice, st));
+    if (need_def) CUDA_TRY(cudaMemcpyAsync(b->d_def, src_def, (size_t)n * 12 * esz, cudaMemcpyHostToDevice, st));
     k_att = b->d_att;
     k_def = need_def ? b->d_def : nullptr;
   }
-  int rc = cbx_batch_step(b, k_att, k_def, nullptr, cuda_stream);
+  // With both agents stepping, every env writes all six result arrays each step: the kernel then also writes them straight
+  // into the caller's page-locked block (posted PCIe writes, visible after the stream sync) and no D2H copy follows.
+  // CBX_HOST_RESULTS=0 restores the copy.
+  static const bool mirror_ok = [] { const char* e = getenv("CBX_HOST_RESULTS"); return !(e && e[0] == '0'); }();
+  void* out_view = pinned_view(host_out);
+  const bool out_pinned = out_view != nullptr;
+  uint8_t* mirror = (mirror_ok && zero_copy && need_def) ? (uint8_t*)out_view : nullptr;
+  b->p.host_results = mirror;
+  b->p.act_i16 = esz == 2;
+  int rc = cbx_batch_step(b, (const int32_t*)k_att, (const int32_t*)k_def, nullptr, cuda_stream);
+  b->p.host_results = nullptr;
+  b->p.act_i16 = 0;
   if (rc) return rc;
   const cbx_views& v = b->p.v;
-  const bool out_pinned = is_pinned(host_out);
   uint8_t* o = out_pinned ? (uint8_t*)host_out : b->h_out;
-  if (b->p.n_pad == n) {  // [att_reward | def_reward | att_terminated | att_truncated | def_terminated | def_truncated] is one block
+  if (mirror) {
+    // nothing to copy
+  } else if (b->p.n_pad == n) {  // [att_reward | def_reward | att_terminated | att_truncated | def_terminated | def_truncated] is one block
     CUDA_TRY(cudaMemcpyAsync(o, v.att_reward, out_bytes, cudaMemcpyDeviceToHost, st));
   } else {
     CUDA_TRY(cudaMemcpyAsync(o, v.att_reward, (size_t)n * 4, cudaMemcpyDeviceToHost, st));

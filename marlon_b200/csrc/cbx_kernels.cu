@@ -702,6 +702,11 @@ __device__ void build_desc(const Ctx& c, uint32_t* d, int DW, const uint32_t* de
   (void)DW;
 }
 
+// one action element: the arrays are int32, or int16 for the compact host format (cbx_params.act_i16)
+__device__ __forceinline__ int32_t load_act(const int32_t* base, const int64_t idx, const int i16) {
+  return i16 ? (int32_t)reinterpret_cast<const int16_t*>(base)[idx] : base[idx];
+}
+
 struct Acc {  // per-thread episode statistics, reduced once per CTA
   double v[CBX_STAT_COUNT];
 };
@@ -745,6 +750,12 @@ __device__ void attacker_wrapper_step(const Ctx& c, const cbx_params& p, const i
   p.v.att_reward[c.env] = (float)reward;
   p.v.att_terminated[c.env] = (uint8_t)terminated;
   p.v.att_truncated[c.env] = (uint8_t)truncated;
+  if (p.host_results) {  // cbx_batch_step_host: the caller's page-locked result block, written in place over PCIe
+    uint8_t* h = p.host_results;
+    reinterpret_cast<float*>(h)[c.env] = (float)reward;
+    h[8 * p.n_envs + c.env] = (uint8_t)terminated;
+    h[9 * p.n_envs + c.env] = (uint8_t)truncated;
+  }
   p.v.network_availability[c.env] = c.live_availability();
   acc.v[CBX_STAT_ENV_STEPS] += 1;
   const int done = terminated || truncated;
@@ -802,6 +813,12 @@ __device__ void defender_wrapper_step(const Ctx& c, const cbx_params& p, const i
   p.v.def_reward[c.env] = (float)reward;
   p.v.def_terminated[c.env] = (uint8_t)term;
   p.v.def_truncated[c.env] = (uint8_t)trunc;
+  if (p.host_results) {
+    uint8_t* h = p.host_results;
+    reinterpret_cast<float*>(h + 4 * p.n_envs)[c.env] = (float)reward;
+    h[10 * p.n_envs + c.env] = (uint8_t)term;
+    h[11 * p.n_envs + c.env] = (uint8_t)trunc;
+  }
   const int done = term || trunc;
   c.g(STG_DEF_DONE) = (uint32_t)done;
   if (done) {
@@ -1007,9 +1024,9 @@ __global__ void __launch_bounds__(CBX_THREADS, CBX_MIN_CTAS) cbx_step_kernel(con
     }
     if (!reset_only) {  // coalesced: the tile's actions are contiguous in the [n, width] action arrays
       if (p.att_actions && (who_att || !marlon))
-        for (int k = tid; k < n_valid * AW; k += CBX_THREADS) s_act[k] = p.att_actions[e0 * AW + k];
+        for (int k = tid; k < n_valid * AW; k += CBX_THREADS) s_act[k] = load_act(p.att_actions, e0 * AW + k, p.act_i16);
       if (def_on)
-        for (int k = tid; k < n_valid * 12; k += CBX_THREADS) s_act[CBX_TILE * 10 + k] = p.def_actions[e0 * 12 + k];
+        for (int k = tid; k < n_valid * 12; k += CBX_THREADS) s_act[CBX_TILE * 10 + k] = load_act(p.def_actions, e0 * 12 + k, p.act_i16);
     }
     if (USE_TMA) {
       mbar_wait(&bars[1], st_phase);

@@ -108,6 +108,8 @@ struct cbx_pipe_plan {
   // shared-memory carve-up in 32-bit words
   int tables, lut, bars, zero, def_static;
   int lbufs, lbuf_words;    // per logic warp: state tile | staging | actions (aliased by the props image) | field images
+  int dynamic;              // tiles after a logic warp's first come from a global ticket counter (cbx_params.tile_counter)
+  int lookahead;            // dynamic order, 1: a logic warp draws its next ticket only when its previous tile is fully encoded
   int l_stage, l_acts;      // inside a logic buffer (the state tile is at 0)
   int i_scal, i_leak, i_cachem, i_props, i_priv, i_local;  // field images [32 envs][words per env], inside a logic buffer
   int slots, slot_words;    // per slot: descriptors [32][desc_words] | header (32 words)
@@ -149,12 +151,14 @@ struct cbx_params {
   uint32_t* state;
   const int32_t* att_actions;
   const int32_t* def_actions;
+  int act_i16;            // the two action arrays hold int16 elements (cbx_batch_step_i16 / _host_i16)
+  uint8_t* host_results;  // optional mirror of the six result arrays in mapped host memory, cbx_batch_step_host's layout
   const double* scan_u;
   const double* detect_u;
   const uint8_t* reset_mask;  // reset kernel only
   float notify_last_reward;   // CBX_OP_NOTIFY
   cbx_views v;
-  int* tile_counter;      // dynamic tile scheduler
+  int* tile_counter;      // pipelined kernel, dynamic tile order: [0] tickets handed out, [1] CTAs finished (both 0 between launches)
   unsigned long long* prof;  // optional: 16 cycle counters accumulated per phase by thread 0 of every CTA (NULL = off)
 };
 

@@ -305,11 +305,36 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
     im.priv = reinterpret_cast<int32_t*>(lb + Q.i_priv); im.local = lb + Q.i_local;
     const int wpe_leak = 4 * L.LEAK, wpe_cachem = 2 * L.C, wpe_props = L.N * L.nprops, wpe_priv = L.N, wpe_local = L.sz_local / 4;
     int u = 0;  // my u-th tile
-    for (int j = warp; j < my_tiles; j += Q.wl, ++u) {
+    // Tile order.  Static: tile j of this CTA is blockIdx.x + j * gridDim.x, warp w takes j = w, w + wl, ...  Dynamic: a warp's
+    // first tile is the static one (no ticket latency in the pipeline fill), every later one is the next ticket of a global
+    // counter -- CTAs that run ahead (the SMs do not all see the same memory latency) take more tiles and the launch ends
+    // when the work does, not when the slowest CTA has finished a fixed share.  The ticket for tile u + 1 is drawn while
+    // tile u is being worked on.  A warp that draws a ticket past the end publishes a stop marker in its next slot.
+    int next_tile = (int)blockIdx.x + warp * (int)gridDim.x;
+    for (int j = warp;; j += Q.wl, ++u) {
       const int slot = warp + Q.wl * (u % spw), use = u / spw;
       uint32_t* desc = smem + Q.slots + slot * Q.slot_words;
       uint32_t* hdr = desc + Q.s_hdr;
-      const int tile = (int)blockIdx.x + j * (int)gridDim.x;
+      int tile;
+      if (Q.dynamic) {
+        if (Q.lookahead && u > 0) {  // bounded run-ahead: my previous tile must have left the encoders
+          const int pu = u - 1;
+          mbar_wait(&bar_empty[warp + Q.wl * (pu % spw)], (uint32_t)(pu / spw) & 1u);
+        }
+        if (Q.dynamic == 2 && u > 0 && lane == 0) next_tile = (int)gridDim.x * Q.wl + atomicAdd(p.tile_counter, 1);  // drawn when needed
+        tile = __shfl_sync(0xFFFFFFFFu, next_tile, 0);
+        if (tile >= p.n_tiles) {
+          if (use > 0) mbar_wait(&bar_empty[slot], (uint32_t)(use - 1) & 1u);
+          if (lane == 0) hdr[CBX_SH_TILE] = 0xFFFFFFFFu;
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_ready[slot]);
+          break;
+        }
+        if (Q.dynamic == 1 && lane == 0) next_tile = (int)gridDim.x * Q.wl + atomicAdd(p.tile_counter, 1);
+      } else {
+        if (j >= my_tiles) break;
+        tile = (int)blockIdx.x + j * (int)gridDim.x;
+      }
       const int64_t e0 = (int64_t)tile * CBX_TILE;
       const int n_valid = (int)min((int64_t)CBX_TILE, p.n_envs - e0);
       const uint4* gstate = reinterpret_cast<const uint4*>(p.state + (int64_t)tile * L.S * CBX_TILE);
@@ -324,12 +349,18 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
         tma_store_wait_read();
         __syncwarp();
         if (lane == 0) {
-          const uint32_t att_bytes = (bulk_acts && need_att) ? (uint32_t)(CBX_TILE * AW * 4) : 0u;
-          const uint32_t def_bytes = (bulk_acts && need_def) ? (uint32_t)(CBX_TILE * 12 * 4) : 0u;
+          // int16 actions land in the upper half of their int32 area and are widened in place after the wait
+          const uint32_t asz = p.act_i16 ? 2u : 4u, half = p.act_i16 ? 1u : 0u;
+          const uint32_t att_bytes = (bulk_acts && need_att) ? (uint32_t)(CBX_TILE * AW) * asz : 0u;
+          const uint32_t def_bytes = (bulk_acts && need_def) ? (uint32_t)(CBX_TILE * 12) * asz : 0u;
           mbar_expect_tx(&bar_load[warp], (uint32_t)L.S * kRowBytes + att_bytes + def_bytes);
           tma_load_1d(lb, gstate, (uint32_t)L.S * kRowBytes, &bar_load[warp]);
-          if (att_bytes) tma_load_1d(act, p.att_actions + e0 * AW, att_bytes, &bar_load[warp]);
-          if (def_bytes) tma_load_1d(act + CBX_TILE * 10, p.def_actions + e0 * 12, def_bytes, &bar_load[warp]);
+          if (att_bytes)
+            tma_load_1d(reinterpret_cast<char*>(act) + half * att_bytes, reinterpret_cast<const char*>(p.att_actions) + e0 * AW * asz,
+                        att_bytes, &bar_load[warp]);
+          if (def_bytes)
+            tma_load_1d(reinterpret_cast<char*>(act + CBX_TILE * 10) + half * def_bytes,
+                        reinterpret_cast<const char*>(p.def_actions) + e0 * 12 * asz, def_bytes, &bar_load[warp]);
         }
       } else {
         uint4* d = reinterpret_cast<uint4*>(lb);
@@ -338,13 +369,32 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
       }
       if (!bulk_acts) {
         if (need_att)
-          for (int q = lane; q < n_valid * AW; q += 32) act[q] = p.att_actions[e0 * AW + q];
+          for (int q = lane; q < n_valid * AW; q += 32) act[q] = load_act(p.att_actions, e0 * AW + q, p.act_i16);
         if (need_def)
-          for (int q = lane; q < n_valid * 12; q += 32) act[CBX_TILE * 10 + q] = p.def_actions[e0 * 12 + q];
+          for (int q = lane; q < n_valid * 12; q += 32) act[CBX_TILE * 10 + q] = load_act(p.def_actions, e0 * 12 + q, p.act_i16);
       }
       if (Q.logic_tma) {
         mbar_wait(&bar_load[warp], load_phase);
         load_phase ^= 1;
+      }
+      if (bulk_acts && p.act_i16) {  // widen this lane's rows: every lane reads before any lane writes (the areas overlap)
+        int32_t va[10], vd[12];
+        const int16_t* a16 = reinterpret_cast<const int16_t*>(act) + CBX_TILE * AW + lane * AW;
+        const int16_t* d16 = reinterpret_cast<const int16_t*>(act + CBX_TILE * 10) + CBX_TILE * 12 + lane * 12;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) va[k] = (need_att && k < AW) ? (int32_t)a16[k] : 0;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) vd[k] = need_def ? (int32_t)d16[k] : 0;
+        __syncwarp();
+        if (need_att) {
+#pragma unroll
+          for (int k = 0; k < 10; ++k)
+            if (k < AW) act[lane * AW + k] = va[k];
+        }
+        if (need_def) {
+#pragma unroll
+          for (int k = 0; k < 12; ++k) act[CBX_TILE * 10 + lane * 12 + k] = vd[k];
+        }
       }
       __syncwarp();
       CBX_PPROF(9)  // state tile + actions in
@@ -489,14 +539,26 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
     const int wid = warp - Q.wl;
     uint8_t* wb = reinterpret_cast<uint8_t*>(smem + Q.wbufs + wid * Q.wbuf_words);
     long long pacc[3] = {0, 0, 0};
-    for (int j = 0; j < my_tiles; ++j) {
+    uint32_t stopped = 0;  // dynamic order: logic warps that have published their stop marker
+    const uint32_t all_stopped = (1u << Q.wl) - 1u;
+    for (int j = 0;; ++j) {
       const int lw = j % Q.wl, u = j / Q.wl;
+      if (Q.dynamic) {
+        if (stopped == all_stopped) break;
+        if ((stopped >> lw) & 1u) continue;
+      } else if (j >= my_tiles) {
+        break;
+      }
       const int slot = lw + Q.wl * (u % spw), use = u / spw;
       const uint32_t* desc = smem + Q.slots + slot * Q.slot_words;
       mbar_wait(&bar_ready[slot], (uint32_t)use & 1u);
       CBX_PPROF(12)  // encoders waiting for a tile
+      const int tile = Q.dynamic ? (int)desc[Q.s_hdr + CBX_SH_TILE] : (int)blockIdx.x + j * (int)gridDim.x;
+      if (tile < 0) {  // stop marker
+        stopped |= 1u << lw;
+        continue;
+      }
       const uint32_t enc_mask = desc[Q.s_hdr + CBX_SH_ENC_MASK];
-      const int tile = (int)blockIdx.x + j * (int)gridDim.x;
       const int64_t e0 = (int64_t)tile * CBX_TILE;
       const int n_valid = (int)min((int64_t)CBX_TILE, p.n_envs - e0);
       if (dense) {
@@ -524,6 +586,17 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
     for (int k = 0; k < 5; ++k)
       if (pp[k]) atomicAdd(p.prof + 8 + k, (unsigned long long)pp[k]);
 #undef CBX_PPROF
+  if (Q.dynamic) {  // the last CTA to finish leaves the ticket counter at zero for the next launch
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      if (atomicAdd(p.tile_counter + 1, 1) == (int)gridDim.x - 1) {
+        p.tile_counter[0] = 0;
+        p.tile_counter[1] = 0;
+        __threadfence();
+      }
+    }
+  }
 }
 
 }  // namespace cbx

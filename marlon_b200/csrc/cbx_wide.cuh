@@ -179,9 +179,9 @@ __global__ void __launch_bounds__(CBX_WIDE_WARPS * 32, 1) cbx_wide_kernel(const 
     for (int r = lane; r < L.S; r += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(gst + (size_t)r * CBX_TILE));
     if (!reset_only) {
       if (p.att_actions && (who_att || !marlon))
-        for (int q = lane; q < n_valid * AW; q += 32) act[q] = p.att_actions[e0 * AW + q];
+        for (int q = lane; q < n_valid * AW; q += 32) act[q] = load_act(p.att_actions, e0 * AW + q, p.act_i16);
       if (def_on)
-        for (int q = lane; q < n_valid * 12; q += 32) act[CBX_TILE * 10 + q] = p.def_actions[e0 * 12 + q];
+        for (int q = lane; q < n_valid * 12; q += 32) act[CBX_TILE * 10 + q] = load_act(p.def_actions, e0 * 12 + q, p.act_i16);
     }
     __syncwarp();
     CBX_WPROF(1)  // actions in

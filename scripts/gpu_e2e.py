@@ -14,14 +14,25 @@ ha = torch.empty((K, n, 10), dtype=torch.int32, pin_memory=True); hd = torch.emp
 ha.copy_(ta); hd.copy_(td); torch.cuda.synchronize()
 han, hdn = ha.numpy(), hd.numpy()
 b.close()
-b = Batch(comp, cfg, n); b.reset()
-for s in range(10): b.step_host(han[s], hdn[s])
-b.enable_timing(True)
-t0 = time.perf_counter()
-for s in range(10, K): b.step_host(han[s], hdn[s])
-wall = (time.perf_counter() - t0) / (K - 10)
-kms, kn = b.step_kernel_ms()
-print(f"step_host: wall {wall*1e3:.4f} ms/step, kernel {kms:.4f} ms ({kn} launches), rest {wall*1e3-kms:.4f} ms")
+for dt in (torch.int32, torch.int16):
+    ha2, hd2 = torch.empty((K, n, 10), dtype=dt, pin_memory=True), torch.empty((K, n, 12), dtype=dt, pin_memory=True)
+    ha2.copy_(ha.to(dt)); hd2.copy_(hd.to(dt))
+    a_n, d_n = ha2.numpy(), hd2.numpy()
+    b = Batch(comp, cfg, n); b.reset()
+    for s in range(10): b.step_host(a_n[s], d_n[s])
+    t0 = time.perf_counter()
+    for s in range(10, K): b.step_host(a_n[s], d_n[s])
+    wall0 = (time.perf_counter() - t0) / (K - 10)
+    b.close()
+    b = Batch(comp, cfg, n); b.reset()
+    for s in range(10): b.step_host(a_n[s], d_n[s])
+    b.enable_timing(True)
+    t0 = time.perf_counter()
+    for s in range(10, K): b.step_host(a_n[s], d_n[s])
+    wall = (time.perf_counter() - t0) / (K - 10)
+    kms, kn = b.step_kernel_ms()
+    print(f"step_host {dt}: wall {wall0*1e3:.4f} ms/step untimed, {wall*1e3:.4f} with events, kernel {kms:.4f} ms ({kn} launches), rest {wall*1e3-kms:.4f} ms")
+    b.close()
 # D2H alone
 out = torch.empty(n * 12, dtype=torch.uint8, pin_memory=True)
 src = torch.empty(n * 12, dtype=torch.uint8, device="cuda")

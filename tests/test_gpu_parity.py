@@ -196,6 +196,74 @@ def test_step_host_roundtrip():
     b.close()
 
 
+def test_step_host_page_locked_buffers_and_int16_actions():
+    """Page-locked callers: the kernel reads the actions in place and writes the result block itself (no copies).  int16
+    action elements give the same step as int32 ones; 513 envs = 16 full tiles (bulk action loads) + a ragged one."""
+    import torch
+
+    comp = scenario.compile_scenario(scenarios.toyctf_environment())
+    cfg = config.make_config(_abi.MODE_MARLON, maximum_node_count=12, maximum_total_credentials=10, throws_on_invalid_actions=False,
+                             attacker_goal=config.AttackerGoal(own_atleast=6), defender_constraint=config.DefenderConstraint(0.60),
+                             losing_reward=-5000.0, defender_enabled=True)
+    n = 513
+    ref, b32, b16 = _batch(comp, cfg, n), _batch(comp, cfg, n), _batch(comp, cfg, n)
+    for b in (ref, b32, b16):
+        b.reset()
+    p_att32, p_def32 = torch.empty((n, 10), dtype=torch.int32, pin_memory=True), torch.empty((n, 12), dtype=torch.int32, pin_memory=True)
+    p_att16, p_def16 = torch.empty((n, 10), dtype=torch.int16, pin_memory=True), torch.empty((n, 12), dtype=torch.int16, pin_memory=True)
+    keys = ("att_reward", "def_reward", "att_terminated", "att_truncated", "def_terminated", "def_truncated")
+    for s in range(40):
+        att, dfn = ref.sample_actions(seed=5)
+        if s % 4 == 0:
+            dfn[::3, 0] = -1  # empty defender actions (negative values must survive the narrowing)
+        ref.step(att, dfn)
+        p_att32.copy_(att); p_def32.copy_(dfn); p_att16.copy_(att.to(torch.int16)); p_def16.copy_(dfn.to(torch.int16))
+        o32 = b32.step_host(p_att32.numpy(), p_def32.numpy())
+        o16 = b16.step_host(p_att16.numpy(), p_def16.numpy())
+        for k in keys:
+            want = ref.numpy(k)
+            assert np.array_equal(o32[k], want), (s, k, "int32 page-locked")
+            assert np.array_equal(o16[k], want), (s, k, "int16 page-locked")
+            assert np.array_equal(b16.numpy(k), want), (s, k, "device copy of the results")
+        if s % 8 == 7:
+            st = ref.export_state()
+            assert np.array_equal(b32.export_state(), st) and np.array_equal(b16.export_state(), st), s
+            for k, t in ref.tensors.items():
+                assert torch.equal(t, b16.tensors[k]), (s, k)
+    for b in (ref, b32, b16):
+        b.close()
+
+
+@pytest.mark.parametrize("case", ["chain100_factored", "odd_bounds_cyber"])
+def test_int16_device_actions_match_int32(case):
+    """cbx_batch_step_i16 on the other two kernels (warp-per-tile and fused) and in CyberBattleEnv mode ([n,5] actions)."""
+    import torch
+
+    if case == "chain100_factored":
+        comp = scenario.compile_scenario(scenarios.chain_environment(100))
+        cfg = config.make_config(_abi.MODE_MARLON, maximum_node_count=102, maximum_total_credentials=102,
+                                 throws_on_invalid_actions=False, defender_constraint=config.DefenderConstraint(0.60),
+                                 losing_reward=-5000.0, defender_enabled=True, defender_max_timesteps=500,
+                                 attacker_max_timesteps=500, mask_mode=_abi.MASK_FACTORED)
+        n = 200
+    else:
+        comp = scenario.compile_scenario(scenarios.chain_environment(4))
+        cfg = config.make_config(_abi.MODE_CYBERBATTLE, maximum_node_count=7, maximum_total_credentials=5,
+                                 throws_on_invalid_actions=False, auto_reset=True, emit_terminal_obs=True)
+        n = 77
+    ref, b16 = _batch(comp, cfg, n), _batch(comp, cfg, n)
+    ref.reset(); b16.reset()
+    for s in range(60):
+        att, dfn = ref.sample_actions(seed=9)
+        ref.step(att, dfn)
+        b16.step(att.to(torch.int16), dfn.to(torch.int16) if dfn is not None else None)
+        if s % 6 == 5:
+            assert np.array_equal(b16.export_state(), ref.export_state()), s
+            for k, t in ref.tensors.items():
+                assert torch.equal(t, b16.tensors[k]), (s, k)
+    ref.close(); b16.close()
+
+
 # ---- configs[4]: several generated CyberBattleRandom networks in ONE batch (padded layout, scenario per env group) ----
 def _slice_export(x, n_max, n_k, C, nsec_k):
     """multi-scenario export (sections sized for the largest scenario) -> the layout a single-scenario export of n_k nodes has"""
