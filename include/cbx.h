@@ -395,7 +395,8 @@ int cbx_gae(const float* rewards, const float* values, const uint8_t* episode_st
  * logic warps ahead of TMA-storing encoder warps) / 2 warp-per-tile kernel for large state (cbx_wide_kernel) / 0 fused kernel
  * (cbx_step_kernel); [1] CTAs; [2] threads per CTA;
  * [3] dynamic shared memory bytes per CTA; [4] logic warps; [5] encoder warps; [6] encoder variant (0 generic, 1 warp per
- * env, 2 ToyCtf(12,10) static, 3 Chain-10(12,12) static); [7] TMA staging enabled. */
+ * env, 2 ToyCtf(12,10) static, 3 Chain-10(12,12) static); [7] bit 0 TMA staging enabled, bit 1 dynamic tile order (tiles after a warp's first are drawn
+ * from a global ticket counter instead of a fixed stride). */
 int cbx_batch_kernel_info(const cbx_batch* b, int32_t* out8);
 
 /* Instrumentation: per-phase SM cycle counters of the step kernel, summed over CTAs (thread 0 of each CTA):

@@ -489,12 +489,12 @@ static int create_impl(const cbx_scenario* const* scns, int n_scn, const int64_t
       if (ok && cbx_pipe_attrs(b->p.enc.warp_env, Q.total_bytes) == cudaSuccess) {
         Q.enabled = 1;
         { const char* lt = getenv("CBX_PIPE_LOGIC_TMA"); Q.logic_tma = !(lt && lt[0] == '0'); }
-        { const char* dy = getenv("CBX_PIPE_DYNAMIC"); Q.dynamic = dy ? atoi(dy) : 0; }
-        { const char* la = getenv("CBX_PIPE_LOOKAHEAD"); Q.lookahead = la ? atoi(la) : 0; }
-        b->p.pipe = Q;
         int per_sm = ect ? atoi(ect) : 1;
         if (per_sm < 1) per_sm = 1;
         b->pipe_grid = sms * per_sm < b->p.n_tiles ? sms * per_sm : b->p.n_tiles;
+        // dynamic tile order pays from ~24 tiles per CTA on (131 072 envs per GPU); CBX_PIPE_DYNAMIC=0/1 overrides
+        { const char* dy = getenv("CBX_PIPE_DYNAMIC"); Q.dynamic = dy ? atoi(dy) != 0 : b->p.n_tiles >= 24 * b->pipe_grid; }
+        b->p.pipe = Q;
       } else {
         cudaGetLastError();
       }
@@ -509,6 +509,7 @@ static int create_impl(const cbx_scenario* const* scns, int n_scn, const int64_t
     cbx_wide_plan Q;
     if (want && plan_wide(b->p, sms, &Q) && cbx_wide_attrs(Q.total_bytes) == cudaSuccess) {
       Q.enabled = 1;
+      { const char* dy = getenv("CBX_WIDE_DYNAMIC"); Q.dynamic = dy ? atoi(dy) != 0 : 1; }  // never slower, +6 % on multi-scenario batches
       b->p.wide = Q;
       const int need = (b->p.n_tiles + Q.nwarps - 1) / Q.nwarps;
       b->wide_grid = sms < need ? sms : need;
@@ -562,7 +563,7 @@ static int create_impl(const cbx_scenario* const* scns, int n_scn, const int64_t
       b->p.tile_scn = b->d_tile_scn;
     }
   }
-  if (b->p.pipe.enabled) {
+  {
     void* pc = nullptr;
     cudaError_t e = dalloc(&pc, 64);
     if (e != cudaSuccess) { int rc2 = fail(CBX_ERR_CUDA, "cudaMalloc(tile counter): %s", cudaGetErrorString(e)); cbx_batch_destroy(b); return rc2; }
@@ -948,7 +949,7 @@ int cbx_batch_kernel_info(const cbx_batch* b, int32_t* out8) {
   out8[4] = Q.enabled ? Q.wl : 0;
   out8[5] = Q.enabled ? Q.we : 0;
   out8[6] = b->p.enc.warp_env;
-  out8[7] = b->use_tma;
+  out8[7] = b->use_tma | ((Q.enabled ? Q.dynamic : wide ? b->p.wide.dynamic : 0) ? 2 : 0);
   return CBX_OK;
 }
 

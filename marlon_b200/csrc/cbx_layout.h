@@ -109,7 +109,6 @@ struct cbx_pipe_plan {
   int tables, lut, bars, zero, def_static;
   int lbufs, lbuf_words;    // per logic warp: state tile | staging | actions (aliased by the props image) | field images
   int dynamic;              // tiles after a logic warp's first come from a global ticket counter (cbx_params.tile_counter)
-  int lookahead;            // dynamic order, 1: a logic warp draws its next ticket only when its previous tile is fully encoded
   int l_stage, l_acts;      // inside a logic buffer (the state tile is at 0)
   int i_scal, i_leak, i_cachem, i_props, i_priv, i_local;  // field images [32 envs][words per env], inside a logic buffer
   int slots, slot_words;    // per slot: descriptors [32][desc_words] | header (32 words)
@@ -127,6 +126,7 @@ enum { CBX_SH_ENC_MASK = 0, CBX_SH_TILE = 1 };
 struct cbx_wide_plan {
   int enabled;
   int nwarps;                                      // warps per CTA: as many as fit (<= CBX_WIDE_WARPS)
+  int dynamic;                                     // tiles after a warp's first come from the global ticket counter
   int lut, lut4, warps, warp_words;                // shared-memory carve-up in 32-bit words
   int w_stage, w_desc, w_acts, w_img, w_drows;     // inside a warp's area
   int total_bytes;
@@ -158,7 +158,7 @@ struct cbx_params {
   const uint8_t* reset_mask;  // reset kernel only
   float notify_last_reward;   // CBX_OP_NOTIFY
   cbx_views v;
-  int* tile_counter;      // pipelined kernel, dynamic tile order: [0] tickets handed out, [1] CTAs finished (both 0 between launches)
+  int* tile_counter;      // dynamic tile order: [0] tickets handed out, [1] CTAs finished (both 0 between launches)
   unsigned long long* prof;  // optional: 16 cycle counters accumulated per phase by thread 0 of every CTA (NULL = off)
 };
 

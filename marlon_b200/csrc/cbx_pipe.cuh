@@ -308,8 +308,9 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
     // Tile order.  Static: tile j of this CTA is blockIdx.x + j * gridDim.x, warp w takes j = w, w + wl, ...  Dynamic: a warp's
     // first tile is the static one (no ticket latency in the pipeline fill), every later one is the next ticket of a global
     // counter -- CTAs that run ahead (the SMs do not all see the same memory latency) take more tiles and the launch ends
-    // when the work does, not when the slowest CTA has finished a fixed share.  The ticket for tile u + 1 is drawn while
-    // tile u is being worked on.  A warp that draws a ticket past the end publishes a stop marker in its next slot.
+    // when the work does, not when the slowest CTA has finished a fixed share.  A warp that draws a ticket past the end
+    // publishes a stop marker in its next slot.  Measured: +2 % at 28 tiles per CTA, +9..11 % from 55 on,
+    // -2.5 % at 14 (most of a short launch is assigned before any CTA has shown its speed), hence the threshold in the plan.
     int next_tile = (int)blockIdx.x + warp * (int)gridDim.x;
     for (int j = warp;; j += Q.wl, ++u) {
       const int slot = warp + Q.wl * (u % spw), use = u / spw;
@@ -317,11 +318,7 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
       uint32_t* hdr = desc + Q.s_hdr;
       int tile;
       if (Q.dynamic) {
-        if (Q.lookahead && u > 0) {  // bounded run-ahead: my previous tile must have left the encoders
-          const int pu = u - 1;
-          mbar_wait(&bar_empty[warp + Q.wl * (pu % spw)], (uint32_t)(pu / spw) & 1u);
-        }
-        if (Q.dynamic == 2 && u > 0 && lane == 0) next_tile = (int)gridDim.x * Q.wl + atomicAdd(p.tile_counter, 1);  // drawn when needed
+        if (u > 0 && lane == 0) next_tile = (int)gridDim.x * Q.wl + atomicAdd(p.tile_counter, 1);
         tile = __shfl_sync(0xFFFFFFFFu, next_tile, 0);
         if (tile >= p.n_tiles) {
           if (use > 0) mbar_wait(&bar_empty[slot], (uint32_t)(use - 1) & 1u);
@@ -330,7 +327,6 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
           if (lane == 0) mbar_arrive(&bar_ready[slot]);
           break;
         }
-        if (Q.dynamic == 1 && lane == 0) next_tile = (int)gridDim.x * Q.wl + atomicAdd(p.tile_counter, 1);
       } else {
         if (j >= my_tiles) break;
         tile = (int)blockIdx.x + j * (int)gridDim.x;

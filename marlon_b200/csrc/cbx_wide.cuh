@@ -168,7 +168,15 @@ __global__ void __launch_bounds__(CBX_WIDE_WARPS * 32, 1) cbx_wide_kernel(const 
   const int n6 = 6 * L.n;
   const int nw = (int)blockDim.x >> 5;  // warps per CTA (<= CBX_WIDE_WARPS)
   const int gw = (int)gridDim.x * nw;
-  for (int tile = (int)blockIdx.x * nw + warp; tile < p.n_tiles; tile += gw) {
+  // tile order: static stride, or (Q.dynamic) every tile after a warp's first is the next ticket of a global counter, so that
+  // warps on faster SMs -- and, in a multi-scenario batch, warps that drew cheap tiles -- take more of them
+  auto next_tile = [&](int t) {
+    if (!Q.dynamic) return t + gw;
+    int x = 0;
+    if (lane == 0) x = gw + atomicAdd(p.tile_counter, 1);
+    return __shfl_sync(0xFFFFFFFFu, x, 0);
+  };
+  for (int tile = (int)blockIdx.x * nw + warp; tile < p.n_tiles; tile = next_tile(tile)) {
     const int64_t e0 = (int64_t)tile * CBX_TILE;
     const int n_valid = (int)min((int64_t)CBX_TILE, p.n_envs - e0);
     const int scn = p.tile_scn ? p.tile_scn[tile] : 0;
@@ -341,6 +349,17 @@ __global__ void __launch_bounds__(CBX_WIDE_WARPS * 32, 1) cbx_wide_kernel(const 
     double x = acc.v[k];
     for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xFFFFFFFFu, x, o);
     if (lane == 0 && x != 0.0) atomicAdd(p.v.episode_stats + k, x);
+  }
+  if (Q.dynamic) {  // the last CTA to finish leaves the ticket counter at zero for the next launch
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      if (atomicAdd(p.tile_counter + 1, 1) == (int)gridDim.x - 1) {
+        p.tile_counter[0] = 0;
+        p.tile_counter[1] = 0;
+        __threadfence();
+      }
+    }
   }
 }
 
