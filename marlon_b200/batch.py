@@ -17,6 +17,25 @@ from .scenario import CompiledScenario
 _TYPESTR = {"int32": "<i4", "int8": "|i1", "uint8": "|u1", "uint32": "<u4", "float32": "<f4", "float64": "<f8"}
 
 
+def narrow_actions(actions, out: Optional[np.ndarray] = None) -> np.ndarray:
+    """MultiDiscrete actions as the policy returns them (int64 from SB3, ``baseline_marlon_agent.py:118-131``) -> int16
+    elements for ``Batch.step_host`` / ``cbx_batch_step_host_i16``.  `out` may be a page-locked array
+    (``torch.empty(shape, dtype=torch.int16, pin_memory=True).numpy()``) that the kernel then reads in place.  Values that
+    do not fit raise instead of wrapping: no component of either action space comes near 32 768 (the largest is
+    ``maximum_total_credentials``), so an overflow means a corrupted action, not a big one."""
+    a = np.asarray(actions)
+    if a.dtype.kind not in "iu":
+        raise TypeError(f"integer actions expected, got {a.dtype}")
+    if a.size and (int(a.max()) > np.iinfo(np.int16).max or int(a.min()) < np.iinfo(np.int16).min):
+        raise OverflowError("action component outside the int16 range")
+    if out is None:
+        return np.ascontiguousarray(a, dtype=np.int16)
+    if out.dtype != np.int16 or out.shape != a.shape:
+        raise ValueError(f"out must be int16 of shape {a.shape}")
+    np.copyto(out, a, casting="unsafe")
+    return out
+
+
 class _DevArray:
     def __init__(self, ptr, shape, dtype):
         self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": _TYPESTR[dtype], "data": (int(ptr), False),

@@ -161,3 +161,26 @@ def test_wrappers_construct_without_a_gpu_and_expose_reference_spaces():
     assert cbe.make("CyberBattleChain-v0", size=10, maximum_node_count=12, maximum_total_credentials=12).name == "CyberBattleChain-10"
     with pytest.raises(ValueError, match="exceeds the specified limit"):
         cbe.make("CyberBattleChain-v0", size=100)  # 102 nodes > default maximum_node_count=100 (cyberbattle_env.py:417-418)
+
+
+def test_narrow_actions_checks_the_range_and_fills_caller_buffers():
+    """int64 policy output -> int16 elements for the host-buffer step (cbx_batch_step_host_i16)."""
+    import numpy as np
+    import pytest
+
+    from marlon_b200.batch import narrow_actions
+
+    a = np.array([[2, 11, 9, 6, 9, 0, 2, 0, 0, 7], [-1, 0, 0, 0, 0, 0, 0, 0, 0, 999]], dtype=np.int64)
+    n = narrow_actions(a)
+    assert n.dtype == np.int16 and n.flags["C_CONTIGUOUS"] and np.array_equal(n, a)
+    out = np.full(a.shape, 7, dtype=np.int16)
+    assert narrow_actions(a[:, ::1], out=out) is out and np.array_equal(out, a)
+    with pytest.raises(OverflowError):
+        narrow_actions(np.array([[40000]], dtype=np.int64))
+    with pytest.raises(OverflowError):
+        narrow_actions(np.array([[-40000]], dtype=np.int32))
+    with pytest.raises(TypeError):
+        narrow_actions(np.array([[1.0]]))
+    with pytest.raises(ValueError):
+        narrow_actions(a, out=np.zeros((2, 9), dtype=np.int16))
+    assert narrow_actions(np.zeros((0, 10), dtype=np.int64)).shape == (0, 10)
