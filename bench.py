@@ -260,6 +260,23 @@ def cpu_baseline(seconds=12.0, n_envs=256, cores=None):
                       f"{seconds:.0f} s wall each, only oracle step() timed ({sum(s for s, _ in res)} env-steps)"}
 
 
+def workload_label(workload, factored):
+    """The `config.workload` string: one function for both arms, so that the driver's same_config comparison holds."""
+    return WORKLOADS[workload] + ", " + ("factored" if factored else "dense int8") + " action masks, random valid actions"
+
+
+def python_reference_baseline():
+    """The north star's CPU baseline -- the UNMODIFIED Python reference under multiprocessing.Pool on every core -- cannot run
+    on the GPU box (/root/reference does not travel): it was timed on the dev container by oracle/time_python_reference.py
+    and is carried from profiles/r02_python_reference_cpu.json, labelled as such."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r02_python_reference_cpu.json")))
+        d["note"] = "measured on the dev container (no GPU), not on this box: " + d.get("note", "")
+        return d
+    except Exception:
+        return None
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -267,145 +284,143 @@ def run_reference(args):
     t0 = time.time()
     per = max(2.0, min(20.0, 1.5 * (args.steps + args.warmup) / 10.0))
     cb = cpu_baseline(seconds=per)
-    comp, cfg = workload_config()
     line = {
         "impl": "reference", "metric": "attacker+defender env-steps/sec", "value": cb["value"], "unit": "env-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "CyberBattleToyCtf-v0 (N=12,C=10) MARLon attacker+defender pair step, dense masks, random valid actions",
+        "config": {"workload": workload_label("toyctf", False),
                    "note": "reference arm = CPU oracle port of the reference step (the reference is pure Python and does not travel); "
                            "one process per host core, bounded sample"},
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.time() - t0,
     }
+    pr = python_reference_baseline()
+    if pr:
+        line["cpu_baseline"]["python_reference"] = pr
     print(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------------------------------
-def run_ours(args):
+def pin_to_gpu_numa(local):
+    """Run this rank on the CPUs next to its GPU (NVML's affinity mask for the device): the page-locked action / result
+    buffers are then allocated on that NUMA node and the per-step launch + sync loop does not cross sockets."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[local]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else local
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {i * 64 + b for i, w in enumerate(mask) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return {"pinned_cpus": len(cpus), "first_cpu": min(cpus) if cpus else None}
+    except Exception as e:  # noqa: BLE001
+        return {"pinned_cpus": 0, "error": str(e)[:80]}
+
+
+def record_tape(comp, cfg, counts, n, steps, seed, local, dev):
+    """Synthetic action tape: valid attacker actions for the evolving state (sampler kernel) + uniform defender actions,
+    recorded once on a scratch batch -- the env dynamics are deterministic, so replaying it on a fresh batch stays valid."""
+    import torch
+
+    from marlon_b200 import _abi
+    from marlon_b200.batch import Batch
+
+    rec = Batch(comp, cfg, counts, device=local)
+    rec.reset()
+    aw = rec.att_width  # 10: MARLon MultiDiscrete attacker action; 5: CyberBattleEnv [kind, 4 coordinates]
+    has_def = bool(cfg.mode == _abi.MODE_MARLON and cfg.def_enabled)
+    tape_a = torch.empty((steps, n, aw), dtype=torch.int32, device=dev)
+    tape_d = torch.empty((steps, n, 12), dtype=torch.int32, device=dev) if has_def else [None] * steps
+    for s in range(steps):
+        rec.sample_actions(seed=seed, attacker_out=tape_a[s], defender_out=tape_d[s] if has_def else None)
+        rec.step(tape_a[s], tape_d[s])
+    torch.cuda.synchronize()
+    rec.close()
+    return tape_a, tape_d, aw, has_def
+
+
+def touched_state_words(comp, cfg):
+    """In-place kernel (cbx_wide_kernel): words of the per-env state a step has to touch -- the wrappers' words, the stale
+    copy's countdowns and the header read + written; discovery order / inverse map, installed bits, privilege levels,
+    property bitsets and the credential cache read to build the observation.  The rest of the state (attacked bits, live
+    countdowns, gathered / cached bitsets, ever-owned, not-running) is touched only by the few envs whose action needs it
+    and is NOT counted -- see DESIGN.md 4.3."""
+    n = comp.n_nodes
+    ident = comp.identifiers
+    props = len(ident.properties)
+    Wn, PW = (n + 31) // 32, (props + 31) // 32
+    ntr = len(comp.triples)
+    rw = 13 + (n + 3) // 4 + 2                     # wrapper words + shadow countdowns + stepcount / episode sum
+    ro = Wn + (n + 15) // 16 + 2 * ((n + 3) // 4) + n * PW + (ntr + 2) // 2
+    return rw, ro
+
+
+def measure_device(args, workload, n_req, K, W, world, rank, local, dev, clocks=None):
+    """W untimed + K timed device-resident steps of `workload` with n_req envs on this rank, then the per-rollout statistics
+    all-reduce INSIDE the timed region.  -> dict (rank 0 fills the derived numbers)."""
     import torch
     import torch.distributed as dist
 
     from marlon_b200 import _abi
     from marlon_b200.batch import Batch
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    dev = torch.device("cuda", local)
-    comp, cfg = workload_config(mask_mode=1 if args.factored else 0, workload=args.workload)
+    comp, cfg = workload_config(mask_mode=1 if args.factored else 0, workload=workload)
     factored = bool(cfg.mask_mode)
-    n = args.envs_per_gpu
-    K, W = args.steps, args.warmup
-
-    # ---- record the synthetic action tape (valid attacker actions for the evolving state), untimed ----
     multi = isinstance(comp, list)
-    counts = [n // len(comp)] * len(comp) if multi else n  # envs per scenario (multiples of 32 for the default sizes)
-    if multi:
-        n = sum(counts)
-    rec = Batch(comp, cfg, counts, device=local)
-    rec.reset()
-    aw = rec.att_width  # 10: MARLon MultiDiscrete attacker action; 5: CyberBattleEnv [kind, 4 coordinates]
-    has_def = bool(cfg.mode == _abi.MODE_MARLON and cfg.def_enabled)
-    tape_a = torch.empty((W + K, n, aw), dtype=torch.int32, device=dev)
-    tape_d = torch.empty((W + K, n, 12), dtype=torch.int32, device=dev) if has_def else [None] * (W + K)
-    for s in range(W + K):
-        rec.sample_actions(seed=args.seed + rank, attacker_out=tape_a[s], defender_out=tape_d[s] if has_def else None)
-        rec.step(tape_a[s], tape_d[s])
-    torch.cuda.synchronize()
-    S_words = None
-    rec.close()
-    del rec
-
+    counts = [n_req // len(comp)] * len(comp) if multi else n_req
+    n = sum(counts) if multi else n_req
+    tape_a, tape_d, aw, has_def = record_tape(comp, cfg, counts, n, W + K, args.seed + rank, local, dev)
     b = Batch(comp, cfg, counts, device=local)
     b.reset()
-    S_words = b.export_state(0, 1).shape[1]  # canonical words (not the packed layout); packed size comes from the library
-    packed_state_words = int(os.environ.get("CBX_STATE_WORDS", "0")) or None
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
     for s in range(W):
         b.step(tape_a[s], tape_d[s])
     b.stats_reset()
     b.enable_timing(True)
     launches0 = b.launch_count
     torch.cuda.synchronize()
-    if rank == 0:
+    if clocks is not None:
         clocks.wait_first()
     if world > 1:
         dist.barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0, evc, ev1 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     torch.cuda.synchronize()
-    clocks.mark_begin()
+    if clocks is not None:
+        clocks.mark_begin()
     ev0.record()
     for s in range(W, W + K):
         b.step(tape_a[s], tape_d[s])
-    ev1.record()
-    torch.cuda.synchronize()
-    clocks.mark_end()
-    if world > 1:
-        dist.barrier()
-    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    evc.record()
+    # the only collective of the path (SURVEY.md 8e): one SUM all-reduce of the 16-slot episode-statistics vector per rollout
     stats = b.stats_tensor.clone()
     if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+    ev1.record()
+    torch.cuda.synchronize()
+    if clocks is not None:
+        clocks.mark_end()
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1), evc.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(stats, op=dist.ReduceOp.SUM)  # the only collective of the path: per-rollout episode statistics
-    clk = clocks.stop() if rank == 0 else None
-    total_ms = float(ms.item())
+    total_ms, coll_ms = (float(x) for x in ms.tolist())
     launches = b.launch_count - launches0
     kernel_ms, kernel_n = b.step_kernel_ms()
     kinfo = b.kernel_info()
     b.enable_timing(False)
-
-    # ---- e2e: the same step through the public API with HOST action buffers and host-side results ----
-    # host action buffers in page-locked memory (what a host-side policy loop would hand over)
-    CH = min(K, 64)  # the tape reaches the host in chunks (bounded page-locked memory); only the step_host calls are timed
-
-    def run_e2e(dtype):
-        """K host-buffer steps of a fresh batch with action elements of `dtype`; -> seconds (max over ranks)."""
-        h_a = torch.empty((CH, n, aw), dtype=dtype, pin_memory=True)
-        h_d = torch.empty((CH, n, 12), dtype=dtype, pin_memory=True) if has_def else None
-        h_an, h_dn = h_a.numpy(), (h_d.numpy() if has_def else [None] * CH)
-        b2 = Batch(comp, cfg, counts, device=local)
-        b2.reset()
-        for s in range(W):
-            b2.step(tape_a[s], tape_d[s])
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        secs = 0.0
-        out = None
-        for c0 in range(0, K, CH):
-            c1 = min(K, c0 + CH)
-            h_a[: c1 - c0].copy_(tape_a[W + c0:W + c1].to(dtype))
-            if has_def:
-                h_d[: c1 - c0].copy_(tape_d[W + c0:W + c1].to(dtype))
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            for s in range(c1 - c0):
-                out = b2.step_host(h_an[s], h_dn[s])
-            secs += time.perf_counter() - t0
-        assert out["att_reward"].shape[0] == n
-        # the host-side results must be the device's (the kernel wrote both)
-        assert (out["att_reward"] == b2.numpy("att_reward")).all() and (out["def_truncated"] == b2.numpy("def_truncated")).all()
-        b2.close()
-        t = torch.tensor([secs], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    e2e_s = run_e2e(torch.int16)
-    e2e32_s = run_e2e(torch.int32)
-
+    b.close()
+    out = {"comp": comp, "cfg": cfg, "counts": counts, "n": n, "tape_a": tape_a, "tape_d": tape_d, "aw": aw, "has_def": has_def,
+           "factored": factored, "multi": multi, "total_ms": total_ms, "collective_ms": coll_ms, "launches": launches,
+           "kernel_ms": kernel_ms, "kernel_n": kernel_n, "kinfo": kinfo, "stats": stats.cpu().numpy()}
     if rank == 0:
-        from marlon_b200 import _lib  # noqa: F401
-
         peak, peak_kind = measured_peak_gbs()
-        # packed per-env state words: ask the library through the export of the layout (S) -- state array bytes / n_pad
+        packed_state_words = int(os.environ.get("CBX_STATE_WORDS", "0")) or None
         if multi:  # padded layout: the largest scenario's dimensions, as the library lays the batch out
             import copy
 
@@ -413,51 +428,322 @@ def run_ours(args):
             big.n_services = max(c.n_services for c in comp)
             S_packed = packed_state_words or max(_packed_state_words(c, cfg) for c in comp)
             ab = algorithmic_bytes_per_env_step(big, cfg, S_packed)
+            ref_comp = big
         else:
             S_packed = packed_state_words or _packed_state_words(comp, cfg)
             ab = algorithmic_bytes_per_env_step(comp, cfg, S_packed)
+            ref_comp = comp
+        if kinfo["name"] == "cbx_wide_kernel":  # in-place kernel: only the words a step has to touch count
+            rw, ro = touched_state_words(ref_comp, cfg)
+            ab["state_rw_full_tile"] = ab["state_rw"]
+            ab["total"] += 4 * (2 * rw + ro) - ab["state_rw"]
+            ab["state_rw"] = 4 * (2 * rw + ro)
+            ab["state_note"] = "in-place kernel: wrapper/header/shadow words read+written, observation sources read once"
         achieved = ab["total"] * n / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else None
         total_envs = n * world
-        line = {
-            "metric": "attacker+defender env-steps/sec", "value": total_envs * K / (total_ms * 1e-3), "unit": "env-steps/s",
-            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOADS[args.workload] + ", " + ("factored" if factored else "dense int8")
-                                   + " action masks, random valid actions",
-                       "envs_per_gpu": n, "total_envs": total_envs, "parallelism": f"env-sharded x{world}, no data-path collective",
-                       "l2": "per-step output (%.0f MB/GPU) larger than the 126 MB L2; no flush needed" % (ab["total"] * n / 1e6),
-                       "algorithmic_bytes_per_env_step": ab},
+        out.update({
+            "value": total_envs * K / (total_ms * 1e-3), "ms_per_step": total_ms / K, "total_envs": total_envs, "ab": ab,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                         "traffic": ncu_traffic(kinfo["name"], n, factored) if args.workload == "toyctf" else None,
+                         "traffic": ncu_traffic(kinfo["name"], workload, n, factored),
                          "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
-                         "kernel": kinfo["name"], "kernel_launch": kinfo, "kernel_ms": kernel_ms, "kernel_launches_timed": kernel_n},
-            "e2e": {"value": total_envs * K / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": n * (aw + (12 if has_def else 0)) * 2,
-                    "d2h_bytes_per_step": n * 12,
-                    "int32_actions": {"value": total_envs * K / e2e32_s, "h2d_bytes_per_step": n * (aw + (12 if has_def else 0)) * 4},
-                    "note": "cbx_batch_step_host_i16 per step with HOST action buffers (int16 elements) in page-locked memory: the step "
-                            "kernel reads each tile's actions over PCIe in place (TMA bulk loads from the mapped host buffers; "
-                            "h2d_bytes_per_step is what crosses the link) and writes rewards + done flags (d2h_bytes_per_step) straight "
-                            "into a rotating page-locked result buffer, stream sync; int32_actions = the same through "
-                            "cbx_batch_step_host; observations stay in HBM as torch tensors (consumers are GPU policies)"},
-            "gpu_launches": launches,
+                         "kernel": kinfo["name"], "kernel_launch": kinfo, "kernel_ms": kernel_ms, "kernel_launches_timed": kernel_n}})
+    return out
+
+
+class HostTape:
+    """The action tape in page-locked HOST memory, CH steps at a time (bounded pinned memory); refills are outside the timed calls."""
+
+    def __init__(self, m, dtype, rows=None, CH=64):
+        import torch
+
+        self.m, self.dtype, self.CH = m, dtype, CH
+        self.rows = rows if rows is not None else slice(None)
+        n = m["tape_a"][0][self.rows].shape[0]
+        self.h_a = torch.empty((CH, n, m["aw"]), dtype=dtype, pin_memory=True)
+        self.h_d = torch.empty((CH, n, 12), dtype=dtype, pin_memory=True) if m["has_def"] else None
+        self.a_np = self.h_a.numpy()
+        self.d_np = self.h_d.numpy() if m["has_def"] else None
+        self.base = -1
+
+    def get(self, s):
+        """-> (attacker actions, defender actions or None) of tape step s as numpy views of the pinned chunk."""
+        import torch
+
+        c0 = (s // self.CH) * self.CH
+        if c0 != self.base:
+            c1 = min(len(self.m["tape_a"]), c0 + self.CH)
+            self.h_a[: c1 - c0].copy_(self.m["tape_a"][c0:c1, self.rows].to(self.dtype))
+            if self.h_d is not None:
+                self.h_d[: c1 - c0].copy_(self.m["tape_d"][c0:c1, self.rows].to(self.dtype))
+            torch.cuda.synchronize()
+            self.base = c0
+        return self.a_np[s - c0], (self.d_np[s - c0] if self.d_np is not None else None)
+
+
+def _max_over_ranks(secs, world, dev):
+    import torch
+    import torch.distributed as dist
+
+    t = torch.tensor([secs], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def e2e_results_only(m, K, W, dtype, world, local, dev):
+    """K host-buffer steps (cbx_batch_step_host[_i16]) of a fresh batch; W untimed calls of the SAME entry point first, all
+    allocations done before (host_prepare).  -> seconds, max over ranks."""
+    import torch
+    import torch.distributed as dist
+
+    from marlon_b200.batch import Batch
+
+    tape = HostTape(m, dtype)
+    b2 = Batch(m["comp"], m["cfg"], m["counts"], device=local)
+    b2.reset()
+    b2.host_prepare()
+    for s in range(W):
+        b2.step_host(*tape.get(s))
+    tape.get(W)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    secs, out = 0.0, None
+    s = W
+    while s < W + K:
+        tape.get(s)  # refill (untimed) when s enters a new chunk
+        e = min(W + K, (s // tape.CH + 1) * tape.CH)
+        t0 = time.perf_counter()
+        for q in range(s, e):
+            out = b2.step_host(*tape.get(q))
+        secs += time.perf_counter() - t0
+        s = e
+    n = m["n"]
+    assert out["att_reward"].shape[0] == n
+    # the host-side results must be the device's (the kernel wrote both)
+    assert (out["att_reward"] == b2.numpy("att_reward")).all() and (out["def_truncated"] == b2.numpy("def_truncated")).all()
+    b2.close()
+    return _max_over_ranks(secs, world, dev)
+
+
+def e2e_obs_factored(m, K, W, world, local, dev, halves):
+    """Host-buffer steps that also bring the observation a host-side policy needs to page-locked host memory every step:
+    scalars, leaked credentials, credential cache, property matrix, privilege levels, owned bits (= the factored action masks,
+    SURVEY.md A.4), the defender's observation, rewards and done flags (cbx_batch_fetch_host).  halves = 1: step, fetch,
+    synchronise.  halves = 2: the envs are two half batches on two streams, so one half's copies overlap the other half's
+    step (what a host loop that acts on half A while half B steps would see).  -> (seconds max over ranks, D2H bytes/step)."""
+    import torch
+    import torch.distributed as dist
+
+    from marlon_b200 import _abi
+    from marlon_b200.batch import Batch
+
+    n = m["n"]
+    if m["multi"] or n % (64 * halves):
+        return None, 0
+    h = n // halves
+    import copy
+
+    parts = []
+    for q in range(halves):
+        cfg = copy.copy(m["cfg"])
+        cfg.env_index_base = m["cfg"].env_index_base + q * h
+        bq = Batch(m["comp"], cfg, h, device=local)
+        bq.reset()
+        bq.host_prepare()
+        parts.append((bq, HostTape(m, torch.int16, rows=slice(q * h, (q + 1) * h)), torch.cuda.Stream(device=dev)))
+    fields = _abi.F_OBS_FACTORED | _abi.F_RESULTS
+    d2h = 0
+
+    def one(s):
+        nonlocal d2h
+        got = []
+        for bq, tape, st in parts:
+            a, d = tape.get(s)
+            with torch.cuda.stream(st):
+                bq.step_host(a, d, sync=False)
+                got.append(bq.fetch_host(fields, sync=False))
+        for _, _, st in parts:
+            st.synchronize()
+        d2h = sum(sum(v.nbytes for k, v in g.items()) for g in got)
+        return got
+
+    for s in range(W):
+        one(s)
+    for _, tape, _ in parts:
+        tape.get(W)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    secs, s, got = 0.0, W, None
+    CH = parts[0][1].CH
+    while s < W + K:
+        for _, tape, _ in parts:
+            tape.get(s)
+        e = min(W + K, (s // CH + 1) * CH)
+        t0 = time.perf_counter()
+        for q in range(s, e):
+            got = one(q)
+        secs += time.perf_counter() - t0
+        s = e
+    # what reached the host is what the device holds
+    for (bq, _, _), g in zip(parts, got):
+        assert (g["discovered_nodes_properties"] == bq.numpy("discovered_nodes_properties")).all()
+        assert (g["att_reward"] == bq.numpy("att_reward")).all()
+        bq.close()
+    return _max_over_ranks(secs, world, dev), d2h
+
+
+def e2e_vecenv(m, K, W, world, local, dev, observations):
+    """The SB3 VecEnv adapter: attacker_vec_env.step then defender_vec_env.step per env-step pair (marl_algorithm.py:43-49) on
+    host int64 action arrays (what a policy's .cpu().numpy() hands over), infos built.  observations="torch": the policy is on
+    the GPU, only rewards / done flags cross PCIe.  "numpy": the full stacked dense observation goes to the host every step."""
+    import torch
+    import torch.distributed as dist
+
+    from marlon_b200.universe import MultiAgentUniversalEnv
+
+    n = m["n"]
+    u = MultiAgentUniversalEnv("CyberBattleToyCtf-v0", n, device=local, maximum_node_count=12, maximum_total_credentials=10,
+                               maximum_discoverable_credentials_per_action=5, max_timesteps=2000, emit_terminal_obs=True)
+    av = u.vec_env("attacker", observations=observations, terminal_observations="truncated")
+    dv = u.vec_env("defender", observations=observations, terminal_observations="truncated")
+    av.reset()
+    dv.reset()
+    ta = m["tape_a"][: W + K].cpu().numpy().astype(np.int64)
+    td = m["tape_d"][: W + K].cpu().numpy().astype(np.int64)
+    for s in range(W):
+        av.step(ta[s])
+        dv.step(td[s])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for s in range(W, W + K):
+        obs, r, done, infos = av.step(ta[s])
+        dobs, dr, ddone, dinfos = dv.step(td[s])
+    secs = time.perf_counter() - t0
+    assert r.shape[0] == n and len(infos) == n
+    u.close()
+    return _max_over_ranks(secs, world, dev)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from marlon_b200 import _abi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    pin = pin_to_gpu_numa(local)
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    K, W = args.steps, args.warmup
+    clocks = ClockSampler(local) if rank == 0 else None
+    if clocks:
+        clocks.start()
+    m = measure_device(args, args.workload, args.envs_per_gpu, K, W, world, rank, local, dev, clocks)
+    clk = clocks.stop() if clocks else None
+    n, aw, has_def = m["n"], m["aw"], m["has_def"]
+
+    # ---- e2e: the same step through the public API with HOST action buffers and host-side results ----
+    e2e = None
+    if not args.no_e2e and has_def and not m["multi"]:
+        Ke = K
+        e2e_s = e2e_results_only(m, Ke, W, torch.int16, world, local, dev)
+        e2e32_s = e2e_results_only(m, Ke, W, torch.int32, world, local, dev)
+        Ko = min(K, 200)
+        obs2_s, d2h_obs = e2e_obs_factored(m, Ko, W, world, local, dev, halves=2)
+        obs1_s, _ = e2e_obs_factored(m, Ko, W, world, local, dev, halves=1)
+        vt_s = vn_s = None
+        Kv, Kn = min(K, 100), min(K, 5)
+        if args.workload == "toyctf" and not m["factored"]:
+            vt_s = e2e_vecenv(m, Kv, W, world, local, dev, "torch")
+            if world == 1:
+                vn_s = e2e_vecenv(m, Kn, min(W, 3), world, local, dev, "numpy")
+        total_envs = n * world
+        act_b = n * (aw + 12)
+        e2e = {"value": total_envs * Ke / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": act_b * 2, "d2h_bytes_per_step": n * 12,
+               "which": "results_only_int16",
+               "variants": {
+                   "results_only_int16": {"value": total_envs * Ke / e2e_s, "steps": Ke, "h2d_bytes_per_step": act_b * 2, "d2h_bytes_per_step": n * 12},
+                   "results_only_int32": {"value": total_envs * Ke / e2e32_s, "steps": Ke, "h2d_bytes_per_step": act_b * 4, "d2h_bytes_per_step": n * 12},
+                   "obs_factored_two_halves": None if obs2_s is None else {
+                       "value": total_envs * Ko / obs2_s, "steps": Ko, "h2d_bytes_per_step": act_b * 2, "d2h_bytes_per_step": d2h_obs},
+                   "obs_factored_sequential": None if obs1_s is None else {
+                       "value": total_envs * Ko / obs1_s, "steps": Ko, "h2d_bytes_per_step": act_b * 2, "d2h_bytes_per_step": d2h_obs},
+                   "vecenv_torch_obs": None if vt_s is None else {
+                       "value": total_envs * Kv / vt_s, "steps": Kv, "h2d_bytes_per_step": act_b * 4, "d2h_bytes_per_step": n * 24},
+                   "vecenv_numpy_dense_obs": None if vn_s is None else {
+                       "value": total_envs * Kn / vn_s, "steps": Kn, "h2d_bytes_per_step": act_b * 4,
+                       "d2h_bytes_per_step": n * (m["ab"]["attacker_obs"] + m["ab"]["masks"] + m["ab"]["defender_obs"] + 24) if rank == 0 else None}},
+               "note": "value = results_only_int16: cbx_batch_step_host_i16 per step with HOST action buffers (int16 elements) in "
+                       "page-locked memory -- the kernel reads each tile's actions over PCIe in place (TMA bulk loads from the mapped "
+                       "host buffers) and writes rewards + done flags straight into a rotating page-locked result block, stream sync; "
+                       "observations stay in HBM as torch tensors (the consumer is a GPU-resident policy).  For a HOST-side policy "
+                       "the observation has to cross PCIe as well: obs_factored_* bring every small field + the factored masks + the "
+                       "defender observation to pinned host memory each step (cbx_batch_fetch_host; two_halves overlaps one half "
+                       "batch's copies with the other's step), vecenv_* go through the SB3 VecEnv adapter (attacker step + defender "
+                       "step, int64 numpy actions, infos built; numpy_dense_obs copies the full dense observation, 12.4 KB per env, "
+                       "every step).  All variants: allocations and W warm-up calls of the same entry point before the clock starts."}
+
+    # ---- config 4 as BASELINE.json names it, when the job has more than one GPU: Chain-100, 1 048 576 envs in total ----
+    cfg4 = None
+    if world > 1 and not args.no_config4:
+        K4 = min(K, 50)
+        per = (1048576 // world) // 32 * 32
+        m4 = measure_device(args, "chain100", per, K4, W, world, rank, local, dev)
+        if rank == 0:
+            cfg4 = {"workload": workload_label("chain100", True), "envs_per_gpu": m4["n"], "total_envs": m4["total_envs"], "steps": K4,
+                    "value": m4["value"], "unit": "env-steps/s", "ms_per_step": m4["ms_per_step"], "collective_ms": m4["collective_ms"],
+                    "roofline": m4["roofline"], "algorithmic_bytes_per_env_step": m4["ab"], "gpu_launches": m4["launches"]}
+
+    if rank == 0:
+        ab = m["ab"]
+        line = {
+            "metric": "attacker+defender env-steps/sec", "value": m["value"], "unit": "env-steps/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": workload_label(args.workload, m["factored"]),
+                       "envs_per_gpu": n, "total_envs": m["total_envs"], "parallelism": f"env-sharded x{world}, no data-path collective",
+                       "l2": "per-step output (%.0f MB/GPU) larger than the 126 MB L2; no flush needed" % (ab["total"] * n / 1e6),
+                       "algorithmic_bytes_per_env_step": ab, "numa": pin},
+            "roofline": m["roofline"],
+            "collective_ms": m["collective_ms"],
+            "collective": "one SUM all-reduce of the 16-slot fp64 episode-statistics vector per K-step rollout, inside the timed region"
+                          + ("" if world > 1 else " (single rank: the clone only, nothing to reduce)"),
+            "gpu_launches": m["launches"],
             "clocks": clk,
-            "episode_stats": {k: float(v) for k, v in zip(_abi.STAT_NAMES, stats.cpu().numpy())},
+            "episode_stats": {k: float(v) for k, v in zip(_abi.STAT_NAMES, m["stats"])},
         }
+        if e2e:
+            line["e2e"] = e2e
+        if cfg4:
+            line["config4"] = cfg4
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(seconds=args.cpu_seconds)
+            pr = python_reference_baseline()
+            if pr:
+                line["cpu_baseline"]["python_reference"] = pr
         print(json.dumps(line))
-    b.close()
     if world > 1:
         dist.destroy_process_group()
 
 
-def ncu_traffic(kernel, envs, factored):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the step kernel from the committed `ncu --set full` capture
-    (profiles/ncu_traffic.json, written by scripts/ncu_summary.py); None when no capture matches this kernel and workload."""
+def ncu_traffic(kernel, workload, envs, factored):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the step kernel from the committed `ncu --set full` captures
+    (profiles/ncu_traffic.json, written by scripts/ncu_summary.py: one entry per kernel + workload); None when no capture
+    matches this kernel, workload and batch size."""
     try:
-        t = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")))
-        if t.get("kernel") == kernel and int(t.get("envs", -1)) == int(envs) and bool(t.get("factored", False)) == bool(factored):
-            return float(t["dram_bytes_per_launch"])
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        for c in (t if isinstance(t, list) else [t]):
+            if (c.get("kernel") == kernel and c.get("workload", "toyctf") == workload and int(c.get("envs", -1)) == int(envs)
+                    and bool(c.get("factored", False)) == bool(factored)):
+                return float(c["dram_bytes_per_launch"])
     except Exception:
         pass
     return None
@@ -486,6 +772,8 @@ def main():
     ap.add_argument("--factored", action="store_true", help="factored masks instead of dense int8 masks")
     ap.add_argument("--workload", default="toyctf", choices=sorted(WORKLOADS), help="toyctf = the headline configuration")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer legs (kernel experiments)")
+    ap.add_argument("--no-config4", action="store_true", help="multi-GPU runs: skip the Chain-100 / 1M-env block")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

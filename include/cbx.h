@@ -353,6 +353,46 @@ int cbx_batch_notify_reset(cbx_batch* b, const uint8_t* mask_or_null, int who, d
 int cbx_batch_step_host(cbx_batch* b, const int32_t* host_attacker_actions, const int32_t* host_defender_actions,
                         void* host_out, size_t host_out_bytes, void* cuda_stream);
 
+/* The general form: elem_bytes = 4 (int32 action elements) or 2 (int16); flags = CBX_HOST_NOSYNC: only enqueue -- the call
+ * returns before the buffers are used, all three must be page-locked and stay untouched until the caller has synchronised
+ * the stream (lets a host loop overlap this batch's step with another batch's copies). */
+enum { CBX_HOST_NOSYNC = 1 };
+int cbx_batch_step_host_ex(cbx_batch* b, const void* host_attacker_actions, const void* host_defender_actions, int elem_bytes,
+                           void* host_out, size_t host_out_bytes, int flags, void* cuda_stream);
+
+/* Allocate what the host-buffer calls need -- page-locked staging for pageable caller buffers, device action buffers for
+ * the explicit-copy mode -- NOW instead of inside the first cbx_batch_step_host call (which otherwise does it, all or
+ * nothing).  A loop that is timed calls this (and a few untimed steps) first.  Idempotent. */
+int cbx_batch_host_prepare(cbx_batch* b);
+
+/* Observation arrays of the last step to HOST memory in one call: what a host-side policy (the reference's
+ * obs_as_tensor(self._last_obs) consumer, baseline_marlon_agent.py:113-116) reads back each step.  `fields` selects arrays
+ * (CBX_F_*); they are packed one after the other, each [n_envs, per-env size] row-major in its reference dtype, in the
+ * order of the CBX_F_* bits, every array starting on a 256-byte boundary.  cbx_batch_fetch_host_layout fills
+ * offsets[k] (byte offset of the array of bit k, -1 if not selected or not materialised) and returns the total size.
+ * The copies are enqueued on the stream (page-locked host_out: asynchronous); nothing is synchronised. */
+enum {
+  CBX_F_SCALARS = 1 << 0,      /* int32 [n,8] */
+  CBX_F_LEAKED = 1 << 1,       /* int32 [n,4*LEAK] */
+  CBX_F_CACHEM = 1 << 2,       /* int32 [n,2*C] */
+  CBX_F_PROPS = 1 << 3,        /* int32 [n,N*n_props] */
+  CBX_F_PRIV = 1 << 4,         /* int32 [n,N] */
+  CBX_F_OWNED_BITS = 1 << 5,   /* uint32 [n,owned_words]: with scalars[5], scalars[6] the factored action masks */
+  CBX_F_LOCAL = 1 << 6,        /* int8 dense masks (dense mode only) */
+  CBX_F_REMOTE = 1 << 7,
+  CBX_F_CONNECT = 1 << 8,
+  CBX_F_DEF_INFECTED = 1 << 9, /* int8 defender observation (def_enabled only) */
+  CBX_F_DEF_FW_IN = 1 << 10,
+  CBX_F_DEF_FW_OUT = 1 << 11,
+  CBX_F_DEF_SERVICES = 1 << 12,
+  CBX_F_RESULTS = 1 << 13,     /* float att_reward[n], float def_reward[n], uint8 att_terminated[n], att_truncated[n],
+                                  def_terminated[n], def_truncated[n] (cbx_batch_step_host's layout) */
+  CBX_F_COUNT = 14,
+  CBX_F_OBS_FACTORED = 0x3F | (0xF << 9)  /* every small field + factored masks + defender observation */
+};
+int64_t cbx_batch_fetch_host_layout(const cbx_batch* b, uint32_t fields, int64_t* offsets /* [CBX_F_COUNT] */);
+int cbx_batch_fetch_host(cbx_batch* b, uint32_t fields, void* host_out, size_t host_out_bytes, void* cuda_stream);
+
 /* The same two calls with int16 action elements (every component of both MultiDiscrete spaces is far below 32768):
  * half the bytes over PCIe, which is what bounds cbx_batch_step_host.  The reference hands int64 numpy arrays from the
  * policy to env.step (baseline_marlon_agent.py:118-131), so an adapter narrows them either way. */
@@ -398,6 +438,10 @@ int cbx_gae(const float* rewards, const float* values, const uint8_t* episode_st
  * env, 2 ToyCtf(12,10) static, 3 Chain-10(12,12) static); [7] bit 0 TMA staging enabled, bit 1 dynamic tile order (tiles after a warp's first are drawn
  * from a global ticket counter instead of a fixed stride). */
 int cbx_batch_kernel_info(const cbx_batch* b, int32_t* out8);
+
+/* Parity instrumentation: the dynamic tile order's global counters {tickets handed out, CTAs finished}; both must read 0
+ * between launches (the last CTA of a launch resets them).  Synchronises the device. */
+int cbx_batch_tile_counter(cbx_batch* b, int32_t* out2);
 
 /* Instrumentation: per-phase SM cycle counters of the step kernel, summed over CTAs (thread 0 of each CTA):
  * [0] prologue [1] state-tile load [2] attacker logic [3] terminal observations [4] reset/defender logic + descriptors

@@ -29,6 +29,16 @@ X_NAMES = ["stepcount", "done", "n_discovered", "n_cached", "att_timesteps", "de
            "live_imaging_count", "shadow_imaging_count", "prev_shadow_imaging_count"]
 
 
+# cbx_batch_fetch_host field bits (CBX_F_*), in packing order, with the view each one copies
+F_NAMES = ["scalars", "leaked_credentials", "credential_cache_matrix", "discovered_nodes_properties", "nodes_privilegelevel",
+           "owned_bits", "local_vulnerability", "remote_vulnerability", "connect", "def_infected_nodes", "def_incoming_firewall",
+           "def_outgoing_firewall", "def_services_status", "results"]
+F_COUNT = 14
+F_RESULTS = 1 << 13
+F_OBS_FACTORED = 0x3F | (0xF << 9)
+F_OBS_DENSE = F_OBS_FACTORED | (0x7 << 6)
+
+
 class Config(C.Structure):
     _fields_ = [
         ("abi_version", C.c_int32),

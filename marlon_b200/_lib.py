@@ -19,6 +19,7 @@ SYMBOLS = [
     "cbx_batch_sample_actions", "cbx_batch_views", "cbx_batch_stats_reset", "cbx_export_words",
     "cbx_batch_export_state", "cbx_batch_launch_count", "cbx_batch_enable_timing", "cbx_batch_step_kernel_ms",
     "cbx_abi_sizeof", "cbx_batch_step_ex", "cbx_batch_reset_ex", "cbx_batch_phase_cycles", "cbx_batch_notify_reset", "cbx_batch_kernel_info", "cbx_batch_create_multi", "cbx_batch_export_words", "cbx_gae",
+    "cbx_batch_host_prepare", "cbx_batch_fetch_host_layout", "cbx_batch_fetch_host", "cbx_batch_step_host_ex", "cbx_batch_tile_counter",
 ]
 
 
@@ -70,6 +71,12 @@ def load():
     L.cbx_batch_export_words.restype = C.c_int64
     L.cbx_batch_export_words.argtypes = [vp]
     L.cbx_gae.argtypes = [vp, vp, vp, vp, vp, C.c_double, C.c_double, C.c_int, i64, vp, vp, vp]
+    L.cbx_batch_host_prepare.argtypes = [vp]
+    L.cbx_batch_tile_counter.argtypes = [vp, vp]
+    L.cbx_batch_step_host_ex.argtypes = [vp, vp, vp, C.c_int, vp, C.c_size_t, C.c_int, vp]
+    L.cbx_batch_fetch_host_layout.restype = C.c_int64
+    L.cbx_batch_fetch_host_layout.argtypes = [vp, C.c_uint32, C.POINTER(C.c_int64)]
+    L.cbx_batch_fetch_host.argtypes = [vp, C.c_uint32, vp, C.c_size_t, vp]
     L.cbx_abi_sizeof.restype = C.c_size_t
     L.cbx_abi_sizeof.argtypes = [C.c_int]
     if L.cbx_abi_version() != _abi.ABI_VERSION:

@@ -179,32 +179,91 @@ class Batch:
                                                  C.byref(tape) if tape is not None else None, int(who), self._stream()))
         self._keep = [a, d, su, du]  # keep inputs alive until the next call (stream-ordered use)
 
-    def step_host(self, attacker_actions: np.ndarray, defender_actions: Optional[np.ndarray] = None):
+    def host_prepare(self):
+        """Allocate everything the host-buffer calls need (the library's staging, the page-locked result ring) now, so that no
+        ``step_host`` call pays for it; ``step_host`` calls it on first use.  A timed loop calls this, and warms up, first."""
+        if getattr(self, "_host_out", None) is not None:
+            return
+        n = self.n_envs
+        with self._torch.cuda.device(self.device):
+            _lib.check(self._L.cbx_batch_host_prepare(self._h))
+        self._host_out = [self._torch.empty(n * 12, dtype=self._torch.uint8, pin_memory=True).numpy() for _ in range(3)]
+        self._host_views = [{
+            "att_reward": o[: 4 * n].view(np.float32), "def_reward": o[4 * n: 8 * n].view(np.float32),
+            "att_terminated": o[8 * n: 9 * n], "att_truncated": o[9 * n: 10 * n],
+            "def_terminated": o[10 * n: 11 * n], "def_truncated": o[11 * n: 12 * n]} for o in self._host_out]
+        self._host_turn = 0
+
+    def step_host(self, attacker_actions: np.ndarray, defender_actions: Optional[np.ndarray] = None, sync: bool = True):
         """The same step through HOST buffers; synchronous.  Page-locked action arrays (``torch.empty(..., pin_memory=True)``)
         are read by the kernel in place over PCIe; pageable ones go through the library's pinned staging.  The rewards and
         done flags land in one of three page-locked result buffers used in rotation: the returned arrays are views of it and
         stay valid until the third call after this one (copy them to keep them longer).  With both agents stepping and
         page-locked actions the kernel writes the results into that buffer itself (no copy back).  int16 action arrays
-        are taken as they are (``cbx_batch_step_host_i16``: half the PCIe bytes); anything else is converted to int32."""
+        are taken as they are (``cbx_batch_step_host_i16``: half the PCIe bytes); anything else is converted to int32.
+        Observations stay in HBM (``self.tensors``); ``fetch_host`` brings selected ones to the host.
+        ``sync=False`` (page-locked action arrays only) just enqueues the step on the current stream: the results are valid
+        after the caller has synchronised it -- a host loop can overlap this batch's step with another batch's copies."""
         i16 = (getattr(attacker_actions, "dtype", None) == np.int16
                and (defender_actions is None or getattr(defender_actions, "dtype", None) == np.int16))
         dt = np.int16 if i16 else np.int32
         a = np.ascontiguousarray(attacker_actions, dtype=dt)
         d = None if defender_actions is None else np.ascontiguousarray(defender_actions, dtype=dt)
         n = self.n_envs
+        # the library reads n * width elements from these pointers: a wrong shape would run past the caller's buffer
+        if a.shape != (n, self.att_width):
+            raise ValueError(f"attacker actions: expected shape {(n, self.att_width)}, got {a.shape}")
+        if d is not None and d.shape != (n, 12):
+            raise ValueError(f"defender actions: expected shape {(n, 12)}, got {d.shape}")
         if getattr(self, "_host_out", None) is None:
-            self._host_out = [self._torch.empty(n * 12, dtype=self._torch.uint8, pin_memory=True).numpy() for _ in range(3)]
-            self._host_views = [{
-                "att_reward": o[: 4 * n].view(np.float32), "def_reward": o[4 * n: 8 * n].view(np.float32),
-                "att_terminated": o[8 * n: 9 * n], "att_truncated": o[9 * n: 10 * n],
-                "def_terminated": o[10 * n: 11 * n], "def_truncated": o[11 * n: 12 * n]} for o in self._host_out]
-            self._host_turn = 0
+            self.host_prepare()
         out, views = self._host_out[self._host_turn], self._host_views[self._host_turn]
         self._host_turn = (self._host_turn + 1) % 3
         with self._torch.cuda.device(self.device):
-            fn = self._L.cbx_batch_step_host_i16 if i16 else self._L.cbx_batch_step_host
-            _lib.check(fn(self._h, a.ctypes.data, None if d is None else d.ctypes.data, out.ctypes.data, out.nbytes, self._stream()))
+            _lib.check(self._L.cbx_batch_step_host_ex(self._h, a.ctypes.data, None if d is None else d.ctypes.data, 2 if i16 else 4,
+                                                      out.ctypes.data, out.nbytes, 0 if sync else 1, self._stream()))
+        if not sync:
+            self._keep = [a, d]
         return dict(views)
+
+    def fetch_host(self, fields: int = _abi.F_OBS_FACTORED | _abi.F_RESULTS, out: Optional[np.ndarray] = None, sync: bool = True):
+        """Selected observation arrays of the last step in HOST memory with one call (``cbx_batch_fetch_host``): what a
+        host-side policy reads back each step.  -> dict name -> numpy view of a page-locked block (`out`, or one of two
+        internal blocks used in turn: a view stays valid until the second ``fetch_host`` after it).  ``sync=False`` only
+        enqueues the copies on the current stream; synchronise before reading."""
+        offs = (C.c_int64 * _abi.F_COUNT)()
+        total = int(self._L.cbx_batch_fetch_host_layout(self._h, int(fields), offs))
+        if out is None:
+            ring = getattr(self, "_fetch_ring", None)
+            if ring is None or ring[0].nbytes < total:
+                ring = self._fetch_ring = [self._torch.empty(max(total, 256), dtype=self._torch.uint8, pin_memory=True).numpy()
+                                           for _ in range(2)]
+                self._fetch_turn = 0
+            out = ring[self._fetch_turn]
+            self._fetch_turn ^= 1
+        elif out.nbytes < total:
+            raise ValueError(f"out needs {total} bytes")
+        with self._torch.cuda.device(self.device):
+            _lib.check(self._L.cbx_batch_fetch_host(self._h, int(fields), out.ctypes.data, out.nbytes, self._stream()))
+            if sync:
+                self._torch.cuda.current_stream(self.device).synchronize()
+        n, res = self.n_envs, {}
+        specs = _abi.view_specs(self.views, self.cfg)
+        flat = out.reshape(-1).view(np.uint8)
+        for k, name in enumerate(_abi.F_NAMES):
+            o = int(offs[k])
+            if o < 0:
+                continue
+            if name == "results":
+                blk = flat[o:o + 12 * n]
+                res.update(att_reward=blk[:4 * n].view(np.float32), def_reward=blk[4 * n:8 * n].view(np.float32),
+                           att_terminated=blk[8 * n:9 * n], att_truncated=blk[9 * n:10 * n],
+                           def_terminated=blk[10 * n:11 * n], def_truncated=blk[11 * n:12 * n])
+                continue
+            shape, dt = specs[name]
+            nb = int(np.prod((n,) + tuple(shape))) * np.dtype(dt).itemsize
+            res[name] = flat[o:o + nb].view(dt).reshape((n,) + tuple(shape))
+        return res
 
     def sample_actions(self, seed: int = 0, attacker_out=None, defender_out=None):
         """Uniformly sampled VALID attacker actions (and uniform defender actions) for the current state, on device."""
@@ -264,6 +323,13 @@ class Batch:
         d["tma"] &= 1
         d["name"] = {1: "cbx_pipe_kernel", 2: "cbx_wide_kernel"}.get(d["pipelined"], "cbx_step_kernel")
         return d
+
+    def tile_counter(self):
+        """(tickets handed out, CTAs finished) of the dynamic tile order: (0, 0) between launches."""
+        out = (C.c_int32 * 2)()
+        with self._torch.cuda.device(self.device):
+            _lib.check(self._L.cbx_batch_tile_counter(self._h, out))
+        return int(out[0]), int(out[1])
 
     @property
     def launch_count(self) -> int:

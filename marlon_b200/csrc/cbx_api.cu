@@ -175,7 +175,8 @@ struct cbx_batch {
   uint32_t sample_step;
   // pinned staging for the host-buffer entry point
   int32_t *h_att, *h_def, *d_att, *d_def;
-  uint8_t *h_out, *d_out_unused;
+  uint8_t* h_out;
+  int host_ready;  // cbx_batch_host_prepare has allocated the five buffers above
   // kernel timing
   int timing;
   std::vector<cudaEvent_t> ev;
@@ -187,6 +188,18 @@ struct cbx_batch {
   int32_t* d_tile_scn;
   std::vector<uint32_t> init_state;
 };
+
+static void host_release(cbx_batch* b) {
+  if (b->h_att) cudaFreeHost(b->h_att);
+  if (b->h_def) cudaFreeHost(b->h_def);
+  if (b->h_out) cudaFreeHost(b->h_out);
+  if (b->d_att) cudaFree(b->d_att);
+  if (b->d_def) cudaFree(b->d_def);
+  b->h_att = b->h_def = b->d_att = b->d_def = nullptr;
+  b->h_out = nullptr;
+  b->host_ready = 0;
+}
+
 
 extern "C" {
 
@@ -260,7 +273,6 @@ static int compute_layout(const cbx_scenario* s, const cbx_config* cfg, int64_t 
                 s->max_leak, L->LEAK);  // ENV:430-435
   if (L->N > 255) return fail(CBX_ERR_UNSUPPORTED, "maximum_node_count %d > 255", L->N);
   if (L->C > 65535) return fail(CBX_ERR_UNSUPPORTED, "maximum_total_credentials %d > 65535", L->C);
-  if (L->LEAK > CBX_MAX_LEAK) L->LEAK = L->LEAK;  // staging grows with LEAK; checked against shared memory below
   if (s->ntriples > L->C)
     return fail(CBX_ERR_UNSUPPORTED, "scenario has %d distinct credentials but maximum_total_credentials is %d (the reference would emit out-of-space observations)",
                 s->ntriples, L->C);
@@ -380,7 +392,7 @@ static int create_impl(const cbx_scenario* const* scns, int n_scn, const int64_t
   cbx_batch* b = new cbx_batch();
   memset(&b->p, 0, sizeof(b->p));
   b->device = device; b->launches = 0; b->sample_step = 0; b->timing = 0; b->ev_used = 0; b->ms_sum = 0; b->ms_count = 0;
-  b->h_att = b->h_def = b->d_att = b->d_def = nullptr; b->h_out = nullptr; b->scn = s; b->d_tile_scn = nullptr;
+  b->h_att = b->h_def = b->d_att = b->d_def = nullptr; b->h_out = nullptr; b->host_ready = 0; b->scn = s; b->d_tile_scn = nullptr;
   size_t max_blob = s->blob.size();
   if (n_scn > 1) {  // padded layout: the maximum of every per-scenario dimension
     cbx_scenario& v = b->vscn;
@@ -421,7 +433,10 @@ static int create_impl(const cbx_scenario* const* scns, int n_scn, const int64_t
   K.d_rowc = make_fastdiv(L.N * L.P * L.C); K.d_C = make_fastdiv(L.C); K.d_n = make_fastdiv(L.n);
   K.d_6n = make_fastdiv(6 * L.n); K.d_svc = make_fastdiv(L.nservices > 0 ? L.nservices : 1);
   K.desc_words = 8 + L.OW + L.Wn;
+  K.debug_skip = 0;
+#ifdef CBX_EXPERIMENTS
   { const char* dbg = getenv("CBX_DEBUG_SKIP"); K.debug_skip = dbg ? atoi(dbg) : 0; }
+#endif
   auto gcd16 = [](int x) { int g = 16; while (x % g) g >>= 1; return g; };
   {
     const int row_r = L.N * L.R, row_c = L.N * L.P * L.C;
@@ -462,14 +477,17 @@ static int create_impl(const cbx_scenario* const* scns, int n_scn, const int64_t
     delete b;
     return fail(CBX_ERR_UNSUPPORTED, "scenario needs %d bytes of shared memory per CTA (> 227 KiB)", pl.total_bytes);
   }
-  const char* no_tma = getenv("CBX_NO_TMA");
-  b->use_tma = !(no_tma && no_tma[0] == '1');
+  b->use_tma = 1;
+#ifdef CBX_EXPERIMENTS  // plain-copy staging instead of TMA bulk copies: debugging aid, not in the release library
+  { const char* no_tma = getenv("CBX_NO_TMA"); b->use_tma = !(no_tma && no_tma[0] == '1'); }
+#endif
   int bps = 0;
   { cudaError_t e = cbx_kernel_attrs(b->smem_bytes, b->use_tma, b->p.enc.warp_env, &bps);
     if (e != cudaSuccess) { delete b; return fail(CBX_ERR_CUDA, "kernel attributes: %s", cudaGetErrorString(e)); } }
   if (bps < 1) { delete b; return fail(CBX_ERR_CUDA, "step kernel does not fit on an SM"); }
   int sms = 0;
-  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  { cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess) { delete b; return fail(CBX_ERR_CUDA, "cudaDeviceGetAttribute: %s", cudaGetErrorString(e)); } }
   b->grid = sms * bps;
   if (b->grid > b->p.n_tiles) b->grid = b->p.n_tiles;
   const char* gridenv = getenv("CBX_GRID");
@@ -638,11 +656,7 @@ int cbx_batch_destroy(cbx_batch* b) {
   if (!b) return CBX_OK;
   cudaSetDevice(b->device);
   for (void* p : b->allocs) cudaFree(p);
-  if (b->h_att) cudaFreeHost(b->h_att);
-  if (b->h_def) cudaFreeHost(b->h_def);
-  if (b->h_out) cudaFreeHost(b->h_out);
-  if (b->d_att) cudaFree(b->d_att);
-  if (b->d_def) cudaFree(b->d_def);
+  host_release(b);
   for (cudaEvent_t e : b->ev) cudaEventDestroy(e);
   delete b;
   return CBX_OK;
@@ -723,19 +737,44 @@ int cbx_batch_step_ex(cbx_batch* b, const int32_t* att, const int32_t* def, cons
 }
 
 static int step_host_impl(cbx_batch* b, const void* h_att, const void* h_def, size_t esz, void* host_out, size_t host_out_bytes,
-                          void* cuda_stream);
+                          int flags, void* cuda_stream);
+
+int cbx_batch_host_prepare(cbx_batch* b) {
+  if (!b) return fail(CBX_ERR_INVALID, "null batch");
+  if (b->host_ready) return CBX_OK;
+  CUDA_TRY(cudaSetDevice(b->device));
+  const size_t n = (size_t)b->p.n_envs;
+  cudaError_t e = cudaMallocHost((void**)&b->h_att, n * 10 * 4);
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&b->h_def, n * 12 * 4);
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&b->h_out, n * 12);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_att, n * 10 * 4);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_def, n * 12 * 4);
+  if (e != cudaSuccess) {  // all or nothing: a later call starts over instead of running on half of the buffers
+    host_release(b);
+    cudaGetLastError();
+    return fail(CBX_ERR_CUDA, "host staging buffers: %s", cudaGetErrorString(e));
+  }
+  b->host_ready = 1;
+  return CBX_OK;
+}
 
 int cbx_batch_step_host(cbx_batch* b, const int32_t* h_att, const int32_t* h_def, void* host_out, size_t host_out_bytes, void* cuda_stream) {
-  return step_host_impl(b, h_att, h_def, 4, host_out, host_out_bytes, cuda_stream);
+  return step_host_impl(b, h_att, h_def, 4, host_out, host_out_bytes, 0, cuda_stream);
 }
 
 int cbx_batch_step_host_i16(cbx_batch* b, const int16_t* h_att, const int16_t* h_def, void* host_out, size_t host_out_bytes,
                             void* cuda_stream) {
-  return step_host_impl(b, h_att, h_def, 2, host_out, host_out_bytes, cuda_stream);
+  return step_host_impl(b, h_att, h_def, 2, host_out, host_out_bytes, 0, cuda_stream);
+}
+
+int cbx_batch_step_host_ex(cbx_batch* b, const void* h_att, const void* h_def, int elem_bytes, void* host_out, size_t host_out_bytes,
+                           int flags, void* cuda_stream) {
+  if (elem_bytes != 2 && elem_bytes != 4) return fail(CBX_ERR_INVALID, "elem_bytes must be 2 (int16) or 4 (int32)");
+  return step_host_impl(b, h_att, h_def, (size_t)elem_bytes, host_out, host_out_bytes, flags, cuda_stream);
 }
 
 static int step_host_impl(cbx_batch* b, const void* h_att, const void* h_def, const size_t esz, void* host_out, size_t host_out_bytes,
-                          void* cuda_stream) {
+                          const int flags, void* cuda_stream) {
   if (!b || !h_att || !host_out) return fail(CBX_ERR_INVALID, "null argument");
   const cbx_config& c = b->p.cfg;
   const int64_t n = b->p.n_envs;
@@ -746,13 +785,7 @@ static int step_host_impl(cbx_batch* b, const void* h_att, const void* h_def, co
   if (host_out_bytes < out_bytes) return fail(CBX_ERR_INVALID, "host_out needs %zu bytes", out_bytes);
   CUDA_TRY(cudaSetDevice(b->device));
   cudaStream_t st = (cudaStream_t)cuda_stream;
-  if (!b->h_att) {
-    CUDA_TRY(cudaMallocHost((void**)&b->h_att, (size_t)n * 10 * 4));
-    CUDA_TRY(cudaMallocHost((void**)&b->h_def, (size_t)n * 12 * 4));
-    CUDA_TRY(cudaMallocHost((void**)&b->h_out, out_bytes));
-    CUDA_TRY(cudaMalloc((void**)&b->d_att, (size_t)n * 10 * 4));
-    CUDA_TRY(cudaMalloc((void**)&b->d_def, (size_t)n * 12 * 4));
-  }
+  if (!b->host_ready) { const int rc0 = cbx_batch_host_prepare(b); if (rc0) return rc0; }
   // caller buffers that are already page-locked go to the device directly; pageable ones through the pinned staging
   // one query per buffer: page-locked or not, and the address the device sees it at
   auto pinned_view = [](const void* ptr) -> void* {
@@ -765,6 +798,9 @@ static int step_host_impl(cbx_batch* b, const void* h_att, const void* h_def, co
   // preceding the launch.  Pageable buffers go through the library's pinned staging first.  CBX_HOST_ZEROCOPY=0 restores
   // the explicit H2D copies.
   static const bool zero_copy = [] { const char* e = getenv("CBX_HOST_ZEROCOPY"); return !(e && e[0] == '0'); }();
+  const bool nosync = flags & CBX_HOST_NOSYNC;
+  if (nosync && (!pinned_view(h_att) || (need_def && !pinned_view(h_def)) || !pinned_view(host_out)))
+    return fail(CBX_ERR_INVALID, "CBX_HOST_NOSYNC needs page-locked action and result buffers (the call returns before they are used)");
   const void* src_att = h_att;
   const void* k_att = pinned_view(h_att);
   if (!k_att) { memcpy(b->h_att, h_att, (size_t)n * aw * esz); src_att = b->h_att; k_att = pinned_view(b->h_att); }
@@ -808,11 +844,77 @@ static int step_host_impl(cbx_batch* b, const void* h_att, const void* h_def, co
     CUDA_TRY(cudaMemcpyAsync(o + (size_t)n * 10, v.def_terminated, (size_t)n, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(o + (size_t)n * 11, v.def_truncated, (size_t)n, cudaMemcpyDeviceToHost, st));
   }
+  if (nosync) return CBX_OK;
   CUDA_TRY(cudaStreamSynchronize(st));
   if (!out_pinned) memcpy(host_out, o, out_bytes);
   return CBX_OK;
 }
 
+}  // extern "C"
+
+// ---- observation arrays to host memory, packed (cbx_batch_fetch_host) ----
+namespace {
+struct fetch_item { const void* src; size_t row_bytes; };
+void fetch_items(const cbx_batch* b, fetch_item* it) {
+  const cbx_views& v = b->p.v;
+  const cbx_layout& L = b->p.lay;
+  it[0] = {v.scalars, 32};
+  it[1] = {v.leaked_credentials, (size_t)16 * L.LEAK};
+  it[2] = {v.credential_cache_matrix, (size_t)8 * L.C};
+  it[3] = {v.discovered_nodes_properties, (size_t)4 * L.N * L.nprops};
+  it[4] = {v.nodes_privilegelevel, (size_t)4 * L.N};
+  it[5] = {v.owned_bits, (size_t)4 * L.OW};
+  it[6] = {v.local_vulnerability, (size_t)L.sz_local};
+  it[7] = {v.remote_vulnerability, (size_t)L.sz_remote};
+  it[8] = {v.connect, (size_t)L.sz_connect};
+  it[9] = {v.def_infected_nodes, (size_t)L.n};
+  it[10] = {v.def_incoming_firewall, (size_t)6 * L.n};
+  it[11] = {v.def_outgoing_firewall, (size_t)6 * L.n};
+  it[12] = {v.def_services_status, (size_t)L.nservices};
+  it[13] = {v.att_reward, 12};
+}
+}  // namespace
+
+extern "C" int64_t cbx_batch_fetch_host_layout(const cbx_batch* b, uint32_t fields, int64_t* offsets) {
+  if (!b) return -1;
+  fetch_item it[CBX_F_COUNT];
+  fetch_items(b, it);
+  int64_t o = 0;
+  for (int k = 0; k < CBX_F_COUNT; ++k) {
+    const bool on = ((fields >> k) & 1u) && it[k].src && it[k].row_bytes;
+    if (offsets) offsets[k] = on ? o : -1;
+    if (on) o = (o + (int64_t)it[k].row_bytes * b->p.n_envs + 255) / 256 * 256;
+  }
+  return o;
+}
+
+extern "C" int cbx_batch_fetch_host(cbx_batch* b, uint32_t fields, void* host_out, size_t host_out_bytes, void* cuda_stream) {
+  if (!b || !host_out) return fail(CBX_ERR_INVALID, "null argument");
+  int64_t off[CBX_F_COUNT];
+  const int64_t total = cbx_batch_fetch_host_layout(b, fields, off);
+  if ((int64_t)host_out_bytes < total) return fail(CBX_ERR_INVALID, "host_out needs %lld bytes", (long long)total);
+  CUDA_TRY(cudaSetDevice(b->device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  fetch_item it[CBX_F_COUNT];
+  fetch_items(b, it);
+  const size_t n = (size_t)b->p.n_envs, np = (size_t)b->p.n_pad;
+  uint8_t* o = (uint8_t*)host_out;
+  for (int k = 0; k < CBX_F_COUNT; ++k) {
+    if (off[k] < 0) continue;
+    if (k == 13 && np != n) {  // rewards / flags: six arrays laid out for the padded env count
+      const uint8_t* s = (const uint8_t*)it[k].src;
+      uint8_t* d = o + off[k];
+      CUDA_TRY(cudaMemcpyAsync(d, s, n * 4, cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaMemcpyAsync(d + n * 4, s + np * 4, n * 4, cudaMemcpyDeviceToHost, st));
+      for (int q = 0; q < 4; ++q) CUDA_TRY(cudaMemcpyAsync(d + n * (8 + q), s + np * (8 + q), n, cudaMemcpyDeviceToHost, st));
+    } else {
+      CUDA_TRY(cudaMemcpyAsync(o + off[k], it[k].src, it[k].row_bytes * n, cudaMemcpyDeviceToHost, st));
+    }
+  }
+  return CBX_OK;
+}
+
+extern "C" {
 int cbx_batch_sample_actions(cbx_batch* b, int32_t* att, int32_t* def, uint64_t seed, void* cuda_stream) {
   if (!b || !att) return fail(CBX_ERR_INVALID, "null argument");
   CUDA_TRY(cudaSetDevice(b->device));
@@ -935,6 +1037,14 @@ int cbx_batch_phase_cycles(cbx_batch* b, int enable, uint64_t* out16) {
     CUDA_TRY(cudaMemset(b->p.prof, 0, 16 * sizeof(unsigned long long)));
   }
   if (!enable) b->p.prof = nullptr;
+  return CBX_OK;
+}
+
+int cbx_batch_tile_counter(cbx_batch* b, int32_t* out2) {
+  if (!b || !out2) return fail(CBX_ERR_INVALID, "null argument");
+  CUDA_TRY(cudaSetDevice(b->device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpy(out2, b->p.tile_counter, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost));
   return CBX_OK;
 }
 

@@ -450,13 +450,16 @@ struct Ctx {
     setf32(L->o_def_return, 0.f);
   }
   __device__ bool defender_action_valid(const int32_t* a) const {  // DWR:329-412, on the LIVE env
-    const int n = n_nodes();  // node coordinates beyond the scenario's own nodes (padded action space) are invalid
+    // node coordinates beyond the scenario's own nodes (padded action space) are invalid; so is anything negative or past the
+    // six firewall rule names -- values the MultiDiscrete space cannot produce are an invalid action, never an index
+    const int n = n_nodes();
+    auto node_ok = [&](int x) { return x >= 0 && x < n && !bit(L->o_notrunning, x); };
     switch (a[0]) {
-      case 0: return a[1] < n && !bit(L->o_notrunning, a[1]) && (node_rec(a[1])[CBX_N_FLAGS] & 1u);
-      case 1: return a[2] < n && !bit(L->o_notrunning, a[2]) && ((node_rec(a[2])[CBX_N_DEFOBS] >> ((a[4] ? 0 : 8) + a[3])) & 1u);
-      case 2: return a[5] < n && !bit(L->o_notrunning, a[5]);
-      case 3: return a[8] < n && !bit(L->o_notrunning, a[8]) && a[9] < (int)((node_rec(a[8])[CBX_N_FLAGS] >> 8) & 0xFFu);
-      case 4: return a[10] < n && !bit(L->o_notrunning, a[10]) && a[11] < (int)((node_rec(a[10])[CBX_N_FLAGS] >> 8) & 0xFFu);
+      case 0: return node_ok(a[1]) && (node_rec(a[1])[CBX_N_FLAGS] & 1u);
+      case 1: return node_ok(a[2]) && a[3] >= 0 && a[3] < 6 && ((node_rec(a[2])[CBX_N_DEFOBS] >> ((a[4] ? 0 : 8) + a[3])) & 1u);
+      case 2: return node_ok(a[5]);
+      case 3: return node_ok(a[8]) && a[9] >= 0 && a[9] < (int)((node_rec(a[8])[CBX_N_FLAGS] >> 8) & 0xFFu);
+      case 4: return node_ok(a[10]) && a[11] >= 0 && a[11] < (int)((node_rec(a[10])[CBX_N_FLAGS] >> 8) & 0xFFu);
       default: return false;
     }
   }

@@ -1,0 +1,23 @@
+// cbx_pipe.cu -- translation unit of the pipelined, warp-specialised step kernel (cbx_pipe.cuh) and its launch helpers.
+#include "cbx_shared.cuh"
+#include "cbx_pipe.cuh"
+
+extern "C" {
+// pipelined kernel: enc = 1 runtime dimensions, 2 ToyCtf(12,10), 3 Chain-10(12,12)
+cudaError_t cbx_pipe_attrs(int enc, int smem_bytes) {
+  switch (enc) {
+    case 3: return cudaFuncSetAttribute(cbx::cbx_pipe_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    case 2: return cudaFuncSetAttribute(cbx::cbx_pipe_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    default: return cudaFuncSetAttribute(cbx::cbx_pipe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  }
+}
+cudaError_t cbx_launch_pipe(const cbx_params* p, int op, int grid, cudaStream_t stream) {
+  const int threads = (p->pipe.wl + p->pipe.we) * 32;
+  switch (p->enc.warp_env) {
+    case 3: cbx::cbx_pipe_kernel<3><<<grid, threads, p->pipe.total_bytes, stream>>>(*p, op); break;
+    case 2: cbx::cbx_pipe_kernel<2><<<grid, threads, p->pipe.total_bytes, stream>>>(*p, op); break;
+    default: cbx::cbx_pipe_kernel<1><<<grid, threads, p->pipe.total_bytes, stream>>>(*p, op); break;
+  }
+  return cudaGetLastError();
+}
+}

@@ -1,4 +1,4 @@
-// cbx_pipe.cuh -- pipelined (warp-specialised) step kernel for sm_100a; included by cbx_kernels.cu.
+// cbx_pipe.cuh -- pipelined (warp-specialised) step kernel for sm_100a; included by cbx_pipe.cu.
 //
 // Why: in the fused kernel every CTA alternates "warp 0 plays 32 envs" (latency bound, ~13 us, store path idle) and "all warps
 // encode" (bandwidth bound); the CTAs of an SM start together and stay in phase, so HBM idles while the SMs think
@@ -115,7 +115,7 @@ __device__ __forceinline__ void encode_masks_pipe(const uint32_t* de, const uint
   const int N = CBX_DIM(D, N, L->N), NR = CBX_DIM(D, R, L->R), NP = CBX_DIM(D, P, L->P), NC = CBX_DIM(D, C, L->C);
   const int ROWR = N * NR, ROWC = N * NP * NC;
   const uint32_t nc = de[D_NC];
-  const int skip = K.debug_skip;  // experiments only (CBX_DEBUG_SKIP): 128 no connect copies, 256 no copies at all
+  const int skip = CBX_SKIP(K);  // -DCBX_EXPERIMENTS builds only (CBX_DEBUG_SKIP): 128 no connect copies, 256 no copies at all
   // the bulk copies that read this buffer for the warp's previous env must have finished reading it
   tma_store_wait_read();
   __syncwarp();

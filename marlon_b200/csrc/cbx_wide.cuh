@@ -1,4 +1,4 @@
-// cbx_wide.cuh -- warp-per-tile step kernel for LARGE per-env state (Chain-100, generated networks); included by cbx_kernels.cu.
+// cbx_wide.cuh -- warp-per-tile step kernel for LARGE per-env state (Chain-100, generated networks); included by cbx_wide.cu.
 //
 // Why: with 400 state words per env a staged 32-env state tile is 51 KB of shared memory, so the fused kernel fits two CTAs
 // (two game-logic warps) per SM, and the pipelined kernel's per-tile field images (225 KB at Chain-100) do not fit at all:

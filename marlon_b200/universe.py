@@ -205,17 +205,24 @@ class MultiAgentUniversalEnv:
             self.batch.stats_reset()
         return summarize_stats(v.cpu().numpy())
 
-    @property
-    def attacker_vec_env(self):
+    def vec_env(self, role: str = "attacker", observations: str = "torch", terminal_observations: str = "all"):
+        """The SB3 ``VecEnv`` adapter of one agent (``vec_env.BatchedVecEnv``).  One adapter per (role, settings) is kept: it
+        carries the Monitor-style episode return / length accumulators, which a fresh object on every access would lose."""
         from .vec_env import BatchedVecEnv
 
-        return BatchedVecEnv(self, "attacker")
+        key = (role, observations, terminal_observations)
+        cache = self.__dict__.setdefault("_vec_envs", {})
+        if key not in cache:
+            cache[key] = BatchedVecEnv(self, role, observations=observations, terminal_observations=terminal_observations)
+        return cache[key]
+
+    @property
+    def attacker_vec_env(self):
+        return self.vec_env("attacker")
 
     @property
     def defender_vec_env(self):
-        from .vec_env import BatchedVecEnv
-
-        return BatchedVecEnv(self, "defender")
+        return self.vec_env("defender")
 
     def close(self):
         self.batch.close()

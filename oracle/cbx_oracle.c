@@ -676,14 +676,18 @@ static void defender_reset(orc_batch* b, oenv_t* e, int64_t i) {
 /* DWR:329-412 is_defender_action_valid (reads the LIVE environment) */
 static int defender_action_valid(const orc_batch* b, const oenv_t* e, const int32_t* a) {
   const scn_t* s = &b->s;
+  /* values the MultiDiscrete space cannot produce (negative, node >= n, rule >= 6) count as an invalid action: the
+     reference would raise IndexError for that env; a batch must not */
+#define NODE_OK(x) ((x) >= 0 && (x) < s->n && e->nodes[(x)].running)
   switch (a[0]) {
-    case 0: return e->nodes[a[1]].running && (scn_node(s, a[1])[CBX_N_FLAGS] & 1u);
-    case 1: return e->nodes[a[2]].running && (scn_node(s, a[2])[CBX_N_DEFOBS] >> ((a[4] ? 0 : 8) + a[3]) & 1u);
-    case 2: return e->nodes[a[5]].running;
-    case 3: return e->nodes[a[8]].running && a[9] < (int)(scn_node(s, a[8])[CBX_N_FLAGS] >> 8 & 0xFF);
-    case 4: return e->nodes[a[10]].running && a[11] < (int)(scn_node(s, a[10])[CBX_N_FLAGS] >> 8 & 0xFF);
+    case 0: return NODE_OK(a[1]) && (scn_node(s, a[1])[CBX_N_FLAGS] & 1u);
+    case 1: return NODE_OK(a[2]) && a[3] >= 0 && a[3] < 6 && (scn_node(s, a[2])[CBX_N_DEFOBS] >> ((a[4] ? 0 : 8) + a[3]) & 1u);
+    case 2: return NODE_OK(a[5]);
+    case 3: return NODE_OK(a[8]) && a[9] >= 0 && a[9] < (int)(scn_node(s, a[8])[CBX_N_FLAGS] >> 8 & 0xFF);
+    case 4: return NODE_OK(a[10]) && a[11] >= 0 && a[11] < (int)(scn_node(s, a[10])[CBX_N_FLAGS] >> 8 & 0xFF);
     default: return 0;
   }
+#undef NODE_OK
 }
 
 static void defender_half_step(orc_batch* b, int64_t i, const int32_t* da);
@@ -700,11 +704,15 @@ static void marlon_pair_step(orc_batch* b, int64_t i, const int32_t* aa, const i
   int32_t* info = b->v.att_info + i * 8;
   memset(info, 0, 8 * sizeof(int32_t));
   /* ---------------- AttackerEnvWrapper.step, ATT:255-398 ---------------- */
-  int kind = c->kind_of_index[aa[0]];
+  /* action[0] outside 0..2 or a negative coordinate: not producible by the MultiDiscrete space (the reference would raise
+     for this env); treated as the wrapper-level invalid action */
+  int kind_ok = aa[0] >= 0 && aa[0] <= 2;
+  int kind = c->kind_of_index[kind_ok ? aa[0] : 0];
   const int32_t* coords = aa + b->slice_of_kind[kind];
   int in_range; /* ATT:233-253 */
-  if (kind == CBX_KIND_LOCAL) in_range = coords[0] < e->n_discovered;
-  else in_range = coords[0] < e->n_discovered && coords[1] < e->n_discovered;
+  if (kind == CBX_KIND_LOCAL) in_range = coords[0] >= 0 && coords[0] < e->n_discovered;
+  else in_range = coords[0] >= 0 && coords[0] < e->n_discovered && coords[1] >= 0 && coords[1] < e->n_discovered;
+  in_range = in_range && kind_ok;
   double reward_modifier = 0.0, reward = 0.0, cyber_reward = 0.0;
   int terminated = 0, truncated = 0;
   if (!in_range) {

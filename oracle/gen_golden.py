@@ -363,7 +363,9 @@ def record_raw(name, env_id, env_kwargs, n_tapes, steps, seed, p_valid=0.5, scri
 
 # ---- MARLon attacker+defender tapes ------------------------------------------------------------------------
 def record_marlon(name, env_id, env_kwargs, att_kwargs, def_kwargs, n_tapes, steps, seed, with_defender=True,
-                  p_att_valid=0.0, p_def_empty=0.0, factory=None, meta_kwargs=None):
+                  p_att_valid=0.0, p_def_empty=0.0, factory=None, meta_kwargs=None, masked=False):
+    """`masked`: the attacker is driven through the reference's MaskedDiscreteAttackerWrapper (action_masking.py:30-165): per step
+    its action_masks() (CRC + count) and the Discrete action fed to its step() are recorded next to the MultiDiscrete encoding."""
     rec = Recorder()
     units = []
     for t in range(n_tapes):
@@ -374,7 +376,12 @@ def record_marlon(name, env_id, env_kwargs, att_kwargs, def_kwargs, n_tapes, ste
         # SB3 learn() resets every env once before the first step: attacker first, then defender
         aobs, _ = att.reset()
         dobs = dfn.reset()[0] if dfn else None
-        units.append(dict(env=env, att=att, dfn=dfn, aobs=aobs, dobs=dobs, rng=np.random.default_rng(seed + t)))
+        mw = None
+        if masked:
+            from marlon.baseline_models.env_wrappers.action_masking import MaskedDiscreteAttackerWrapper
+
+            mw = MaskedDiscreteAttackerWrapper(att)
+        units.append(dict(env=env, att=att, dfn=dfn, aobs=aobs, dobs=dobs, rng=np.random.default_rng(seed + t), mw=mw))
     env0 = units[0]["env"]
     comp = scenario.compile_scenario(env0._CyberBattleEnv__initial_environment)
     b = env0.bounds
@@ -390,7 +397,18 @@ def record_marlon(name, env_id, env_kwargs, att_kwargs, def_kwargs, n_tapes, ste
         for u in units:
             env, att, dfn, rng = u["env"], u["att"], u["dfn"], u["rng"]
             # ---- attacker.perform_step
-            if rng.random() < p_att_valid:
+            extra = {}
+            if masked:
+                mw = u["mw"]
+                mask = mw.action_masks()
+                valid = np.flatnonzero(mask)
+                if len(valid) and rng.random() < p_att_valid:
+                    a_disc = int(valid[int(rng.integers(len(valid)))])
+                else:
+                    a_disc = int(rng.integers(int(mw.action_space.n)))
+                a_act = mw._encode_for_inner_env(*mw._decode(a_disc)).astype(np.int64)
+                extra = dict(att_discrete=np.int64(a_disc), mask_crc=np.uint32(crc(mask.astype(np.int8))), mask_count=np.int32(mask.sum()))
+            elif rng.random() < p_att_valid:
                 va = env.sample_valid_action(kinds=[0, 1, 2])
                 kind = next(iter(va))
                 a_act = np.zeros(len(att_nvec), dtype=np.int64)
@@ -400,7 +418,10 @@ def record_marlon(name, env_id, env_kwargs, att_kwargs, def_kwargs, n_tapes, ste
             else:
                 a_act = np.array([int(rng.integers(m)) for m in att_nvec], dtype=np.int64)
             LAST["raw"], LAST["outcome"] = 0.0, "unset"
-            aobs, ar, aterm, atrunc, ainfo = att.step(a_act)
+            if masked:
+                aobs, ar, aterm, atrunc, ainfo = u["mw"].step(np.array(extra["att_discrete"]))
+            else:
+                aobs, ar, aterm, atrunc, ainfo = att.step(a_act)
             intercepted = bool(ainfo.get("invalid_action", False))
             if LAST["outcome"] == "unset":
                 raw, code = (0.0, 0) if intercepted else (-1.0, 0)
@@ -413,6 +434,7 @@ def record_marlon(name, env_id, env_kwargs, att_kwargs, def_kwargs, n_tapes, ste
                      att_truncated=np.uint8(atrunc), cyber_reward=np.float64(att.last_cyber_reward), raw=np.float64(raw),
                      outcome=np.int32(code), intercepted=np.uint8(intercepted),
                      availability=np.float64(env._defender_actuator.network_availability))
+            r.update(extra)
             if aterm or atrunc:
                 for k, v in o.items():
                     r["term_" + k] = v
@@ -647,8 +669,63 @@ def main_random():
                   factory=factory(3), meta_kwargs=dict(seed=3))
 
 
+def main_round2(only_masked=False):
+    """Round-2 tapes (the other tapes are left alone): a scenario with PRIVILEGE ESCALATION outcomes and dynamic privilege_N
+    tags (tests/escalation_scenario.py, built here from the reference's model classes), and Chain-100 -- the config-4 scenario --
+    with the MARLon pair and with the built-in ScanAndReimage defender."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import escalation_scenario
+
+    AG, DC = ref_env.AttackerGoal, ref_env.DefenderConstraint
+    Scan = ref_defender.ScanAndReimageCompromisedMachines
+
+    def esc_factory(**kw):
+        return ref_env.CyberBattleEnv(initial_environment=escalation_scenario.build(ref_model), **kw)
+
+    e1 = dict(maximum_node_count=6, maximum_total_credentials=4, throws_on_invalid_actions=False, attacker_goal=AG(own_atleast_percent=1.0))
+    if only_masked:
+        t1 = dict(maximum_node_count=12, maximum_total_credentials=10, maximum_discoverable_credentials_per_action=5,
+                  throws_on_invalid_actions=False, defender_constraint=DC(maintain_sla=0.60), losing_reward=-5000.0)
+        akw_m = dict(max_timesteps=80, invalid_action_reward_modifier=-1.0, invalid_action_reward_multiplier=1.0, loss_reward=-5000.0)
+        dkw_m = dict(max_timesteps=80, invalid_action_reward=-1, reset_on_constraint_broken=True, loss_reward=-5000.0)
+        record_marlon("marlon_toyctf_masked", "CyberBattleToyCtf-v0", t1, akw_m, dkw_m, 4, 400, seed=8300, p_att_valid=0.9, p_def_empty=0.5,
+                      masked=True)
+        return
+    record_raw("raw_escalation_valid", escalation_scenario.ENV_ID, e1, 16, 300, seed=8000, p_valid=0.85, factory=esc_factory)
+    e2 = dict(e1, defender_agent=Scan(probability=0.7, scan_capacity=2, scan_frequency=3), defender_constraint=DC(maintain_sla=0.5))
+    record_raw("raw_escalation_scan", escalation_scenario.ENV_ID, e2, 16, 400, seed=8100, p_valid=0.9, factory=esc_factory)
+    akw = dict(max_timesteps=60, invalid_action_reward_modifier=-1.0, invalid_action_reward_multiplier=1.0, loss_reward=-5000.0)
+    dkw = dict(max_timesteps=45, invalid_action_reward=-1, reset_on_constraint_broken=True, loss_reward=-5000.0)
+    e3 = dict(maximum_node_count=6, maximum_total_credentials=4, throws_on_invalid_actions=False,
+              defender_constraint=DC(maintain_sla=0.60), losing_reward=-5000.0)
+    record_marlon("marlon_escalation_valid", escalation_scenario.ENV_ID, e3, akw, dkw, 8, 400, seed=8200, p_att_valid=0.8, p_def_empty=0.4,
+                  factory=esc_factory)
+
+    # the attacker behind the reference's MaskedDiscreteAttackerWrapper: mask content and Discrete -> MultiDiscrete decoding
+    t1 = dict(maximum_node_count=12, maximum_total_credentials=10, maximum_discoverable_credentials_per_action=5,
+              throws_on_invalid_actions=False, defender_constraint=DC(maintain_sla=0.60), losing_reward=-5000.0)
+    akw_m = dict(max_timesteps=80, invalid_action_reward_modifier=-1.0, invalid_action_reward_multiplier=1.0, loss_reward=-5000.0)
+    dkw_m = dict(max_timesteps=80, invalid_action_reward=-1, reset_on_constraint_broken=True, loss_reward=-5000.0)
+    record_marlon("marlon_toyctf_masked", "CyberBattleToyCtf-v0", t1, akw_m, dkw_m, 4, 400, seed=8300, p_att_valid=0.9, p_def_empty=0.5,
+                  masked=True)
+
+    # Chain-100 (chainpattern.py:198-243): bounds must be raised to 102 nodes / 102 credentials (SURVEY.md 8, config C100)
+    c100 = dict(size=100, maximum_node_count=102, maximum_total_credentials=102, throws_on_invalid_actions=False,
+                defender_constraint=DC(maintain_sla=0.60), losing_reward=-5000.0)
+    akw4 = dict(max_timesteps=2000, invalid_action_reward_modifier=-1.0, invalid_action_reward_multiplier=1.0, loss_reward=-5000.0)
+    dkw4 = dict(max_timesteps=2000, invalid_action_reward=-1, reset_on_constraint_broken=True, loss_reward=-5000.0)
+    record_marlon("marlon_chain100_valid", "CyberBattleChain-v0", c100, akw4, dkw4, 2, 300, seed=9000, p_att_valid=0.95, p_def_empty=0.5)
+    c100s = dict(size=100, maximum_node_count=102, maximum_total_credentials=102, throws_on_invalid_actions=False,
+                 defender_agent=Scan(probability=0.6, scan_capacity=2, scan_frequency=5), defender_constraint=DC(maintain_sla=0.80))
+    record_raw("raw_chain100_scan", "CyberBattleChain-v0", c100s, 2, 300, seed=9100, p_valid=0.95)
+
+
 if __name__ == "__main__":
     if "--random" in sys.argv:
         main_random()
+    elif "--round2" in sys.argv:
+        main_round2()
+    elif "--masked" in sys.argv:
+        main_round2(only_masked=True)
     else:
         main()

@@ -17,6 +17,15 @@ def pytest_configure(config):
 def pytest_collection_modifyitems(config, items):
     have_ref = os.path.isdir("/root/reference/src/CyberBattleSim/cyberbattle")
     skip_ref = pytest.mark.skip(reason="/root/reference not present")
+    try:
+        import torch
+
+        have_gpu = torch.cuda.is_available() and os.path.exists(os.path.join(ROOT, "marlon_b200", "libcbx.so"))
+    except Exception:
+        have_gpu = False
+    skip_gpu = pytest.mark.skip(reason="no CUDA device (or marlon_b200/libcbx.so not built): the GPU parity tests run on the B200 box")
     for item in items:
         if "reference" in item.keywords and not have_ref:
             item.add_marker(skip_ref)
+        if "gpu" in item.keywords and not have_gpu:
+            item.add_marker(skip_gpu)

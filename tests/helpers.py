@@ -49,7 +49,13 @@ def _decode_kwargs(kw):
 
 def config_from_meta(meta, **overrides):
     """-> (CompiledScenario, cbx_config) for a tape header."""
-    env, env_kw = registry.resolve(meta["env_id"], **_decode_kwargs(meta["env_kwargs"]))
+    if meta["env_id"] == "test:escalation":  # not a registered id: the test-only escalation network (tests/escalation_scenario.py)
+        import escalation_scenario
+        from marlon_b200 import model
+
+        env, env_kw = escalation_scenario.build(model), _decode_kwargs(meta["env_kwargs"])
+    else:
+        env, env_kw = registry.resolve(meta["env_id"], **_decode_kwargs(meta["env_kwargs"]))
     comp = scenario.compile_scenario(env)
     assert comp.fingerprint() == meta["fingerprint"], "scenario tables differ from the ones the tape was recorded on"
     env_kw.pop("observation_padding", None)

@@ -110,6 +110,69 @@ def test_wrappers_replay_reference_tape(name):
     att.close()
 
 
+def test_masked_discrete_wrapper_replays_reference_tape():
+    """MaskedDiscreteAttackerWrapper (action_masking.py:30-165) against a tape recorded through the REFERENCE's wrapper: the
+    CONTENT of action_masks() every step (concat order connect, local, remote: CRC + count of valid actions) and the
+    Discrete -> MultiDiscrete decoding of every action that was played."""
+    import zlib
+
+    from marlon_b200 import cyberbattle_env as cbe
+    from marlon_b200.wrappers import AttackerEnvWrapper, DefenderEnvWrapper, EnvironmentEventSource, MaskedDiscreteAttackerWrapper
+
+    meta, z = helpers.load_tape("marlon_toyctf_masked")
+    env = cbe.make(meta["env_id"], **helpers._decode_kwargs(meta["env_kwargs"]))
+    es = EnvironmentEventSource()
+    att = AttackerEnvWrapper(env, es, **meta["att_kwargs"])
+    dfn = DefenderEnvWrapper(env, att, es, defender=True, **meta["def_kwargs"])
+    mw = MaskedDiscreteAttackerWrapper(att)
+    assert mw.action_space.n == 12 * 12 * 7 * 10 + 12 * 3 + 12 * 12 * 8
+    mw.reset()
+    dfn.reset()
+    t = 0
+    for s in range(meta["steps"]):
+        mask = mw.action_masks()
+        assert mask.dtype == np.bool_ and mask.shape == (11268,)
+        assert int(mask.sum()) == int(z["mask_count"][s, t]), s
+        assert (zlib.crc32(mask.astype(np.int8).tobytes()) & 0xFFFFFFFF) == int(z["mask_crc"][s, t]), s
+        a = int(z["att_discrete"][s, t])
+        assert np.array_equal(mw._encode_for_inner_env(*mw._decode(a)), z["att_action"][s, t]), s
+        aobs, ar, aterm, atrunc, _ = mw.step(np.array(a))
+        assert abs(ar - z["att_reward"][s, t]) <= 1e-6 * max(1, abs(z["att_reward"][s, t])), s
+        assert (aterm, atrunc) == (bool(z["att_terminated"][s, t]), bool(z["att_truncated"][s, t])), s
+        if aterm or atrunc:
+            mw.reset()
+        d_act = z["def_action"][s, t]
+        _, _, dterm, dtrunc, _ = dfn.step([] if d_act[0] < 0 else d_act)
+        if dterm or dtrunc:
+            dfn.reset()
+    att.close()
+
+
+def test_batched_action_masks_match_reference_tape():
+    """The batched face of the same wrapper (universe.action_masks(): bool [n, 11268] built on the device from the dense masks)
+    against the reference-recorded mask CRCs, all tapes of the file side by side in one batch."""
+    import zlib
+
+    from marlon_b200.batch import Batch
+
+    meta, z = helpers.load_tape("marlon_toyctf_masked")
+    comp, cfg = helpers.config_from_meta(meta)
+    n = meta["n_tapes"]
+    b = Batch(comp, cfg, n)
+    b.reset()
+    import torch
+
+    for s in range(meta["steps"]):
+        t = b.tensors
+        m = torch.cat([t["connect"].reshape(n, -1), t["local_vulnerability"].reshape(n, -1), t["remote_vulnerability"].reshape(n, -1)],
+                      dim=1).to(torch.bool).cpu().numpy()
+        for e in range(n):
+            assert int(m[e].sum()) == int(z["mask_count"][s, e]), (s, e)
+            assert (zlib.crc32(m[e].astype(np.int8).tobytes()) & 0xFFFFFFFF) == int(z["mask_crc"][s, e]), (s, e)
+        b.step(z["att_action"][s], z["def_action"][s])
+    b.close()
+
+
 def test_half_steps_and_notify_match_oracle():
     from marlon_b200.batch import Batch
     from oracle import OracleBatch
@@ -153,7 +216,8 @@ def test_universe_and_vec_env_contract():
                                max_timesteps=25, emit_terminal_obs=True)
     o = OracleBatch(u.compiled, u.cfg, n)
     o.reset()
-    av, dv = u.attacker_vec_env, u.defender_vec_env
+    assert u.attacker_vec_env is u.attacker_vec_env  # one adapter per role: the episode accumulators live on it
+    av, dv = u.vec_env("attacker", observations="numpy"), u.vec_env("defender", observations="numpy")
     assert av.num_envs == n and av.action_space.nvec.tolist() == [3, 12, 12, 7, 10, 12, 3, 12, 12, 8]
     aobs, dobs = av.reset(), dv.reset()
     assert aobs["connect"].shape == (n, 12, 12, 7, 10) and aobs["connect"].dtype == np.int8 and dobs["infected_nodes"].shape == (n, 10)
@@ -174,7 +238,14 @@ def test_universe_and_vec_env_contract():
             assert info["TimeLimit.truncated"] == bool(o.arrays["att_truncated"][i] and not o.arrays["att_terminated"][i])
             assert info["episode"]["l"] >= 1 and info["terminal_observation"]["connect"].shape == (12, 12, 7, 10)
             assert np.array_equal(info["terminal_observation"]["discovered_nodes_properties"], o.arrays["term_discovered_nodes_properties"][i])
+            assert np.array_equal(info["terminal_observation"]["connect"], o.arrays["term_connect"][i])
+        for i in np.nonzero(ddone)[0]:
+            assert np.array_equal(dinfos[i]["terminal_observation"]["infected_nodes"], o.arrays["term_def_infected_nodes"][i])
         assert all(ainfos[i] == {} for i in np.nonzero(~adone)[0])
+        # the device-tensor adapter of the same universe sees the same observation without any copy
+        tobs = u.attacker_observation()
+        assert tobs["connect"].data_ptr() == u.batch.tensors["connect"].data_ptr()
+        assert np.array_equal(tobs["discovered_node_count"].cpu().numpy(), aobs["discovered_node_count"])
     assert episodes > 0
     masks = av.env_method("action_masks")
     assert len(masks) == n and masks[0].shape == (11268,) and masks[0].dtype == np.bool_

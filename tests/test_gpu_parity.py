@@ -30,9 +30,7 @@ def _compare_all(b, o, step, names=None):
     for k, t in b.tensors.items():
         if names and k not in names:
             continue
-        if k.startswith("term_"):
-            continue
-        got, want = t.cpu().numpy(), o.arrays[k]
+        got, want = t.cpu().numpy(), o.arrays[k]  # term_* too: both sides write a terminal row only when its env finishes
         assert got.shape == want.shape, k
         if got.dtype.kind == "f":
             assert np.allclose(got, want, rtol=helpers.REWARD_RTOL, atol=helpers.REWARD_RTOL), (step, k)
@@ -41,14 +39,24 @@ def _compare_all(b, o, step, names=None):
     assert np.array_equal(b.export_state(), o.export_state()), (step, "state")
 
 
-def _run_against_oracle(comp, cfg, n, steps, seed, uniform_every=3, check_every=8, tape_rng=None):
+def _run_against_oracle(comp, cfg, n, steps, seed, uniform_every=3, check_every=8, tape_rng=None, expect_order=None, i16=False,
+                        reset_at=None):
+    """`expect_order`: the tile order the batch must be running ("dynamic" / "static"); the ticket counter must then be back at
+    zero after every launch.  `i16`: int16 device actions (bulk action loads of half the size).  `reset_at`: a masked explicit
+    reset of half the envs after that step, followed by more steps."""
+    import torch
+
     from oracle import OracleBatch
 
     b = _batch(comp, cfg, n)
+    if expect_order:
+        assert b.kernel_info()["tile_order"] == expect_order, b.kernel_info()
     o = OracleBatch(comp, cfg, n)
     b.reset()
     o.reset()
     _compare_all(b, o, -1)
+    if expect_order:
+        assert b.tile_counter() == (0, 0)
     rng = np.random.default_rng(seed)
     marlon = cfg.mode == _abi.MODE_MARLON
     cap = max(cfg.scan_capacity, 1)
@@ -80,12 +88,61 @@ def _run_against_oracle(comp, cfg, n, steps, seed, uniform_every=3, check_every=
         su = du = None
         if tape_rng is not None and cfg.builtin_defender:
             su, du = tape_rng.random((n, cap)), tape_rng.random((n, cap))
-        b.step(att, dfn, su, du)
+        if i16 and su is None:
+            b.step(torch.as_tensor(att).to(torch.int16).cuda(), None if dfn is None else torch.as_tensor(dfn).to(torch.int16).cuda())
+        else:
+            b.step(att, dfn, su, du)
         o.step(att, dfn, su, du)
+        if expect_order:
+            assert b.tile_counter() == (0, 0), s
+        if reset_at is not None and s == reset_at:
+            m = (np.arange(n) % 2 == 0).astype(np.uint8)
+            b.reset(mask=m)
+            o.reset(mask=m)
+            _compare_all(b, o, s)
         if s % check_every == 0 or s == steps - 1:
             _compare_all(b, o, s)
     assert np.allclose(b.stats(), o.stats, rtol=1e-9, atol=1e-6), (b.stats(), o.stats)
     assert b.stats()[_abi.STAT_ENV_STEPS] == n * steps
+    b.close()
+
+
+def _toyctf_pair_cfg(**kw):
+    args = dict(maximum_node_count=12, maximum_total_credentials=10, maximum_discoverable_credentials_per_action=5,
+                throws_on_invalid_actions=False, attacker_goal=config.AttackerGoal(own_atleast=6),
+                defender_constraint=config.DefenderConstraint(0.60), losing_reward=-5000.0, defender_enabled=True,
+                defender_max_timesteps=2000, defender_invalid_action_reward=-1, attacker_max_timesteps=2000)
+    args.update(kw)
+    return config.make_config(_abi.MODE_MARLON, **args)
+
+
+@pytest.mark.parametrize("n", [257, 513, 4099])
+@pytest.mark.parametrize("mask_mode", [_abi.MASK_DENSE, _abi.MASK_FACTORED])
+def test_pipe_kernel_dynamic_tile_order_vs_oracle(monkeypatch, n, mask_mode):
+    """The pipelined kernel's DYNAMIC tile order (global ticket counter, stop markers, counter reset by the last CTA) is what
+    every batch of >= 24 tiles per CTA runs (>= 113 664 envs per GPU: the 1M-env and multi-GPU figures).  Forced on here at
+    small ragged sizes: every array and the state against the oracle, int16 bulk actions, a masked reset mid-run, short
+    episodes so that terminal observations and auto-resets occur, and the ticket counter back at {0, 0} after every launch."""
+    monkeypatch.setenv("CBX_PIPE_DYNAMIC", "1")
+    comp = scenario.compile_scenario(scenarios.toyctf_environment())
+    cfg = _toyctf_pair_cfg(mask_mode=mask_mode, emit_terminal_obs=True, attacker_max_timesteps=23, defender_max_timesteps=17)
+    _run_against_oracle(comp, cfg, n, 90, seed=41 + n, check_every=5, expect_order="dynamic", i16=(n != 513), reset_at=31)
+
+
+def test_pipe_kernel_dynamic_tile_order_default_threshold_vs_oracle():
+    """131 072 envs on one GPU: 4 096 tiles >= 24 per CTA, so the library picks the dynamic order BY DEFAULT (no environment
+    override) -- the configuration of the 1M-env / multi-GPU runs.  Every array of every env against the oracle."""
+    comp = scenario.compile_scenario(scenarios.toyctf_environment())
+    _run_against_oracle(comp, _toyctf_pair_cfg(), 131072, 14, seed=43, check_every=13, expect_order="dynamic")
+
+
+def test_static_tile_order_is_the_default_at_bench_size():
+    from marlon_b200.batch import Batch
+
+    comp = scenario.compile_scenario(scenarios.toyctf_environment())
+    b = Batch(comp, _toyctf_pair_cfg(), 65536)
+    info = b.kernel_info()
+    assert info["name"] == "cbx_pipe_kernel" and info["tile_order"] == "static", info
     b.close()
 
 
