@@ -345,12 +345,15 @@ def record_tape(comp, cfg, counts, n, steps, seed, local, dev):
     return tape_a, tape_d, aw, has_def
 
 
-def touched_state_words(comp, cfg):
-    """In-place kernel (cbx_wide_kernel): words of the per-env state a step has to touch -- the wrappers' words, the stale
-    copy's countdowns and the header read + written; discovery order / inverse map, installed bits, privilege levels,
-    property bitsets and the credential cache read to build the observation.  The rest of the state (attacked bits, live
-    countdowns, gathered / cached bitsets, ever-owned, not-running) is touched only by the few envs whose action needs it
-    and is NOT counted -- see DESIGN.md 4.3."""
+def in_place_kernel_bytes(comp, cfg, ab):
+    """Algorithmic bytes per env-step of the IN-PLACE kernel (cbx_wide_kernel), from the SURVEY 8(d) figure `ab`:
+      * state: only the words a step has to touch -- the wrappers' words, the stale copy's countdowns and the header read +
+        written; discovery order / inverse map, installed bits, privilege levels, property bitsets and the credential cache
+        read once to build the observation.  The rest of the per-env state (attacked bits, live countdowns, gathered / cached
+        bitsets, ever-owned, not-running) is touched only by the few envs whose action needs it and is NOT counted;
+      * defender observation: only infected_nodes -- the firewall / service rows cannot change under the reference's stale
+        defender binding and are written when an env is created or reset, not by a step.
+    Both corrections LOWER the numerator; the SURVEY figure is kept under `survey_8d_total`."""
     n = comp.n_nodes
     ident = comp.identifiers
     props = len(ident.properties)
@@ -358,7 +361,15 @@ def touched_state_words(comp, cfg):
     ntr = len(comp.triples)
     rw = 13 + (n + 3) // 4 + 2                     # wrapper words + shadow countdowns + stepcount / episode sum
     ro = Wn + (n + 15) // 16 + 2 * ((n + 3) // 4) + n * PW + (ntr + 2) // 2
-    return rw, ro
+    out = dict(ab)
+    out["survey_8d_total"] = ab["total"]
+    out["state_rw"] = 4 * (2 * rw + ro)
+    if cfg.def_enabled:
+        out["defender_obs"] = n
+    out["total"] = sum(out[k] for k in ("attacker_obs", "masks", "defender_obs", "state_rw", "actions_rewards_flags"))
+    out["note"] = ("in-place kernel: state = wrapper/header/stale-copy words read+written + observation sources read once; defender "
+                   "observation = infected_nodes only (static firewall / service rows are written at reset, not per step)")
+    return out
 
 
 def measure_device(args, workload, n_req, K, W, world, rank, local, dev, clocks=None):
@@ -433,12 +444,8 @@ def measure_device(args, workload, n_req, K, W, world, rank, local, dev, clocks=
             S_packed = packed_state_words or _packed_state_words(comp, cfg)
             ab = algorithmic_bytes_per_env_step(comp, cfg, S_packed)
             ref_comp = comp
-        if kinfo["name"] == "cbx_wide_kernel":  # in-place kernel: only the words a step has to touch count
-            rw, ro = touched_state_words(ref_comp, cfg)
-            ab["state_rw_full_tile"] = ab["state_rw"]
-            ab["total"] += 4 * (2 * rw + ro) - ab["state_rw"]
-            ab["state_rw"] = 4 * (2 * rw + ro)
-            ab["state_note"] = "in-place kernel: wrapper/header/shadow words read+written, observation sources read once"
+        if kinfo["name"] == "cbx_wide_kernel":  # in-place kernel: only what a step has to move counts
+            ab = in_place_kernel_bytes(ref_comp, cfg, ab)
         achieved = ab["total"] * n / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else None
         total_envs = n * world
         out.update({

@@ -417,7 +417,9 @@ int cbx_batch_export_state(cbx_batch* b, int64_t env_begin, int64_t env_end, int
 /* Number of kernels this library has launched on behalf of the batch so far (bench.py's gpu_launches). */
 int64_t cbx_batch_launch_count(const cbx_batch* b);
 /* Average duration (ms) of the step kernel over the launches recorded since the last call, measured with CUDA events
- * on the launch stream when timing is enabled. */
+ * on the launch stream when timing is enabled.  When consecutive launches overlap (cbx_batch_kernel_info bit 2) an event
+ * between two launches would serialise them: the events then bracket the whole run of step launches since timing was
+ * enabled (or since the last call) and the mean is that span divided by the launches in it. */
 int cbx_batch_enable_timing(cbx_batch* b, int enabled);
 int cbx_batch_step_kernel_ms(cbx_batch* b, double* mean_ms, int64_t* launches);
 
@@ -436,7 +438,8 @@ int cbx_gae(const float* rewards, const float* values, const uint8_t* episode_st
  * (cbx_step_kernel); [1] CTAs; [2] threads per CTA;
  * [3] dynamic shared memory bytes per CTA; [4] logic warps; [5] encoder warps; [6] encoder variant (0 generic, 1 warp per
  * env, 2 ToyCtf(12,10) static, 3 Chain-10(12,12) static); [7] bit 0 TMA staging enabled, bit 1 dynamic tile order (tiles after a warp's first are drawn
- * from a global ticket counter instead of a fixed stride). */
+ * from a global ticket counter instead of a fixed stride), bit 2 consecutive launches overlap (programmatic dependent launch, accesses
+ * ordered tile by tile through completion counters in HBM). */
 int cbx_batch_kernel_info(const cbx_batch* b, int32_t* out8);
 
 /* Parity instrumentation: the dynamic tile order's global counters {tickets handed out, CTAs finished}; both must read 0

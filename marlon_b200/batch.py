@@ -320,6 +320,7 @@ class Batch:
         keys = ["pipelined", "ctas", "threads", "smem_bytes", "logic_warps", "encoder_warps", "encoder_variant", "tma"]
         d = {k: int(out[i]) for i, k in enumerate(keys)}
         d["tile_order"] = "dynamic" if d["tma"] & 2 else "static"
+        d["overlapped_launches"] = bool(d["tma"] & 4)
         d["tma"] &= 1
         d["name"] = {1: "cbx_pipe_kernel", 2: "cbx_wide_kernel"}.get(d["pipelined"], "cbx_step_kernel")
         return d

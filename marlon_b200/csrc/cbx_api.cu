@@ -124,21 +124,33 @@ bool plan_pipe(const cbx_params& p, int wl, int we, cbx_pipe_plan* Q) {
   return true;
 }
 
-// Shared-memory plan of the warp-per-tile kernel (cbx_wide.cuh): factored masks, warp-per-env encoder available.
+// Shared-memory plan of the warp-per-tile kernel (cbx_wide.cuh): factored masks only.
 bool plan_wide(const cbx_params& p, int sms, cbx_wide_plan* Q) {
   const cbx_layout& L = p.lay;
   memset(Q, 0, sizeof(*Q));
   if (p.enc.warp_env < 1 || CBX_TILE != 32 || L.sz_connect > 0) return false;
+  // image words per env: the tile's actions (22), the credential cache two entries per word (chunks of at most 56 words), the
+  // property bit stream of a chunk of nodes + their 2-bit privilege codes, the infected-node bytes, the defender's static rows
+  auto cdiv = [](int a, int b) { return (a + b - 1) / b; };
+  const int cache_words = cdiv(L.C, 2) < 56 ? cdiv(L.C, 2) : 56;
+  int npc = (L.N + 3) & ~3;                                         // nodes per chunk: a multiple of 4, all of them if they fit
+  while (npc > 4 && cdiv(npc * L.nprops, 32) + cdiv(npc, 16) > 64) npc -= 4;
+  const int prop_words = cdiv(npc * L.nprops, 32) + cdiv(npc, 16);
+  const int n6s = (6 * L.n + 4 + 3) & ~3, svs = (L.nservices + 4 + 3) & ~3;
+  int iw = 22;
+  if (cache_words > iw) iw = cache_words;
+  if (prop_words > iw) iw = prop_words;
+  if (cdiv(L.n, 4) > iw) iw = cdiv(L.n, 4);
+  if (cdiv(2 * n6s + svs, 4 * CBX_TILE) > iw) iw = cdiv(2 * n6s + svs, 4 * CBX_TILE);
+  Q->img_words = iw;
+  Q->img_stride = iw | 1;
+  Q->nodes_per_chunk = npc;
   int64_t o = 0;
-  Q->lut = (int)o; o += 512;
-  Q->lut4 = (int)o; o += 17 * 4 + 28;  // 17 x uint4, padded to 32 words
   Q->warps = (int)o;
   int64_t q = 0;
   Q->w_stage = (int)q; q += (int64_t)L.G * CBX_TILE;
   Q->w_desc = (int)q; q += (int64_t)p.enc.desc_words * CBX_TILE;
-  Q->w_acts = (int)q; q += 22 * CBX_TILE;
-  Q->w_img = (int)q; q += 36 * CBX_TILE;
-  Q->w_drows = (int)q; q += 2 * ((6 * L.n + 4 + 3) / 4) + (L.nservices + 4 + 3) / 4 + 1;
+  Q->w_img = (int)q; q += (int64_t)Q->img_stride * CBX_TILE;
   q = (q + 31) / 32 * 32;
   Q->warp_words = (int)q;
   // as many warps as fit while leaving L1 room for the scenario tables and the hot state lines; then the FEWEST warps that
@@ -183,6 +195,10 @@ struct cbx_batch {
   size_t ev_used;
   double ms_sum;
   int64_t ms_count;
+  // overlapped launches: an event between two launches would serialise them, so the timed region is bracketed instead
+  int region_open;
+  int64_t region_count;
+  cudaStream_t region_stream;
   const cbx_scenario* scn;       // dimensions the layout was computed from (== &vscn for a multi-scenario batch)
   cbx_scenario vscn;             // multi-scenario batch: the element-wise maximum of the scenarios' dimensions (no blob)
   int32_t* d_tile_scn;
@@ -392,6 +408,7 @@ static int create_impl(const cbx_scenario* const* scns, int n_scn, const int64_t
   cbx_batch* b = new cbx_batch();
   memset(&b->p, 0, sizeof(b->p));
   b->device = device; b->launches = 0; b->sample_step = 0; b->timing = 0; b->ev_used = 0; b->ms_sum = 0; b->ms_count = 0;
+  b->region_open = 0; b->region_count = 0; b->region_stream = nullptr;
   b->h_att = b->h_def = b->d_att = b->d_def = nullptr; b->h_out = nullptr; b->host_ready = 0; b->scn = s; b->d_tile_scn = nullptr;
   size_t max_blob = s->blob.size();
   if (n_scn > 1) {  // padded layout: the maximum of every per-scenario dimension
@@ -513,6 +530,9 @@ static int create_impl(const cbx_scenario* const* scns, int n_scn, const int64_t
         // dynamic tile order pays from ~24 tiles per CTA on (131 072 envs per GPU); CBX_PIPE_DYNAMIC=0/1 overrides
         { const char* dy = getenv("CBX_PIPE_DYNAMIC"); Q.dynamic = dy ? atoi(dy) != 0 : b->p.n_tiles >= 24 * b->pipe_grid; }
         b->p.pipe = Q;
+        // consecutive launches overlap (programmatic dependent launch + per-tile completion counters); CBX_PIPE_OVERLAP=0
+        // restores fully serialised launches
+        { const char* ov = getenv("CBX_PIPE_OVERLAP"); b->p.overlap = !(ov && ov[0] == '0'); }
       } else {
         cudaGetLastError();
       }
@@ -586,6 +606,11 @@ static int create_impl(const cbx_scenario* const* scns, int n_scn, const int64_t
     cudaError_t e = dalloc(&pc, 64);
     if (e != cudaSuccess) { int rc2 = fail(CBX_ERR_CUDA, "cudaMalloc(tile counter): %s", cudaGetErrorString(e)); cbx_batch_destroy(b); return rc2; }
     b->p.tile_counter = (int*)pc;
+    void* pd = nullptr;
+    e = dalloc(&pd, (size_t)b->p.n_tiles * sizeof(uint32_t));
+    if (e != cudaSuccess) { int rc2 = fail(CBX_ERR_CUDA, "cudaMalloc(tile completion counters): %s", cudaGetErrorString(e)); cbx_batch_destroy(b); return rc2; }
+    b->p.tile_done = (uint32_t*)pd;
+    b->p.seq = 0;
   }
   cbx_views& v = b->p.v;
   v.n_envs = n_envs; v.N = L.N; v.L = L.L; v.R = L.R; v.P = L.P; v.C = L.C; v.LEAK = L.LEAK; v.n_props = L.nprops;
@@ -641,6 +666,7 @@ static int create_impl(const cbx_scenario* const* scns, int n_scn, const int64_t
   {
     b->p.reset_mask = nullptr;
     const int op0 = CBX_OP_RESET | CBX_OP_ATTACKER | CBX_OP_DEFENDER;
+    b->p.seq += 1;
     cudaError_t e = b->p.pipe.enabled ? cbx_launch_pipe(&b->p, op0, b->pipe_grid, 0)
                     : b->p.wide.enabled ? cbx_launch_wide(&b->p, op0, b->wide_grid, 0)
                                         : cbx_launch_step(&b->p, op0, b->grid, b->smem_bytes, b->use_tma, 0);
@@ -665,7 +691,8 @@ int cbx_batch_destroy(cbx_batch* b) {
 static int timed_launch(cbx_batch* b, int op, cudaStream_t st) {
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   const bool t = b->timing && !(op & CBX_OP_RESET);
-  if (t) {
+  const bool region = t && b->p.pipe.enabled && b->p.overlap;  // bracket the run of launches instead of each launch
+  if (t && !region) {
     if (b->ev_used + 2 > b->ev.size()) {
       for (int k = 0; k < 2; ++k) { cudaEvent_t e; CUDA_TRY(cudaEventCreate(&e)); b->ev.push_back(e); }
     }
@@ -673,10 +700,17 @@ static int timed_launch(cbx_batch* b, int op, cudaStream_t st) {
     b->ev_used += 2;
     CUDA_TRY(cudaEventRecord(e0, st));
   }
+  if (region && !b->region_open) {
+    if (b->ev.size() < 2) { for (int k = 0; k < 2; ++k) { cudaEvent_t e; CUDA_TRY(cudaEventCreate(&e)); b->ev.push_back(e); } }
+    CUDA_TRY(cudaEventRecord(b->ev[0], st));
+    b->region_open = 1; b->region_count = 0; b->region_stream = st;
+  }
+  b->p.seq += 1;
   if (b->p.pipe.enabled) CUDA_TRY(cbx_launch_pipe(&b->p, op, b->pipe_grid, st));
   else if (b->p.wide.enabled) CUDA_TRY(cbx_launch_wide(&b->p, op, b->wide_grid, st));
   else CUDA_TRY(cbx_launch_step(&b->p, op, b->grid, b->smem_bytes, b->use_tma, st));
-  if (t) CUDA_TRY(cudaEventRecord(e1, st));
+  if (t && !region) CUDA_TRY(cudaEventRecord(e1, st));
+  if (region) b->region_count++;
   b->launches++;
   return CBX_OK;
 }
@@ -1044,7 +1078,10 @@ int cbx_batch_tile_counter(cbx_batch* b, int32_t* out2) {
   if (!b || !out2) return fail(CBX_ERR_INVALID, "null argument");
   CUDA_TRY(cudaSetDevice(b->device));
   CUDA_TRY(cudaDeviceSynchronize());
-  CUDA_TRY(cudaMemcpy(out2, b->p.tile_counter, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  int32_t c[4];
+  CUDA_TRY(cudaMemcpy(c, b->p.tile_counter, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  out2[0] = c[0] | c[2];  // both pairs (even / odd launches when launches overlap)
+  out2[1] = c[1] | c[3];
   return CBX_OK;
 }
 
@@ -1059,7 +1096,7 @@ int cbx_batch_kernel_info(const cbx_batch* b, int32_t* out8) {
   out8[4] = Q.enabled ? Q.wl : 0;
   out8[5] = Q.enabled ? Q.we : 0;
   out8[6] = b->p.enc.warp_env;
-  out8[7] = b->use_tma | ((Q.enabled ? Q.dynamic : wide ? b->p.wide.dynamic : 0) ? 2 : 0);
+  out8[7] = b->use_tma | ((Q.enabled ? Q.dynamic : wide ? b->p.wide.dynamic : 0) ? 2 : 0) | ((Q.enabled && b->p.overlap) ? 4 : 0);
   return CBX_OK;
 }
 
@@ -1072,6 +1109,15 @@ int cbx_batch_enable_timing(cbx_batch* b, int enabled) {
 int cbx_batch_step_kernel_ms(cbx_batch* b, double* mean_ms, int64_t* launches) {
   if (!b || !mean_ms || !launches) return fail(CBX_ERR_INVALID, "null argument");
   CUDA_TRY(cudaSetDevice(b->device));
+  if (b->region_open) {  // overlapped launches: one bracket around the whole run, averaged over its launches
+    CUDA_TRY(cudaEventRecord(b->ev[1], b->region_stream));
+    CUDA_TRY(cudaEventSynchronize(b->ev[1]));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, b->ev[0], b->ev[1]));
+    b->ms_sum += ms;
+    b->ms_count += b->region_count;
+    b->region_open = 0; b->region_count = 0;
+  }
   for (size_t k = 0; k + 1 < b->ev_used; k += 2) {
     CUDA_TRY(cudaEventSynchronize(b->ev[k + 1]));
     float ms = 0;

@@ -121,14 +121,18 @@ struct cbx_pipe_plan {
 enum { CBX_SH_ENC_MASK = 0, CBX_SH_TILE = 1 };
 
 // Warp-per-tile kernel for large per-env state (cbx_wide.cuh): nothing big is staged; per warp a private area holds the
-// staging words, the encoder descriptors, the tile's actions, the 32 x 36 transpose square and the defender's static rows.
+// staging words, the encoder descriptors and one image area -- the tile's actions while the game logic runs, then the packed
+// field images (property bits + 2-bit privilege codes, credential-cache byte pairs, infected-node bytes), img_stride words
+// per env.
 #define CBX_WIDE_WARPS 14  // most warps per CTA (the kernel is compiled for 448 threads, one CTA per SM)
 struct cbx_wide_plan {
   int enabled;
   int nwarps;                                      // warps per CTA: as many as fit (<= CBX_WIDE_WARPS)
   int dynamic;                                     // tiles after a warp's first come from the global ticket counter
-  int lut, lut4, warps, warp_words;                // shared-memory carve-up in 32-bit words
-  int w_stage, w_desc, w_acts, w_img, w_drows;     // inside a warp's area
+  int warps, warp_words;                           // shared-memory carve-up in 32-bit words
+  int w_stage, w_desc, w_img;                      // inside a warp's area
+  int img_words, img_stride;                       // packed image words per env; the stride is odd (bank-conflict free columns)
+  int nodes_per_chunk;                             // property / privilege images are built for this many nodes at a time
   int total_bytes;
 };
 
@@ -158,7 +162,15 @@ struct cbx_params {
   const uint8_t* reset_mask;  // reset kernel only
   float notify_last_reward;   // CBX_OP_NOTIFY
   cbx_views v;
-  int* tile_counter;      // dynamic tile order: [0] tickets handed out, [1] CTAs finished (both 0 between launches)
+  int* tile_counter;      // dynamic tile order: [0] tickets handed out, [1] CTAs finished (both 0 between launches); a second
+                          // pair [2], [3] serves the odd launches when consecutive launches overlap
+  // Overlapped launches of the pipelined kernel (programmatic dependent launch): launch k+1's CTAs start on every SM the
+  // moment launch k's CTA has left it and take a tile only after ALL of launch k's writes to that tile have completed --
+  // tile_done[t] counts completions of tile t, (1 + encoder warps) per launch (the logic warp and every encoder warp add one
+  // when their stores of the tile are complete); a launch with sequence number seq waits for parts * (seq - 1).
+  uint32_t* tile_done;
+  uint32_t seq;           // sequence number of this launch (1, 2, ...), counted per batch
+  int overlap;            // 1: the protocol above is on (cbx_pipe_kernel only)
   unsigned long long* prof;  // optional: 16 cycle counters accumulated per phase by thread 0 of every CTA (NULL = off)
 };
 

@@ -13,6 +13,25 @@ cudaError_t cbx_pipe_attrs(int enc, int smem_bytes) {
 }
 cudaError_t cbx_launch_pipe(const cbx_params* p, int op, int grid, cudaStream_t stream) {
   const int threads = (p->pipe.wl + p->pipe.we) * 32;
+  if (p->overlap) {
+    // programmatic dependent launch: this grid's CTAs may start while the previous launch of the stream is still draining;
+    // the kernel orders its accesses tile by tile through cbx_params.tile_done
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = (size_t)p->pipe.total_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    switch (p->enc.warp_env) {
+      case 3: return cudaLaunchKernelEx(&cfg, cbx::cbx_pipe_kernel<3>, *p, op);
+      case 2: return cudaLaunchKernelEx(&cfg, cbx::cbx_pipe_kernel<2>, *p, op);
+      default: return cudaLaunchKernelEx(&cfg, cbx::cbx_pipe_kernel<1>, *p, op);
+    }
+  }
   switch (p->enc.warp_env) {
     case 3: cbx::cbx_pipe_kernel<3><<<grid, threads, p->pipe.total_bytes, stream>>>(*p, op); break;
     case 2: cbx::cbx_pipe_kernel<2><<<grid, threads, p->pipe.total_bytes, stream>>>(*p, op); break;

@@ -23,6 +23,35 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// ---- overlapped launches (cbx_params.overlap): per-tile completion counters in HBM ----
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// one more completed part of a tile: everything this warp wrote to the tile (bulk copies that have completed, plain stores of
+// all its lanes before the preceding __syncwarp) is visible to whoever acquires the counter
+__device__ __forceinline__ void tile_part_done(uint32_t* counter) {
+  asm volatile("fence.proxy.async;" ::: "memory");
+  __threadfence();
+  asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+}
+// cp.async.bulk.wait_group takes an immediate: all but the n most recent bulk groups of this thread have completed
+__device__ __forceinline__ void tma_store_wait_all_but(const int n) {
+  switch (n) {
+    case 0: asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); break;
+    case 1: asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); break;
+    case 2: asm volatile("cp.async.bulk.wait_group 2;" ::: "memory"); break;
+    case 3: asm volatile("cp.async.bulk.wait_group 3;" ::: "memory"); break;
+    case 4: asm volatile("cp.async.bulk.wait_group 4;" ::: "memory"); break;
+    case 5: asm volatile("cp.async.bulk.wait_group 5;" ::: "memory"); break;
+    case 6: asm volatile("cp.async.bulk.wait_group 6;" ::: "memory"); break;
+    case 7: asm volatile("cp.async.bulk.wait_group 7;" ::: "memory"); break;
+    case 8: asm volatile("cp.async.bulk.wait_group 8;" ::: "memory"); break;
+    default: asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); break;  // stricter than asked for
+  }
+}
+
 template <int ENC> struct DimsOf { typedef DimsDyn T; };
 template <> struct DimsOf<2> { typedef DimsToyCtf T; };
 template <> struct DimsOf<3> { typedef DimsChain10 T; };
@@ -245,6 +274,12 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
   const uint32_t table_bytes = (uint32_t)(p.table_words + ((L.S + 3) & ~3)) * 4u;
   const int nthreads = (Q.wl + Q.we) * 32;
   constexpr uint32_t kRowBytes = CBX_TILE * 4u;
+  // Overlapped launches: the next launch of the stream may start its CTAs on every SM this launch's CTA has left (its CTAs
+  // then wait tile by tile on tile_done, never on this grid as a whole)
+  const bool overlap = p.overlap != 0;
+  if (overlap) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const uint32_t seq_need = (uint32_t)(1 + Q.we) * (p.seq - 1u);  // completions of a tile after every earlier launch
+  int* const tickets = p.tile_counter + (overlap ? 2 * (int)(p.seq & 1u) : 0);
 
   for (int k = tid; k < 256; k += nthreads) {
     uint32_t lo = ((k & 0xF) * 0x00204081u) & 0x01010101u, hi = (((k >> 4) & 0xF) * 0x00204081u) & 0x01010101u;
@@ -312,13 +347,14 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
     // publishes a stop marker in its next slot.  Measured: +2 % at 28 tiles per CTA, +9..11 % from 55 on,
     // -2.5 % at 14 (most of a short launch is assigned before any CTA has shown its speed), hence the threshold in the plan.
     int next_tile = (int)blockIdx.x + warp * (int)gridDim.x;
+    int done_tile = -1;  // overlapped launches: the tile whose stores were issued last, not yet reported complete
     for (int j = warp;; j += Q.wl, ++u) {
       const int slot = warp + Q.wl * (u % spw), use = u / spw;
       uint32_t* desc = smem + Q.slots + slot * Q.slot_words;
       uint32_t* hdr = desc + Q.s_hdr;
       int tile;
       if (Q.dynamic) {
-        if (u > 0 && lane == 0) next_tile = (int)gridDim.x * Q.wl + atomicAdd(p.tile_counter, 1);
+        if (u > 0 && lane == 0) next_tile = (int)gridDim.x * Q.wl + atomicAdd(tickets, 1);
         tile = __shfl_sync(0xFFFFFFFFu, next_tile, 0);
         if (tile >= p.n_tiles) {
           if (use > 0) mbar_wait(&bar_empty[slot], (uint32_t)(use - 1) & 1u);
@@ -340,6 +376,13 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
       // a full tile's actions are one contiguous 16-byte aligned block per agent: they ride the same mbarrier as the state
       // tile (bulk copies also read page-locked HOST memory efficiently: cbx_batch_step_host hands host pointers over)
       const bool bulk_acts = Q.logic_tma && n_valid == CBX_TILE && ((((uintptr_t)p.att_actions) | ((uintptr_t)p.def_actions)) & 15u) == 0;
+      if (overlap) {  // every write of the earlier launches to this tile (state, observations, results) must have landed
+        if (lane == 0) {
+          while ((int32_t)(ld_acquire_gpu(p.tile_done + tile) - seq_need) < 0) __nanosleep(64);
+          asm volatile("fence.proxy.async;" ::: "memory");
+        }
+        __syncwarp();
+      }
       if (Q.logic_tma) {
         // the previous tile's state store and field copies (issued by lanes 0..6) must be done reading this warp's buffer
         tma_store_wait_read();
@@ -492,6 +535,12 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
             if (lane == 6 && dense) tma_store_1d(tm.local, im.local, (uint32_t)(CBX_TILE * 4 * wpe_local));
           }
           if (lane < 7) tma_store_commit();
+          if (overlap) {  // the tile before this one: its bulk copies (one group per lane) have completed -> report it
+            if (lane < 7) tma_store_wait_all_but(1);
+            __syncwarp();
+            if (lane == 0 && done_tile >= 0) tile_part_done(p.tile_done + done_tile);
+            done_tile = tile;
+          }
         } else {
           // plain 16-byte copies: a tile's rows are contiguous in every tensor (fully coalesced 512-byte warp stores)
           auto copy16 = [&](void* dst, const void* src, int n16) {
@@ -509,6 +558,11 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
             copy16(tm.priv, im.priv, CBX_TILE * wpe_priv / 4);
             if (dense) copy16(tm.local, im.local, CBX_TILE * wpe_local / 4);
           }
+          if (overlap) {
+            __syncwarp();
+            if (lane == 0 && done_tile >= 0) tile_part_done(p.tile_done + done_tile);
+            done_tile = tile;
+          }
         }
         if (!full) {
           copy_field_rows(tm.scalars, im.scal, 8, n_valid, enc_mask, lane);
@@ -523,6 +577,10 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
       CBX_PPROF(11)  // field images + state write-back
     }
     tma_store_wait_all();  // every lane that issued bulk copies waits for its own
+    if (overlap) {
+      __syncwarp();
+      if (lane == 0 && done_tile >= 0) tile_part_done(p.tile_done + done_tile);
+    }
     // episode statistics: warp shuffle reduce, one atomic per slot per warp
 #pragma unroll
     for (int k = 0; k < CBX_STAT_COUNT; ++k) {
@@ -537,6 +595,7 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
     long long pacc[3] = {0, 0, 0};
     uint32_t stopped = 0;  // dynamic order: logic warps that have published their stop marker
     const uint32_t all_stopped = (1u << Q.wl) - 1u;
+    int done_tile = -1;  // overlapped launches: the tile this warp issued last, not yet reported complete
     for (int j = 0;; ++j) {
       const int lw = j % Q.wl, u = j / Q.wl;
       if (Q.dynamic) {
@@ -557,11 +616,14 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
       const uint32_t enc_mask = desc[Q.s_hdr + CBX_SH_ENC_MASK];
       const int64_t e0 = (int64_t)tile * CBX_TILE;
       const int n_valid = (int)min((int64_t)CBX_TILE, p.n_envs - e0);
+      int groups = 0;  // bulk groups every lane of this warp commits for this tile
       if (dense) {
         for (int e = wid; e < n_valid; e += Q.we)
-          if ((enc_mask >> e) & 1u)
+          if ((enc_mask >> e) & 1u) {
             encode_masks_pipe<D>(desc + e * DW, s_lut, &L, p.enc, p.v.remote_vulnerability + (e0 + e) * L.sz_remote,
                                  p.v.connect + (e0 + e) * (int64_t)L.sz_connect, wb, Q, s_zero, lane, p.prof != nullptr, pacc);
+            ++groups;
+          }
       }
       if (def_encode && wid == j % Q.we) {  // the defender has moved by now (it is released after the action masks)
         mbar_wait(&bar_rdef[slot], (uint32_t)use & 1u);
@@ -569,12 +631,23 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
         t.L = &L; t.tb = s_tb; t.st = nullptr; t.sg = nullptr; t.desc = desc; t.lut = s_lut; t.K = &p.enc; t.DW = DW;
         const Target tm = make_target(p.v, L, e0, false);
         encode_defender_tile<D>(t, tm, n_valid, wb, Q, s_defst, lane);
+        if (n_valid == CBX_TILE) ++groups;
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_empty[slot]);
+      if (overlap) {  // this warp's copies of the tile BEFORE this one have completed (groups retire in order): report it
+        tma_store_wait_all_but(groups);
+        __syncwarp();
+        if (lane == 0 && done_tile >= 0) tile_part_done(p.tile_done + done_tile);
+        done_tile = tile;
+      }
       prof_t = p.prof ? clock64() : 0;
     }
     tma_store_wait_all();
+    if (overlap) {
+      __syncwarp();
+      if (lane == 0 && done_tile >= 0) tile_part_done(p.tile_done + done_tile);
+    }
     if (p.prof && lane == 0)
       for (int k = 0; k < 3; ++k) atomicAdd(p.prof + 13 + k, (unsigned long long)pacc[k]);
   }
@@ -586,13 +659,16 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
     __syncthreads();
     if (tid == 0) {
       __threadfence();
-      if (atomicAdd(p.tile_counter + 1, 1) == (int)gridDim.x - 1) {
-        p.tile_counter[0] = 0;
-        p.tile_counter[1] = 0;
+      if (atomicAdd(tickets + 1, 1) == (int)gridDim.x - 1) {
+        tickets[0] = 0;
+        tickets[1] = 0;
         __threadfence();
       }
     }
   }
+  // stream order for whatever follows the NEXT launch: a grid that ends implies the grid before it has ended (it has, long
+  // ago -- its tiles were consumed above -- so this never waits in practice)
+  if (overlap) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 }  // namespace cbx

@@ -10,81 +10,38 @@
 //   * the scenario tables are read through L1 from global memory (30 KB at Chain-100, hot), which also makes a batch over
 //     several scenarios (cbx_batch_create_multi) free: a tile just points at its scenario's tables;
 //   * each warp owns a tile end to end -- no CTA-wide barrier in the loop, up to 14 tiles in flight per SM instead of 2;
-//   * the int32 observation fields are produced by the env's own thread, 32 words at a time, into a padded 32 x 36 shared-
-//     memory square and leave transposed with 16-byte stores (4 envs x 128 contiguous bytes per instruction); the property
-//     matrix is a bit stream expanded four words at a time through a 16-entry uint4 table.
+//   * the int32 observation fields leave in two phases.  Phase 1, one thread per env: GATHER what the field is made of from
+//     the env's own state column into a compact image in shared memory -- the property matrix as a bit stream (props bits per
+//     discovered node), privilege levels as 2-bit codes, the credential cache as (target index, port) byte pairs.  Phase 2,
+//     the whole warp on one env at a time: EXPAND the image to int32 words in registers and store them where they belong --
+//     every store instruction writes 512 contiguous bytes of one env's row.  (Round 1 produced the words thread-per-env into
+//     a 32 x 36 square and stored it transposed: 4 scattered 128-byte segments per instruction and ~2.5 x the instructions;
+//     profiles/r01_ncu_lines_wide_kernel.txt.)
+//   * the static rows of the defender's observation (firewall / service status: the LearningDefender acts on a stale copy,
+//     SURVEY.md B.1, so they never change) are written by RESET launches only; a step writes the infected-nodes row.
 // Factored masks only (what these configurations use: a dense Chain-100 connect mask is 8.5 MB per env).
 namespace cbx {
 
-constexpr int kImgStride = 36;  // padded row of the transpose square: 16-byte aligned, conflict-free for 128-bit accesses both ways
-
-// Streaming writer of one int32 field of a tile: every thread `put`s ITS env's words in order; after every 32 words the warp
-// stores the padded square transposed -- env e's 32 words are 128 contiguous bytes of the output tensor.  All lanes call
-// put() the same number of times (the field has the same length for every env), so the flushes are warp-uniform.
-struct FieldWriter {
-  int32_t* dst;     // the tile's first row of the output tensor (nullptr: field not materialised)
-  uint32_t* img;    // this warp's 32 x kImgStride square
-  const uint4* lut4;  // 17 entries: the 4 bits of a nibble as 4 int32 words; entry 16 = {2,2,2,2} ("unknown", blank observations)
-  int wpe, n_valid, lane, j, k0;
-  uint32_t mask;    // envs whose observation is (re)written
-  bool mine;        // this lane's env is one of them
-  __device__ __forceinline__ void flush(const int m) {  // the square holds words [k0, k0 + m) of every env
-    __syncwarp();
-    if ((wpe & 3) == 0) {  // env rows are 16-byte aligned: 4 envs x 128 bytes per store instruction
-      const int sub = lane >> 3, c4 = (lane & 7) * 4;
-      if (c4 < m) {
-#pragma unroll
-        for (int it = 0; it < CBX_TILE / 4; ++it) {
-          const int e = it * 4 + sub;
-          if (e < n_valid && ((mask >> e) & 1u))
-            *reinterpret_cast<uint4*>(dst + (size_t)e * wpe + k0 + c4) = *reinterpret_cast<const uint4*>(img + e * kImgStride + c4);
-        }
-      }
-    } else if (lane < m) {
-      int32_t* d = dst + k0 + lane;
-      const uint32_t* s = img + lane;
-      for (int e = 0; e < n_valid; ++e)
-        if ((mask >> e) & 1u) d[(size_t)e * wpe] = (int32_t)s[e * kImgStride];
-    }
-    __syncwarp();
-    k0 += m;
-    j = 0;
-  }
-  __device__ __forceinline__ void put(const uint32_t v) {
-    if (mine) img[lane * kImgStride + j] = v;
-    if (++j == 32) flush(32);
-  }
-  __device__ __forceinline__ void put4(const uint4 v) {  // j is a multiple of 4
-    if (mine) *reinterpret_cast<uint4*>(img + lane * kImgStride + j) = v;
-    j += 4;
-    if (j == 32) flush(32);
-  }
-  __device__ __forceinline__ void finish() {
-    if (j) flush(j);
-  }
-};
-
-// Bits -> int32 words, four at a time: the property matrix of an env is one long bit stream (props bits per discovered node).
-struct BitStream {
-  FieldWriter& fw;
-  uint64_t acc;
-  int nb;
-  bool blank;  // this env's observation is blank: every word is 2 (same control flow as the other lanes: flushes are collective)
-  __device__ __forceinline__ void append(const uint32_t lo, const uint32_t hi, const int nbits) {  // nbits <= 64 - 3
-    const uint64_t v = ((uint64_t)hi << 32) | lo;
-    acc |= v << nb;
-    nb += nbits;
-    while (nb >= 4) {
-      fw.put4(fw.lut4[blank ? 16u : ((uint32_t)acc & 15u)]);
-      acc >>= 4;
-      nb -= 4;
+// ---- phase 2: the warp expands one env's row of an int32 field ------------------------------------------------------------
+// `f(w0)` returns words [w0, w0 + 4) of the row (w0 a multiple of 4); words at or beyond wpe are not stored.  The row's
+// alignment decides the store width: 16 bytes when wpe is a multiple of 4 words, 8 when even, else 4.
+template <class F>
+__device__ __forceinline__ void emit_row(int32_t* row, const int w_begin, const int w_end, const int wpe, const int lane, F f) {
+  for (int w0 = w_begin + 4 * lane; w0 < w_end; w0 += 128) {
+    const uint4 v = f(w0);
+    if ((wpe & 3) == 0) {
+      *reinterpret_cast<uint4*>(row + w0) = v;
+    } else if ((wpe & 1) == 0) {
+      *reinterpret_cast<uint2*>(row + w0) = make_uint2(v.x, v.y);
+      if (w0 + 2 < wpe) *reinterpret_cast<uint2*>(row + w0 + 2) = make_uint2(v.z, v.w);
+    } else {
+      row[w0] = (int32_t)v.x;
+      if (w0 + 1 < wpe) row[w0 + 1] = (int32_t)v.y;
+      if (w0 + 2 < wpe) row[w0 + 2] = (int32_t)v.z;
+      if (w0 + 3 < wpe) row[w0 + 3] = (int32_t)v.w;
     }
   }
-  __device__ __forceinline__ void finish() {  // trailing bits (field length not a multiple of 4): word by word
-    for (int k = 0; k < nb; ++k) fw.put(blank ? 2u : ((uint32_t)(acc >> k) & 1u));
-    nb = 0;
-  }
-};
+}
 
 // Static rows of the defender observation for ONE env of the scenario `tb`: incoming [6n] | outgoing [6n] | services [nsvc],
 // each followed by its first 4 bytes again (reads wrap around the end of a row) and padded to a multiple of 4 bytes.
@@ -135,28 +92,18 @@ __global__ void __launch_bounds__(CBX_WIDE_WARPS * 32, 1) cbx_wide_kernel(const 
   const bool def_encode = def_on && !(op & CBX_OP_NOTIFY);
   const int DW = p.enc.desc_words;
   const int AW = marlon ? 10 : 5;
-  uint2* s_lut = reinterpret_cast<uint2*>(smem + Q.lut);
   uint32_t* wb = smem + Q.warps + warp * Q.warp_words;  // this warp's private area
   uint32_t* sg = wb + Q.w_stage;
   uint32_t* desc = wb + Q.w_desc;
-  int32_t* act = reinterpret_cast<int32_t*>(wb + Q.w_acts);
-  uint32_t* img = wb + Q.w_img;
-  uint8_t* drows = reinterpret_cast<uint8_t*>(wb + Q.w_drows);
-  for (int k = tid; k < 256; k += (int)blockDim.x) {
-    uint32_t lo = ((k & 0xF) * 0x00204081u) & 0x01010101u, hi = (((k >> 4) & 0xF) * 0x00204081u) & 0x01010101u;
-    s_lut[k] = make_uint2(lo, hi);
-  }
-  if (tid < 17) {
-    uint4* l4 = reinterpret_cast<uint4*>(smem + Q.lut4);
-    l4[tid] = tid == 16 ? make_uint4(2u, 2u, 2u, 2u) : make_uint4(tid & 1u, (tid >> 1) & 1u, (tid >> 2) & 1u, (tid >> 3) & 1u);
-  }
-  __syncthreads();  // the only CTA-wide barrier
+  uint32_t* img = wb + Q.w_img;                          // packed field images, IS words per env; the tile's actions before that
+  int32_t* act = reinterpret_cast<int32_t*>(img);
+  const int IS = Q.img_stride;                           // odd: thread-per-env writes are bank-conflict free
+  constexpr uint32_t kFull = 0xFFFFFFFFu;
 
   Acc acc;
 #pragma unroll
   for (int k = 0; k < CBX_STAT_COUNT; ++k) acc.v[k] = 0.0;
   int slice_of_kind[3] = {p.slice_of_kind[0], p.slice_of_kind[1], p.slice_of_kind[2]};
-  int rows_scn = -1;  // scenario the defender rows in `drows` were built for
   long long prof_t = p.prof ? clock64() : 0;
   long long pp[6] = {0, 0, 0, 0, 0, 0};  // per-warp phase cycles (instrumentation slots 1..6), flushed once at the end
 #define CBX_WPROF(slot)                    \
@@ -168,13 +115,17 @@ __global__ void __launch_bounds__(CBX_WIDE_WARPS * 32, 1) cbx_wide_kernel(const 
   const int n6 = 6 * L.n;
   const int nw = (int)blockDim.x >> 5;  // warps per CTA (<= CBX_WIDE_WARPS)
   const int gw = (int)gridDim.x * nw;
+  const int NPROPS = L.nprops, PW = L.PW;
+  const uint32_t keep_lo = NPROPS >= 32 ? 0xFFFFFFFFu : ((1u << NPROPS) - 1u);
+  const uint32_t keep_hi = NPROPS > 32 ? (NPROPS >= 64 ? 0xFFFFFFFFu : ((1u << (NPROPS - 32)) - 1u)) : 0u;
+  const int wpe_leak = 4 * L.LEAK, wpe_cachem = 2 * L.C, wpe_props = L.N * NPROPS, wpe_priv = L.N;
   // tile order: static stride, or (Q.dynamic) every tile after a warp's first is the next ticket of a global counter, so that
   // warps on faster SMs -- and, in a multi-scenario batch, warps that drew cheap tiles -- take more of them
   auto next_tile = [&](int t) {
     if (!Q.dynamic) return t + gw;
     int x = 0;
     if (lane == 0) x = gw + atomicAdd(p.tile_counter, 1);
-    return __shfl_sync(0xFFFFFFFFu, x, 0);
+    return __shfl_sync(kFull, x, 0);
   };
   for (int tile = (int)blockIdx.x * nw + warp; tile < p.n_tiles; tile = next_tile(tile)) {
     const int64_t e0 = (int64_t)tile * CBX_TILE;
@@ -185,12 +136,14 @@ __global__ void __launch_bounds__(CBX_WIDE_WARPS * 32, 1) cbx_wide_kernel(const 
     uint32_t* gst = p.state + (int64_t)tile * L.S * CBX_TILE;        // the tile's state, in place
     // pull the tile's S lines towards L2 now, all at once: the game logic's dependent accesses then pay L2 latency, not HBM's
     for (int r = lane; r < L.S; r += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(gst + (size_t)r * CBX_TILE));
-    if (!reset_only) {
+    auto load_actions = [&]() {
+      if (reset_only) return;
       if (p.att_actions && (who_att || !marlon))
         for (int q = lane; q < n_valid * AW; q += 32) act[q] = load_act(p.att_actions, e0 * AW + q, p.act_i16);
       if (def_on)
         for (int q = lane; q < n_valid * 12; q += 32) act[CBX_TILE * 10 + q] = load_act(p.def_actions, e0 * 12 + q, p.act_i16);
-    }
+    };
+    load_actions();
     __syncwarp();
     CBX_WPROF(1)  // actions in
     const bool active = lane < n_valid;
@@ -202,136 +155,209 @@ __global__ void __launch_bounds__(CBX_WIDE_WARPS * 32, 1) cbx_wide_kernel(const 
       att_done = c.g(STG_ATT_DONE);
       keep = c.g(STG_OBS_KIND) == OBS_KEEP;
     }
-    const uint32_t att_done_mask = __ballot_sync(0xFFFFFFFFu, att_done != 0);
-    const uint32_t keep1 = __ballot_sync(0xFFFFFFFFu, keep != 0);
+    const uint32_t att_done_mask = __ballot_sync(kFull, att_done != 0);
+    const uint32_t keep1 = __ballot_sync(kFull, keep != 0);
     CBX_WPROF(2)  // attacker logic
-    Tile t;
-    t.L = &L; t.tb = tb; t.st = gst; t.sg = sg; t.desc = desc; t.lut = s_lut; t.K = &p.enc; t.DW = DW;
-    // terminal observations of the envs that finished: BEFORE the auto-reset (rare; element-wise encoder)
-    if (att_done_mask && cfg.auto_reset && cfg.emit_terminal_obs && !reset_only) {
-      if (active && ((att_done_mask >> lane) & 1u)) build_desc(c, desc + lane * DW, DW, nullptr);
-      __syncwarp();
-      Target tt = make_target(p.v, L, e0, true);
-      EnvMask m_enc, m_cp;
-#pragma unroll
-      for (int q = 0; q < kGroups; ++q) { m_enc.w[q] = 0; m_cp.w[q] = 0; }
-      m_enc.w[0] = att_done_mask & ~keep1;
-      m_cp.w[0] = att_done_mask & keep1;
-      encode_attacker<ENC>(t, tt, n_valid, m_enc, 0, 1);
-      if (m_cp.any()) {
-        Target tm = make_target(p.v, L, e0, false);
-        copy_rows(tt.scalars, tm.scalars, 32, n_valid, m_cp, lane, 32);
-        copy_rows(tt.leaked, tm.leaked, 16 * L.LEAK, n_valid, m_cp, lane, 32);
-        copy_rows(tt.cachem, tm.cachem, 8 * L.C, n_valid, m_cp, lane, 32);
-        copy_rows(tt.props, tm.props, 4 * L.N * L.nprops, n_valid, m_cp, lane, 32);
-        copy_rows(tt.priv, tm.priv, 4 * L.N, n_valid, m_cp, lane, 32);
-      }
-      __syncwarp();
-    }
+    const bool need_term = att_done_mask && cfg.auto_reset && cfg.emit_terminal_obs && !reset_only;
     uint32_t def_done = 0;
-    keep = 1;
-    if (active) {
-      def_done = logic_phase2(c, p, op, act + CBX_TILE * 10 + lane * 12, s_init, desc + lane * DW, acc);
-      keep = c.g(STG_OBS_KIND) == OBS_KEEP;
-      if (def_done && cfg.emit_terminal_obs && p.v.term_def_infected_nodes) {
-        int8_t* ti = p.v.term_def_infected_nodes + c.env * L.n;
-        for (int i = 0; i < L.n; ++i) ti[i] = (int8_t)((c.g(STG_DEF_TERM_INST + (i >> 5)) >> (i & 31)) & 1u);
-      }
-    }
-    const uint32_t enc_mask = ~__ballot_sync(0xFFFFFFFFu, keep != 0);
-    __syncwarp();
-    CBX_WPROF(4)  // auto-reset, defender logic, descriptors
-    // ---- the attacker's observation fields, transposed through the padded square ----
-    {
-      const Target tm = make_target(p.v, L, e0, false);
-      const uint32_t* de = desc + lane * DW;
-      const bool mine = active && !keep;
-      const int nd = mine ? (int)de[D_ND] : 0, nc = mine ? (int)de[D_NC] : 0;
-      const bool blank = mine && de[D_KIND] == OBS_BLANK;
-      FieldWriter fw;
-      fw.img = img; fw.n_valid = n_valid; fw.lane = lane; fw.mask = enc_mask; fw.mine = mine;
-      fw.lut4 = reinterpret_cast<const uint4*>(smem + Q.lut4);
-      auto begin = [&](int32_t* dst, int wpe) { fw.dst = dst; fw.wpe = wpe; fw.j = 0; fw.k0 = 0; };
-      begin(tm.scalars, 8);
+    // pass 0 (rare): terminal observations of the envs that finished, BEFORE the auto-reset; pass 1: this step's observations
+    for (int pass = need_term ? 0 : 1; pass < 2; ++pass) {
+      uint32_t emit_mask;
+      if (pass == 0) {
+        if (active && ((att_done_mask >> lane) & 1u)) build_desc(c, desc + lane * DW, DW, nullptr);
+        emit_mask = att_done_mask & ~keep1;
+        const uint32_t cp = att_done_mask & keep1;
+        if (cp) {  // intercepted-and-truncated step: the terminal observation is the previous one
+          EnvMask m_cp;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) fw.put(mine ? c.g(STG_SCALARS + k) : 0u);
-      fw.finish();
-      begin(tm.leaked, 4 * L.LEAK);
-      for (int k = 0; k < 4 * L.LEAK; ++k) fw.put((mine && k < 4 * L.LEAKS) ? c.g(L.g_leaked + k) : 0u);
-      fw.finish();
-      begin(tm.cachem, 2 * L.C);  // credential_cache_matrix [C][2]: (target discovery index, port) per cached credential
-      for (int i = 0; i < L.C; ++i) {
-        uint32_t a = 0, b = 0;
-        if (!blank && i < nc) {
-          const uint32_t* rec = c.triple((int)c.half(L.o_cache, i));
-          a = c.byte(L.o_disc_idx, (int)rec[0]);
-          b = rec[1];
-        }
-        fw.put(a);
-        fw.put(b);
-      }
-      fw.finish();
-      begin(tm.props, L.N * L.nprops);  // discovered_nodes_properties [N][props]; 2 = unknown only in blank observations
-      if (L.nprops > 60) {  // word by word (warp-uniform choice: the flushes inside are collective)
-        for (int kk = 0; kk < L.N; ++kk) {
-          uint32_t lo = 0, hi = 0;
-          if (!blank && kk < nd) {
-            const int node = (int)c.byte(L.o_disc_order, kk);
-            lo = c.w(L.o_props + node * L.PW);
-            if (L.PW > 1) hi = c.w(L.o_props + node * L.PW + 1);
-          }
-          for (int pi = 0; pi < L.nprops; ++pi) fw.put(blank ? 2u : (((pi < 32 ? lo : hi) >> (pi & 31)) & 1u));
+          for (int q = 0; q < kGroups; ++q) m_cp.w[q] = 0;
+          m_cp.w[0] = cp;
+          const Target tt = make_target(p.v, L, e0, true), tm = make_target(p.v, L, e0, false);
+          copy_rows(tt.scalars, tm.scalars, 32, n_valid, m_cp, lane, 32);
+          copy_rows(tt.leaked, tm.leaked, 16 * L.LEAK, n_valid, m_cp, lane, 32);
+          copy_rows(tt.cachem, tm.cachem, 8 * L.C, n_valid, m_cp, lane, 32);
+          copy_rows(tt.props, tm.props, 4 * L.N * L.nprops, n_valid, m_cp, lane, 32);
+          copy_rows(tt.priv, tm.priv, 4 * L.N, n_valid, m_cp, lane, 32);
         }
       } else {
-        BitStream bs{fw, 0ull, 0, blank};
-        const uint32_t keep_lo = L.nprops >= 32 ? 0xFFFFFFFFu : ((1u << L.nprops) - 1u);
-        const uint32_t keep_hi = L.nprops > 32 ? ((1u << (L.nprops - 32)) - 1u) : 0u;
-        for (int kk = 0; kk < L.N; ++kk) {
-          uint32_t lo = 0, hi = 0;
-          if (kk < nd) {
-            const int node = (int)c.byte(L.o_disc_order, kk);
-            lo = c.w(L.o_props + node * L.PW) & keep_lo;
-            if (L.PW > 1) hi = c.w(L.o_props + node * L.PW + 1) & keep_hi;
+        if (need_term) {  // the terminal pass used the image area: the tile's actions again
+          __syncwarp();
+          load_actions();
+          __syncwarp();
+        }
+        keep = 1;
+        if (active) {
+          def_done = logic_phase2(c, p, op, act + CBX_TILE * 10 + lane * 12, s_init, desc + lane * DW, acc);
+          keep = c.g(STG_OBS_KIND) == OBS_KEEP;
+          if (def_done && cfg.emit_terminal_obs && p.v.term_def_infected_nodes) {
+            int8_t* ti = p.v.term_def_infected_nodes + c.env * L.n;
+            for (int i = 0; i < L.n; ++i) ti[i] = (int8_t)((c.g(STG_DEF_TERM_INST + (i >> 5)) >> (i & 31)) & 1u);
           }
-          bs.append(lo, hi, L.nprops);
         }
-        bs.finish();
+        emit_mask = ~__ballot_sync(kFull, keep != 0);
+        CBX_WPROF(4)  // auto-reset, defender logic, descriptors
       }
-      fw.finish();
-      begin(tm.priv, L.N);  // nodes_privilegelevel [N] in discovery order, as the observation saw it (staging snapshot)
-      for (int k = 0; k < L.N; ++k) {
-        uint32_t val = 0;
-        if (!blank && k < nd) {
-          const uint32_t node = c.byte(L.o_disc_order, k);
-          val = (c.g(L.g_priv + (node >> 4)) >> ((node & 15) * 2)) & 3u;
-        }
-        fw.put(val);
+      __syncwarp();
+      emit_mask &= n_valid == CBX_TILE ? kFull : ((1u << n_valid) - 1u);
+      if (!emit_mask) continue;
+      // ---- the attacker's observation fields of the envs in emit_mask ----
+      const Target tm = make_target(p.v, L, e0, pass == 0);
+      const uint32_t* de = desc + lane * DW;
+      const bool mine = (emit_mask >> lane) & 1u;
+      const int nd = mine ? (int)de[D_ND] : 0, nc = mine ? (int)de[D_NC] : 0;
+      const bool blank = mine && de[D_KIND] == OBS_BLANK;
+      const int nd_eff = blank ? 0 : nd, nc_eff = blank ? 0 : nc;  // a blank observation shows nothing but its counts
+      int nleak = 0;
+      if (mine) {
+        // scalars: this thread's own 8 words, two 16-byte stores (a tile's rows are contiguous: 1 KB per warp)
+        uint4* so = reinterpret_cast<uint4*>(tm.scalars + (size_t)lane * 8);
+        so[0] = make_uint4(c.g(STG_SCALARS + 0), c.g(STG_SCALARS + 1), c.g(STG_SCALARS + 2), c.g(STG_SCALARS + 3));
+        so[1] = make_uint4(c.g(STG_SCALARS + 4), c.g(STG_SCALARS + 5), c.g(STG_SCALARS + 6), c.g(STG_SCALARS + 7));
+        for (int k = 0; k < L.LEAKS; ++k) nleak += c.g(L.g_leaked + 4 * k) != 0;  // slots fill in order (ENV:890-907)
       }
-      fw.finish();
-      CBX_WPROF(5)  // attacker observation fields
-      // ---- the defender's observation of the tile ----
-      if (def_encode) {
-        if (n_valid == CBX_TILE) {
-          if (rows_scn != scn) { build_defender_rows(tb, drows, L.n, L.nservices, lane); rows_scn = scn; __syncwarp(); }
-          // infected_nodes [32][n]: bit i of env e's installed bits (descriptor), 4 bytes per lane and iteration
-          const int words = CBX_TILE * L.n / 4;
-          uint32_t* di32 = reinterpret_cast<uint32_t*>(tm.infected);
-          const FastDiv dn(p.enc.d_n);
-          for (int w = lane; w < words; w += 32) {
-            uint32_t v = 0;
-#pragma unroll
-            for (int bb = 0; bb < 4; ++bb) {
-              const uint32_t b = (uint32_t)w * 4u + bb, e = dn.div(b), i = b - e * L.n;
-              v |= ((desc[e * DW + D_OWNED + L.OW + (i >> 5)] >> (i & 31)) & 1u) << (8 * bb);
+      // leaked_credentials [LEAK][4]: almost always all zero; a used slot is read from the staging words as it is
+      for (int e = 0; e < n_valid; ++e) {
+        if (!((emit_mask >> e) & 1u)) continue;
+        const int nl = __shfl_sync(kFull, nleak, e);
+        emit_row(tm.leaked + (size_t)e * wpe_leak, 0, wpe_leak, wpe_leak, lane, [&](int w0) {
+          const int slot = w0 >> 2;
+          if (slot >= nl) return make_uint4(0u, 0u, 0u, 0u);
+          const uint32_t* q = sg + (L.g_leaked + 4 * slot) * CBX_TILE + e;
+          return make_uint4(q[0], q[CBX_TILE], q[2 * CBX_TILE], q[3 * CBX_TILE]);
+        });
+      }
+      // credential_cache_matrix [C][2] = (target discovery index, port) per cached credential: 16 bits per entry
+      {
+        const int ncmax = __reduce_max_sync(kFull, nc_eff);
+        const int EC = 2 * Q.img_words;  // entries per chunk
+        for (int c0 = 0; c0 < L.C; c0 += EC) {
+          const int c1 = min(L.C, c0 + EC), chi = min(c1, ncmax);
+          for (int i = c0; i < chi; i += 2) {  // phase 1: every thread packs ITS env's entries i, i + 1
+            uint32_t pk = 0;
+            if (i < nc_eff) {
+              const uint32_t cw = c.w(L.o_cache + (i >> 1));
+              const uint32_t* r0 = c.triple((int)(cw & 0xFFFFu));
+              pk = c.byte(L.o_disc_idx, (int)r0[0]) | (r0[1] << 8);
+              if (i + 1 < nc_eff) {
+                const uint32_t* r1 = c.triple((int)(cw >> 16));
+                pk |= (c.byte(L.o_disc_idx, (int)r1[0]) | (r1[1] << 8)) << 16;
+              }
             }
-            di32[w] = v;
+            img[lane * IS + ((i - c0) >> 1)] = pk;
           }
+          __syncwarp();
+          for (int e = 0; e < n_valid; ++e) {  // phase 2
+            if (!((emit_mask >> e) & 1u)) continue;
+            const int nce = __shfl_sync(kFull, nc_eff, e);
+            const uint32_t* im = img + e * IS;
+            emit_row(tm.cachem + (size_t)e * wpe_cachem, 2 * c0, 2 * c1, wpe_cachem, lane, [&](int w0) {
+              const int i = w0 >> 1;  // entries i, i + 1
+              if (i >= nce) return make_uint4(0u, 0u, 0u, 0u);
+              const uint32_t pk = im[(i - c0) >> 1];
+              return make_uint4(pk & 0xFFu, (pk >> 8) & 0xFFu, (pk >> 16) & 0xFFu, pk >> 24);
+            });
+          }
+          __syncwarp();
+        }
+      }
+      // discovered_nodes_properties [N][props] as a bit stream (props bits per discovered node, discovery order) and
+      // nodes_privilegelevel [N] as 2-bit codes behind it; a chunk holds NPC nodes (all of them at Chain-100)
+      {
+        const int ndmax = __reduce_max_sync(kFull, nd_eff);
+        const bool any_blank = __any_sync(kFull, blank);
+        const int NPC = Q.nodes_per_chunk;  // a multiple of 4: a chunk starts on a 16-byte boundary of the row
+        for (int k0 = 0; k0 < L.N; k0 += NPC) {
+          const int k1 = min(L.N, k0 + NPC), khi = min(k1, ndmax);
+          const int priv_at = Q.img_words - ((NPC + 15) >> 4);  // 2-bit codes of the chunk's nodes, behind the bit stream
+          {  // phase 1
+            uint64_t bits = 0;
+            int nb = 0, wi = 0;
+            uint32_t dw = 0, pv = 0;
+            for (int k = k0; k < khi; ++k) {
+              if ((k & 3) == 0 || k == k0) dw = c.w(L.o_disc_order + (k >> 2));
+              uint32_t lo = 0, hi = 0, lvl = 0;
+              if (k < nd_eff) {
+                const uint32_t node = (dw >> ((k & 3) * 8)) & 0xFFu;
+                lo = c.w(L.o_props + node * PW) & keep_lo;
+                if (PW > 1) hi = c.w(L.o_props + node * PW + 1) & keep_hi;
+                lvl = (c.g(L.g_priv + (node >> 4)) >> ((node & 15) * 2)) & 3u;
+              }
+              bits |= (uint64_t)lo << nb;
+              nb += NPROPS < 32 ? NPROPS : 32;
+              if (nb >= 32) { img[lane * IS + wi++] = (uint32_t)bits; bits >>= 32; nb -= 32; }
+              if (NPROPS > 32) {
+                bits |= (uint64_t)hi << nb;
+                nb += NPROPS - 32;
+                if (nb >= 32) { img[lane * IS + wi++] = (uint32_t)bits; bits >>= 32; nb -= 32; }
+              }
+              const int j = (k - k0) & 15;
+              pv |= lvl << (2 * j);
+              if (j == 15) { img[lane * IS + priv_at + ((k - k0) >> 4)] = pv; pv = 0; }
+            }
+            if (nb > 0) img[lane * IS + wi] = (uint32_t)bits;
+            if (khi > k0 && ((khi - k0) & 15)) img[lane * IS + priv_at + ((khi - 1 - k0) >> 4)] = pv;
+          }
+          __syncwarp();
+          for (int e = 0; e < n_valid; ++e) {  // phase 2
+            if (!((emit_mask >> e) & 1u)) continue;
+            const int nde = __shfl_sync(kFull, nd_eff, e);
+            const bool bl = any_blank && __shfl_sync(kFull, (int)blank, e);
+            const uint32_t* im = img + e * IS;
+            const int lim = (min(nde, k1) - k0) * NPROPS;  // bits of this chunk that the env's own thread wrote
+            emit_row(tm.props + (size_t)e * wpe_props, k0 * NPROPS, k1 * NPROPS, wpe_props, lane, [&](int w0) {
+              if (bl) return make_uint4(2u, 2u, 2u, 2u);  // "unknown": blank observations only (ENV:765)
+              const int b = w0 - k0 * NPROPS;
+              if (b >= lim) return make_uint4(0u, 0u, 0u, 0u);
+              const uint32_t nib = im[b >> 5] >> (b & 31);  // b is a multiple of 4: a nibble never straddles a word
+              return make_uint4(nib & 1u, (nib >> 1) & 1u, (nib >> 2) & 1u, (nib >> 3) & 1u);
+            });
+            emit_row(tm.priv + (size_t)e * wpe_priv, k0, k1, wpe_priv, lane, [&](int w0) {
+              if (w0 >= nde) return make_uint4(0u, 0u, 0u, 0u);
+              const int b = 2 * (w0 - k0);
+              const uint32_t q = im[priv_at + (b >> 5)] >> (b & 31);
+              return make_uint4(q & 3u, (q >> 2) & 3u, (q >> 4) & 3u, (q >> 6) & 3u);
+            });
+          }
+          __syncwarp();
+        }
+      }
+      if (pass == 1) CBX_WPROF(5)  // attacker observation fields
+    }
+    // ---- the defender's observation of the tile ----
+    if (def_encode) {
+      const Target tm = make_target(p.v, L, e0, false);
+      if (n_valid == CBX_TILE) {
+        // infected_nodes [32][n] bytes: every thread lays out ITS env's row in the (unpadded) tile image, then the warp copies
+        // the 32 * n contiguous bytes out with 16-byte stores
+        uint8_t* ib = reinterpret_cast<uint8_t*>(img);
+        const uint32_t* di = desc + lane * DW + D_OWNED + L.OW;
+        if ((L.n & 1) == 0) {
+          uint16_t* row = reinterpret_cast<uint16_t*>(ib + lane * L.n);
+          for (int i = 0; i < L.n; i += 2) {
+            const uint32_t two = (di[i >> 5] >> (i & 31)) & 3u;
+            row[i >> 1] = (uint16_t)((two & 1u) | ((two & 2u) << 7));
+          }
+        } else {
+          for (int i = 0; i < L.n; ++i) ib[lane * L.n + i] = (uint8_t)((di[i >> 5] >> (i & 31)) & 1u);
+        }
+        __syncwarp();
+        uint4* dst = reinterpret_cast<uint4*>(tm.infected);
+        const uint4* src = reinterpret_cast<const uint4*>(img);
+        for (int q = lane; q < CBX_TILE * L.n / 16; q += 32) dst[q] = src[q];
+        __syncwarp();
+        if (reset_only) {  // the static rows: written when an env is (re)created, never by a step (they cannot change)
+          uint8_t* drows = reinterpret_cast<uint8_t*>(img);
+          build_defender_rows(tb, drows, L.n, L.nservices, lane);
+          __syncwarp();
           emit_periodic_bytes(tm.fw_in, drows, n6, lane);
           emit_periodic_bytes(tm.fw_out, drows + defender_row_stride(n6), n6, lane);
           emit_periodic_bytes(tm.services, drows + 2 * defender_row_stride(n6), L.nservices, lane);
-        } else {
-          encode_defender_by_warp<DimsDyn>(t, tm, n_valid, mask_all(), true, 0, 1);  // ragged last tile
+          __syncwarp();
         }
+      } else {
+        Tile t;
+        t.L = &L; t.tb = tb; t.st = gst; t.sg = sg; t.desc = desc; t.lut = nullptr; t.K = &p.enc; t.DW = DW;
+        encode_defender_by_warp<DimsDyn>(t, tm, n_valid, mask_all(), reset_only, 0, 1);  // ragged last tile
       }
     }
     // deferred defender auto-reset (DummyVecEnv resets after the step; the observations above were taken before it)
@@ -347,7 +373,7 @@ __global__ void __launch_bounds__(CBX_WIDE_WARPS * 32, 1) cbx_wide_kernel(const 
 #pragma unroll
   for (int k = 0; k < CBX_STAT_COUNT; ++k) {
     double x = acc.v[k];
-    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xFFFFFFFFu, x, o);
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(kFull, x, o);
     if (lane == 0 && x != 0.0) atomicAdd(p.v.episode_stats + k, x);
   }
   if (Q.dynamic) {  // the last CTA to finish leaves the ticket counter at zero for the next launch

@@ -148,12 +148,15 @@ class BatchedVecEnv(_SB3VecEnv):
                     import torch
 
                     rows = self._obs(terminal=True, rows=torch.as_tensor(want, device=b.torch_device))
+                    # one split per key (a tuple of row views), not one indexing call per env and key: a torch index costs
+                    # microseconds and there are thousands of finished envs per step at bench sizes
                     keys = list(rows)
+                    cols = [rows[k].unbind(0) if self.observations == "torch" else list(rows[k]) for k in keys]
                     pos = {int(e): j for j, e in enumerate(want.tolist())}
                     for info, e in zip(made, idx.tolist()):
                         j = pos.get(e)
                         if j is not None:
-                            info["terminal_observation"] = {k: rows[k][j] for k in keys}
+                            info["terminal_observation"] = {k: c[j] for k, c in zip(keys, cols)}
             for info, e in zip(made, idx.tolist()):
                 infos[e] = info
             self._ep_ret[idx] = 0

@@ -36,3 +36,14 @@ def test_totals_are_sums_and_state_is_read_and_written_once():
         ab = bench.algorithmic_bytes_per_env_step(comp, cfg, S)
         assert ab["total"] == sum(v for k, v in ab.items() if k != "total"), w
         assert ab["state_rw"] == 2 * 4 * S, w
+
+
+def test_in_place_kernel_counts_only_what_a_step_moves():
+    """cbx_wide_kernel (Chain-100): the numerator is LOWER than SURVEY 8(d)'s -- state words a step does not touch and the
+    defender's static rows (written at reset only) are not counted."""
+    comp, cfg = bench.workload_config(workload="chain100")
+    ab = bench.in_place_kernel_bytes(comp, cfg, _bytes("chain100"))
+    assert ab["survey_8d_total"] == 11896
+    assert ab["defender_obs"] == 102 and ab["attacker_obs"] == 7044 and ab["masks"] == 16
+    assert ab["state_rw"] == 4 * (2 * (13 + 26 + 2) + (4 + 7 + 52 + 102 + 51)) == 1192
+    assert ab["total"] == 7044 + 16 + 102 + 1192 + 100 == 8454
