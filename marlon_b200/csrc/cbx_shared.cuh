@@ -626,6 +626,27 @@ __device__ __forceinline__ void encode_defender(const Tile& t, const Target& o, 
   write_i8(o.services, L->nservices, K.d_svc, n_valid, enc_mask, [&](int, int i) -> uint32_t { return i < nsvc_own ? 1u : 0u; });
 }
 
+// ---- the warp writes one env's row of an int32 field (cbx_wide.cuh, cbx_pipe.cuh: gather thread-per-env, expand warp-per-env) ----
+// `f(w0)` returns words [w0, w0 + 4) of the row (w0 a multiple of 4); words at or beyond wpe are not stored.  The row's
+// alignment decides the store width: 16 bytes when wpe is a multiple of 4 words, 8 when even, else 4.
+template <class F>
+__device__ __forceinline__ void emit_row(int32_t* row, const int w_begin, const int w_end, const int wpe, const int lane, F f) {
+  for (int w0 = w_begin + 4 * lane; w0 < w_end; w0 += 128) {
+    const uint4 v = f(w0);
+    if ((wpe & 3) == 0) {
+      *reinterpret_cast<uint4*>(row + w0) = v;
+    } else if ((wpe & 1) == 0) {
+      *reinterpret_cast<uint2*>(row + w0) = make_uint2(v.x, v.y);
+      if (w0 + 2 < wpe) *reinterpret_cast<uint2*>(row + w0 + 2) = make_uint2(v.z, v.w);
+    } else {
+      row[w0] = (int32_t)v.x;
+      if (w0 + 1 < wpe) row[w0 + 1] = (int32_t)v.y;
+      if (w0 + 2 < wpe) row[w0 + 2] = (int32_t)v.z;
+      if (w0 + 3 < wpe) row[w0 + 3] = (int32_t)v.w;
+    }
+  }
+}
+
 // copy env rows main -> terminal buffers (terminal observation of an intercepted-and-truncated step is the previous one)
 static __device__ void copy_rows(void* dst, const void* src, int bpe, int n_valid, const EnvMask& mask, int tidx = threadIdx.x,
                           int nthreads = CBX_THREADS) {

@@ -22,27 +22,6 @@
 // Factored masks only (what these configurations use: a dense Chain-100 connect mask is 8.5 MB per env).
 namespace cbx {
 
-// ---- phase 2: the warp expands one env's row of an int32 field ------------------------------------------------------------
-// `f(w0)` returns words [w0, w0 + 4) of the row (w0 a multiple of 4); words at or beyond wpe are not stored.  The row's
-// alignment decides the store width: 16 bytes when wpe is a multiple of 4 words, 8 when even, else 4.
-template <class F>
-__device__ __forceinline__ void emit_row(int32_t* row, const int w_begin, const int w_end, const int wpe, const int lane, F f) {
-  for (int w0 = w_begin + 4 * lane; w0 < w_end; w0 += 128) {
-    const uint4 v = f(w0);
-    if ((wpe & 3) == 0) {
-      *reinterpret_cast<uint4*>(row + w0) = v;
-    } else if ((wpe & 1) == 0) {
-      *reinterpret_cast<uint2*>(row + w0) = make_uint2(v.x, v.y);
-      if (w0 + 2 < wpe) *reinterpret_cast<uint2*>(row + w0 + 2) = make_uint2(v.z, v.w);
-    } else {
-      row[w0] = (int32_t)v.x;
-      if (w0 + 1 < wpe) row[w0 + 1] = (int32_t)v.y;
-      if (w0 + 2 < wpe) row[w0 + 2] = (int32_t)v.z;
-      if (w0 + 3 < wpe) row[w0 + 3] = (int32_t)v.w;
-    }
-  }
-}
-
 // Static rows of the defender observation for ONE env of the scenario `tb`: incoming [6n] | outgoing [6n] | services [nsvc],
 // each followed by its first 4 bytes again (reads wrap around the end of a row) and padded to a multiple of 4 bytes.
 __device__ __forceinline__ int defender_row_stride(const int len) { return (len + 4 + 3) & ~3; }

@@ -47,6 +47,71 @@ _DEF_FIELDS = {"infected_nodes": "def_infected_nodes", "incoming_firewall_status
                "outgoing_firewall_status": "def_outgoing_firewall", "services_status": "def_services_status"}
 
 
+class _LazyRow(dict):
+    """``infos[i]["terminal_observation"]``: row `j` of the gathered terminal observations, materialised on first use.
+    A dict to every consumer (SB3's ``obs_to_tensor`` deep-copies it and iterates ``items()``); building thousands of 14-key
+    dicts per step eagerly would cost more host time than the whole batch's step."""
+
+    __slots__ = ("_src", "_j")
+
+    def __init__(self, src, j):
+        super().__init__()
+        self._src, self._j = src, j
+
+    def _fill(self):
+        src = self._src
+        if src is not None:
+            self._src = None
+            dict.update(self, {k: v[self._j] for k, v in src.items()})
+        return self
+
+    def __getitem__(self, k):
+        return dict.__getitem__(self._fill(), k)
+
+    def __iter__(self):
+        return dict.__iter__(self._fill())
+
+    def __len__(self):
+        return dict.__len__(self._fill())
+
+    def __contains__(self, k):
+        return dict.__contains__(self._fill(), k)
+
+    def keys(self):
+        return dict.keys(self._fill())
+
+    def values(self):
+        return dict.values(self._fill())
+
+    def items(self):
+        return dict.items(self._fill())
+
+    def get(self, k, default=None):
+        return dict.get(self._fill(), k, default)
+
+    def copy(self):
+        return dict(self._fill())
+
+    def __eq__(self, other):
+        return dict.__eq__(self._fill(), other)
+
+    def __ne__(self, other):
+        return not self.__eq__(other)
+
+    __hash__ = None
+
+    def __repr__(self):
+        return dict.__repr__(self._fill())
+
+    def __deepcopy__(self, memo):
+        import copy
+
+        return {k: copy.deepcopy(v, memo) for k, v in self._fill().items()}
+
+    def __reduce__(self):
+        return (dict, (dict(self._fill()),))
+
+
 class BatchedVecEnv(_SB3VecEnv):
     def __init__(self, universe, role: str = "attacker", observations: str = "torch", terminal_observations: str = "all"):
         """`observations`: "torch" (device tensor views) or "numpy" (host arrays, one packed copy per step).
@@ -148,15 +213,13 @@ class BatchedVecEnv(_SB3VecEnv):
                     import torch
 
                     rows = self._obs(terminal=True, rows=torch.as_tensor(want, device=b.torch_device))
-                    # one split per key (a tuple of row views), not one indexing call per env and key: a torch index costs
-                    # microseconds and there are thousands of finished envs per step at bench sizes
-                    keys = list(rows)
-                    cols = [rows[k].unbind(0) if self.observations == "torch" else list(rows[k]) for k in keys]
+                    # rows are sliced when somebody reads them (_LazyRow): thousands of envs finish per step at bench sizes and
+                    # one index call per env and key would cost more host time than the step itself
                     pos = {int(e): j for j, e in enumerate(want.tolist())}
                     for info, e in zip(made, idx.tolist()):
                         j = pos.get(e)
                         if j is not None:
-                            info["terminal_observation"] = {k: c[j] for k, c in zip(keys, cols)}
+                            info["terminal_observation"] = _LazyRow(rows, j)
             for info, e in zip(made, idx.tolist()):
                 infos[e] = info
             self._ep_ret[idx] = 0
