@@ -442,8 +442,10 @@ int cbx_gae(const float* rewards, const float* values, const uint8_t* episode_st
  * ordered tile by tile through completion counters in HBM). */
 int cbx_batch_kernel_info(const cbx_batch* b, int32_t* out8);
 
-/* Parity instrumentation: the dynamic tile order's global counters {tickets handed out, CTAs finished}; both must read 0
- * between launches (the last CTA of a launch resets them).  Synchronises the device. */
+/* Parity instrumentation of the dynamic tile order; both words must read 0 between launches.  Warp-per-tile kernel: the
+ * global counters {tickets handed out, CTAs finished} (the last CTA of a launch resets them).  Pipelined kernel: {tickets
+ * the last launch drew from its own counter - the number of tiles, 0}: every logic warp draws until one ticket is past the
+ * end, which makes exactly n_tiles draws per launch.  Synchronises the device. */
 int cbx_batch_tile_counter(cbx_batch* b, int32_t* out2);
 
 /* Instrumentation: per-phase SM cycle counters of the step kernel, summed over CTAs (thread 0 of each CTA):

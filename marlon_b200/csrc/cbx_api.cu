@@ -66,7 +66,7 @@ int align_up(int x, int a) { return (x + a - 1) / a * a; }
 bool plan_pipe(const cbx_params& p, int wl, int we, cbx_pipe_plan* Q) {
   const cbx_layout& L = p.lay;
   memset(Q, 0, sizeof(*Q));
-  if (p.enc.warp_env < 1 || CBX_TILE != 32 || wl < 1 || we < 1 || (wl + we) * 32 > 512) return false;
+  if (p.enc.warp_env < 1 || CBX_TILE != 32 || wl < 1 || we < 1 || (wl + we + 1) * 32 > 512) return false;
   const bool dense = L.sz_connect > 0;
   const int ROWR = L.N * L.R, ROWC = L.N * L.P * L.C;
   int gs = 1;
@@ -83,6 +83,7 @@ bool plan_pipe(const cbx_params& p, int wl, int we, cbx_pipe_plan* Q) {
   Q->tables = (int)o; o = up(o + p.table_words + ((L.S + 3) & ~3), 32);
   Q->lut = (int)o; o += 512;
   Q->bars = (int)o; o = up(o + 2 * (1 + wl + 3 * Q->nslot), 32);
+  Q->done_ring = (int)o; o += 96;  // overlapped launches: completed parts + tile index of 32 tracked tiles, publisher progress
   Q->zero = (int)o; o = up(o + (dense ? gs * ROWC / 4 : 0), 32);
   Q->def_static = (int)o; o = up(o + (defobs ? CBX_TILE * (12 * L.n + L.nservices) / 4 : 0), 32);
   // logic buffers: state tile | staging | field images [32][words per env] | actions (aliasing the property image when it
@@ -171,6 +172,8 @@ bool plan_wide(const cbx_params& p, int sms, cbx_wide_plan* Q) {
 
 }  // namespace
 
+constexpr int kTicketRing = 1024;
+
 struct cbx_scenario {
   std::vector<uint32_t> blob;
   int n, P, nprops, L, R, nsecrets, ntriples, nservices, max_leak, flags;
@@ -203,6 +206,7 @@ struct cbx_batch {
   cbx_scenario vscn;             // multi-scenario batch: the element-wise maximum of the scenarios' dimensions (no blob)
   int32_t* d_tile_scn;
   std::vector<uint32_t> init_state;
+  int* ticket_ring;  // pipelined kernel: kTicketRing per-launch ticket counters (slot = seq % kTicketRing)
 };
 
 static void host_release(cbx_batch* b) {
@@ -528,11 +532,16 @@ static int create_impl(const cbx_scenario* const* scns, int n_scn, const int64_t
         if (per_sm < 1) per_sm = 1;
         b->pipe_grid = sms * per_sm < b->p.n_tiles ? sms * per_sm : b->p.n_tiles;
         // dynamic tile order pays from ~24 tiles per CTA on (131 072 envs per GPU); CBX_PIPE_DYNAMIC=0/1 overrides
-        { const char* dy = getenv("CBX_PIPE_DYNAMIC"); Q.dynamic = dy ? atoi(dy) != 0 : b->p.n_tiles >= 24 * b->pipe_grid; }
-        b->p.pipe = Q;
         // consecutive launches overlap (programmatic dependent launch + per-tile completion counters); CBX_PIPE_OVERLAP=0
         // restores fully serialised launches
         { const char* ov = getenv("CBX_PIPE_OVERLAP"); b->p.overlap = !(ov && ov[0] == '0'); }
+        // Tile order.  Serialised launches: the dynamic order (global ticket counter) pays from ~24 tiles per CTA on (131 072
+        // envs per GPU) and costs 2.5 % at the 14 tiles per CTA of 65 536 envs.  Overlapped launches: it wins at every size
+        // (+6.5 % at 65 536 envs: a CTA that starts late -- its SM was still draining the previous launch -- takes fewer
+        // tiles), so it is always on.  CBX_PIPE_DYNAMIC=0/1 overrides.
+        { const char* dy = getenv("CBX_PIPE_DYNAMIC");
+          Q.dynamic = dy ? atoi(dy) != 0 : (b->p.overlap || b->p.n_tiles >= 24 * b->pipe_grid); }
+        b->p.pipe = Q;
       } else {
         cudaGetLastError();
       }
@@ -611,6 +620,11 @@ static int create_impl(const cbx_scenario* const* scns, int n_scn, const int64_t
     if (e != cudaSuccess) { int rc2 = fail(CBX_ERR_CUDA, "cudaMalloc(tile completion counters): %s", cudaGetErrorString(e)); cbx_batch_destroy(b); return rc2; }
     b->p.tile_done = (uint32_t*)pd;
     b->p.seq = 0;
+    void* pr = nullptr;
+    e = dalloc(&pr, (size_t)kTicketRing * sizeof(int));
+    if (e != cudaSuccess) { int rc2 = fail(CBX_ERR_CUDA, "cudaMalloc(ticket ring): %s", cudaGetErrorString(e)); cbx_batch_destroy(b); return rc2; }
+    b->ticket_ring = (int*)pr;
+    b->p.tickets = b->ticket_ring;
   }
   cbx_views& v = b->p.v;
   v.n_envs = n_envs; v.N = L.N; v.L = L.L; v.R = L.R; v.P = L.P; v.C = L.C; v.LEAK = L.LEAK; v.n_props = L.nprops;
@@ -667,6 +681,7 @@ static int create_impl(const cbx_scenario* const* scns, int n_scn, const int64_t
     b->p.reset_mask = nullptr;
     const int op0 = CBX_OP_RESET | CBX_OP_ATTACKER | CBX_OP_DEFENDER;
     b->p.seq += 1;
+    b->p.tickets = b->ticket_ring + (b->p.seq % kTicketRing);
     cudaError_t e = b->p.pipe.enabled ? cbx_launch_pipe(&b->p, op0, b->pipe_grid, 0)
                     : b->p.wide.enabled ? cbx_launch_wide(&b->p, op0, b->wide_grid, 0)
                                         : cbx_launch_step(&b->p, op0, b->grid, b->smem_bytes, b->use_tma, 0);
@@ -706,6 +721,14 @@ static int timed_launch(cbx_batch* b, int op, cudaStream_t st) {
     b->region_open = 1; b->region_count = 0; b->region_stream = st;
   }
   b->p.seq += 1;
+  if (b->p.pipe.enabled) {
+    // this launch's ticket counter: the next slot of the ring.  Entering a half, re-zero the OTHER half: a stream operation,
+    // so every launch that used those slots has completed and none of the next 512 starts before they are zero again
+    const int slot = (int)(b->p.seq % kTicketRing);
+    if (slot % (kTicketRing / 2) == 0)
+      CUDA_TRY(cudaMemsetAsync(b->ticket_ring + (slot + kTicketRing / 2) % kTicketRing, 0, (kTicketRing / 2) * sizeof(int), st));
+    b->p.tickets = b->ticket_ring + slot;
+  }
   if (b->p.pipe.enabled) CUDA_TRY(cbx_launch_pipe(&b->p, op, b->pipe_grid, st));
   else if (b->p.wide.enabled) CUDA_TRY(cbx_launch_wide(&b->p, op, b->wide_grid, st));
   else CUDA_TRY(cbx_launch_step(&b->p, op, b->grid, b->smem_bytes, b->use_tma, st));
@@ -1078,10 +1101,14 @@ int cbx_batch_tile_counter(cbx_batch* b, int32_t* out2) {
   if (!b || !out2) return fail(CBX_ERR_INVALID, "null argument");
   CUDA_TRY(cudaSetDevice(b->device));
   CUDA_TRY(cudaDeviceSynchronize());
-  int32_t c[4];
-  CUDA_TRY(cudaMemcpy(c, b->p.tile_counter, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost));
-  out2[0] = c[0] | c[2];  // both pairs (even / odd launches when launches overlap)
-  out2[1] = c[1] | c[3];
+  if (b->p.pipe.enabled) {  // the last launch's own counter: every logic warp drew tickets until one was past the end
+    int32_t drawn = 0;
+    CUDA_TRY(cudaMemcpy(&drawn, b->ticket_ring + (b->p.seq % kTicketRing), sizeof(int32_t), cudaMemcpyDeviceToHost));
+    out2[0] = drawn - (b->p.pipe.dynamic ? b->p.n_tiles : 0);  // exactly n_tiles draws per launch (0 with the static order)
+    out2[1] = 0;
+  } else {
+    CUDA_TRY(cudaMemcpy(out2, b->p.tile_counter, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  }
   return CBX_OK;
 }
 
@@ -1091,7 +1118,7 @@ int cbx_batch_kernel_info(const cbx_batch* b, int32_t* out8) {
   const bool wide = b->p.wide.enabled;
   out8[0] = Q.enabled ? 1 : wide ? 2 : 0;
   out8[1] = Q.enabled ? b->pipe_grid : wide ? b->wide_grid : b->grid;
-  out8[2] = Q.enabled ? (Q.wl + Q.we) * 32 : wide ? b->p.wide.nwarps * 32 : CBX_THREADS;
+  out8[2] = Q.enabled ? (Q.wl + Q.we + (b->p.overlap ? 1 : 0)) * 32 : wide ? b->p.wide.nwarps * 32 : CBX_THREADS;
   out8[3] = Q.enabled ? Q.total_bytes : wide ? b->p.wide.total_bytes : b->smem_bytes;
   out8[4] = Q.enabled ? Q.wl : 0;
   out8[5] = Q.enabled ? Q.we : 0;

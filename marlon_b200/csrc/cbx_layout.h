@@ -106,7 +106,7 @@ struct cbx_pipe_plan {
                     // 0 (CBX_PIPE_LOGIC_TMA=0): with plain 16-byte loads / stores (measured slower: HBM read latency
                     // under the write stream is ~12 us, the TMA queue hides more of it)
   // shared-memory carve-up in 32-bit words
-  int tables, lut, bars, zero, def_static;
+  int tables, lut, bars, done_ring, zero, def_static;
   int lbufs, lbuf_words;    // per logic warp: state tile | staging | actions (aliased by the props image) | field images
   int dynamic;              // tiles after a logic warp's first come from a global ticket counter (cbx_params.tile_counter)
   int l_stage, l_acts;      // inside a logic buffer (the state tile is at 0)
@@ -162,8 +162,11 @@ struct cbx_params {
   const uint8_t* reset_mask;  // reset kernel only
   float notify_last_reward;   // CBX_OP_NOTIFY
   cbx_views v;
-  int* tile_counter;      // dynamic tile order: [0] tickets handed out, [1] CTAs finished (both 0 between launches); a second
-                          // pair [2], [3] serves the odd launches when consecutive launches overlap
+  int* tile_counter;      // warp-per-tile kernel, dynamic tile order: [0] tickets handed out, [1] CTAs finished (both 0 between
+                          // launches: the last CTA of a launch resets them; its launches are serialised)
+  int* tickets;           // pipelined kernel, dynamic tile order: THIS launch's ticket counter, zero at launch (a slot of
+                          // cbx_batch's ring; never reset in-kernel: with overlapped launches and a grid smaller than the
+                          // machine any number of launches can be in flight at once)
   // Overlapped launches of the pipelined kernel (programmatic dependent launch): launch k+1's CTAs start on every SM the
   // moment launch k's CTA has left it and take a tile only after ALL of launch k's writes to that tile have completed --
   // tile_done[t] counts completions of tile t, (1 + encoder warps) per launch (the logic warp and every encoder warp add one

@@ -12,7 +12,8 @@ cudaError_t cbx_pipe_attrs(int enc, int smem_bytes) {
   }
 }
 cudaError_t cbx_launch_pipe(const cbx_params* p, int op, int grid, cudaStream_t stream) {
-  const int threads = (p->pipe.wl + p->pipe.we) * 32;
+  // overlapped launches: one more warp, the publisher of the per-tile completion counters
+  const int threads = (p->pipe.wl + p->pipe.we + (p->overlap ? 1 : 0)) * 32;
   if (p->overlap) {
     // programmatic dependent launch: this grid's CTAs may start while the previous launch of the stream is still draining;
     // the kernel orders its accesses tile by tile through cbx_params.tile_done

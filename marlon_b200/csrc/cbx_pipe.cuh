@@ -29,12 +29,18 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-// one more completed part of a tile: everything this warp wrote to the tile (bulk copies that have completed, plain stores of
-// all its lanes before the preceding __syncwarp) is visible to whoever acquires the counter
-__device__ __forceinline__ void tile_part_done(uint32_t* counter) {
-  asm volatile("fence.proxy.async;" ::: "memory");
-  __threadfence();
-  asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+// Completions are reported in two hops so that no WORKING warp ever executes a gpu-scope fence (measured: with every warp
+// fencing and adding to the HBM counter itself, membar stalls were 30 % of all stall samples of the kernel,
+// profiles/r02_ncu_lines_pipe_kernel_overlap_v1.txt): a warp whose copies of a tile have completed adds one to the tile's
+// entry of a small ring in SHARED memory (cta-scope release); a dedicated publisher warp polls the ring and, once all parts
+// of a tile are in, does the cross-proxy + gpu-scope fences and the release store of the launch's sequence number to HBM.
+constexpr int kDoneRing = 32;              // tiles of one CTA whose completion is being tracked (ordinals j, j + 1, ...)
+constexpr uint32_t kStopTile = 0xFFFFFFFFu;
+// one more completed part of the CTA's tile with ordinal j: everything this warp wrote to the tile (bulk copies that have
+// completed, plain stores of all its lanes before the preceding __syncwarp) happens-before the publisher's release store
+__device__ __forceinline__ void tile_part_done(uint32_t* s_parts, const int j) {
+  __threadfence_block();
+  atomicAdd(s_parts + (j & (kDoneRing - 1)), 1u);
 }
 // cp.async.bulk.wait_group takes an immediate: all but the n most recent bulk groups of this thread have completed
 __device__ __forceinline__ void tma_store_wait_all_but(const int n) {
@@ -268,19 +274,33 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
   uint64_t* bar_ready = bar_load + Q.wl;     // [nslot] logic -> encoders
   uint64_t* bar_empty = bar_ready + Q.nslot; // [nslot] encoders -> logic
   uint64_t* bar_rdef = bar_empty + Q.nslot;  // [nslot] logic -> the encoder of the tile's defender observation
+  uint32_t* s_parts = smem + Q.done_ring;          // [kDoneRing] completed parts per tracked tile
+  uint32_t* s_ptile = s_parts + kDoneRing;         // [kDoneRing] its tile index (kStopTile: the logic warp has no more tiles)
+  volatile uint32_t* s_pub = s_ptile + kDoneRing;  // [1] tiles the publisher warp has dealt with
   uint8_t* s_zero = reinterpret_cast<uint8_t*>(smem + Q.zero);
   uint8_t* s_defst = reinterpret_cast<uint8_t*>(smem + Q.def_static);
   const uint32_t* s_init = s_tb + p.table_words;
   const uint32_t table_bytes = (uint32_t)(p.table_words + ((L.S + 3) & ~3)) * 4u;
-  const int nthreads = (Q.wl + Q.we) * 32;
+  const int nthreads = (int)blockDim.x;  // logic + encoder warps (+ the publisher warp when launches overlap)
   constexpr uint32_t kRowBytes = CBX_TILE * 4u;
   // Overlapped launches: the next launch of the stream may start its CTAs on every SM this launch's CTA has left (its CTAs
   // then wait tile by tile on tile_done, never on this grid as a whole)
   const bool overlap = p.overlap != 0;
   if (overlap) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  const uint32_t seq_need = (uint32_t)(1 + Q.we) * (p.seq - 1u);  // completions of a tile after every earlier launch
-  int* const tickets = p.tile_counter + (overlap ? 2 * (int)(p.seq & 1u) : 0);
+  const uint32_t seq_need = p.seq - 1u;  // tile_done[t] holds the sequence number of the last launch that completed tile t
+  // dynamic tile order: this launch's OWN ticket counter (a fresh slot of a ring the host re-zeroes in halves: any number of
+  // launches may be in flight at once when the grid is smaller than the machine, so no counter is shared or reset in-kernel)
+  int* const tickets = p.tickets;
 
+  // the scenario tables are on their way (one bulk copy, ~2 us from L2 / HBM) while the CTA fills its constant buffers
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    for (int w = 0; w < Q.wl; ++w) mbar_init(&bar_load[w], 1);
+    for (int s = 0; s < Q.nslot; ++s) { mbar_init(&bar_ready[s], 1); mbar_init(&bar_empty[s], Q.we); mbar_init(&bar_rdef[s], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(&bars[0], table_bytes);
+    tma_load_1d(s_tb, p.tables, table_bytes, &bars[0]);
+  }
   for (int k = tid; k < 256; k += nthreads) {
     uint32_t lo = ((k & 0xF) * 0x00204081u) & 0x01010101u, hi = (((k >> 4) & 0xF) * 0x00204081u) & 0x01010101u;
     s_lut[k] = make_uint2(lo, hi);
@@ -288,17 +308,8 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
   // zero row + encoder buffers (the zero halves of the row-pair templates stay zero for the whole kernel)
   for (int k = Q.zero + tid; k < Q.def_static; k += nthreads) smem[k] = 0;
   for (int k = Q.wbufs + tid; k < Q.wbufs + Q.we * Q.wbuf_words; k += nthreads) smem[k] = 0;
-  if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    for (int w = 0; w < Q.wl; ++w) mbar_init(&bar_load[w], 1);
-    for (int s = 0; s < Q.nslot; ++s) { mbar_init(&bar_ready[s], 1); mbar_init(&bar_empty[s], Q.we); mbar_init(&bar_rdef[s], 1); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
+  for (int k = tid; k < 2 * kDoneRing + 1; k += nthreads) s_parts[k] = 0;
   __syncthreads();
-  if (tid == 0) {
-    mbar_expect_tx(&bars[0], table_bytes);
-    tma_load_1d(s_tb, p.tables, table_bytes, &bars[0]);
-  }
   mbar_wait(&bars[0], 0);
   if (def_encode) {  // static parts of the defender observation for a tile of 32 envs: [32][6n] in, [32][6n] out, [32][nsvc]
     const int n6 = 6 * L.n;
@@ -347,7 +358,7 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
     // publishes a stop marker in its next slot.  Measured: +2 % at 28 tiles per CTA, +9..11 % from 55 on,
     // -2.5 % at 14 (most of a short launch is assigned before any CTA has shown its speed), hence the threshold in the plan.
     int next_tile = (int)blockIdx.x + warp * (int)gridDim.x;
-    int done_tile = -1;  // overlapped launches: the tile whose stores were issued last, not yet reported complete
+    int done_j = -1;  // overlapped launches: ordinal of the tile whose stores were issued last, not yet reported complete
     for (int j = warp;; j += Q.wl, ++u) {
       const int slot = warp + Q.wl * (u % spw), use = u / spw;
       uint32_t* desc = smem + Q.slots + slot * Q.slot_words;
@@ -357,6 +368,12 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
         if (u > 0 && lane == 0) next_tile = (int)gridDim.x * Q.wl + atomicAdd(tickets, 1);
         tile = __shfl_sync(0xFFFFFFFFu, next_tile, 0);
         if (tile >= p.n_tiles) {
+          if (overlap && lane == 0) {  // tell the publisher warp that this logic warp is done
+            while (j - (int)*s_pub >= kDoneRing) __nanosleep(32);
+            s_ptile[j & (kDoneRing - 1)] = kStopTile;
+            __threadfence_block();
+            atomicAdd(s_parts + (j & (kDoneRing - 1)), (uint32_t)(1 + Q.we));
+          }
           if (use > 0) mbar_wait(&bar_empty[slot], (uint32_t)(use - 1) & 1u);
           if (lane == 0) hdr[CBX_SH_TILE] = 0xFFFFFFFFu;
           __syncwarp();
@@ -380,6 +397,8 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
         if (lane == 0) {
           while ((int32_t)(ld_acquire_gpu(p.tile_done + tile) - seq_need) < 0) __nanosleep(64);
           asm volatile("fence.proxy.async;" ::: "memory");
+          while (j - (int)*s_pub >= kDoneRing) __nanosleep(32);  // the ring entry of ordinal j - kDoneRing has been retired
+          s_ptile[j & (kDoneRing - 1)] = (uint32_t)tile;
         }
         __syncwarp();
       }
@@ -538,8 +557,8 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
           if (overlap) {  // the tile before this one: its bulk copies (one group per lane) have completed -> report it
             if (lane < 7) tma_store_wait_all_but(1);
             __syncwarp();
-            if (lane == 0 && done_tile >= 0) tile_part_done(p.tile_done + done_tile);
-            done_tile = tile;
+            if (lane == 0 && done_j >= 0) tile_part_done(s_parts, done_j);
+            done_j = j;
           }
         } else {
           // plain 16-byte copies: a tile's rows are contiguous in every tensor (fully coalesced 512-byte warp stores)
@@ -560,8 +579,8 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
           }
           if (overlap) {
             __syncwarp();
-            if (lane == 0 && done_tile >= 0) tile_part_done(p.tile_done + done_tile);
-            done_tile = tile;
+            if (lane == 0 && done_j >= 0) tile_part_done(s_parts, done_j);
+            done_j = j;
           }
         }
         if (!full) {
@@ -579,7 +598,7 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
     tma_store_wait_all();  // every lane that issued bulk copies waits for its own
     if (overlap) {
       __syncwarp();
-      if (lane == 0 && done_tile >= 0) tile_part_done(p.tile_done + done_tile);
+      if (lane == 0 && done_j >= 0) tile_part_done(s_parts, done_j);
     }
     // episode statistics: warp shuffle reduce, one atomic per slot per warp
 #pragma unroll
@@ -595,7 +614,7 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
     long long pacc[3] = {0, 0, 0};
     uint32_t stopped = 0;  // dynamic order: logic warps that have published their stop marker
     const uint32_t all_stopped = (1u << Q.wl) - 1u;
-    int done_tile = -1;  // overlapped launches: the tile this warp issued last, not yet reported complete
+    int done_j = -1;  // overlapped launches: ordinal of the tile this warp issued last, not yet reported complete
     for (int j = 0;; ++j) {
       const int lw = j % Q.wl, u = j / Q.wl;
       if (Q.dynamic) {
@@ -638,34 +657,53 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
       if (overlap) {  // this warp's copies of the tile BEFORE this one have completed (groups retire in order): report it
         tma_store_wait_all_but(groups);
         __syncwarp();
-        if (lane == 0 && done_tile >= 0) tile_part_done(p.tile_done + done_tile);
-        done_tile = tile;
+        if (lane == 0 && done_j >= 0) tile_part_done(s_parts, done_j);
+        done_j = j;
       }
       prof_t = p.prof ? clock64() : 0;
     }
     tma_store_wait_all();
     if (overlap) {
       __syncwarp();
-      if (lane == 0 && done_tile >= 0) tile_part_done(p.tile_done + done_tile);
+      if (lane == 0 && done_j >= 0) tile_part_done(s_parts, done_j);
     }
     if (p.prof && lane == 0)
       for (int k = 0; k < 3; ++k) atomicAdd(p.prof + 13 + k, (unsigned long long)pacc[k]);
+  } else if (overlap && lane == 0) {
+    // =============================== publisher warp (overlapped launches) ===============================
+    // tiles of this CTA in ordinal order: once all 1 + we parts of a tile have been reported, everything the CTA wrote to
+    // it is complete -> release the launch's sequence number into the tile's counter in HBM
+    const uint32_t parts = (uint32_t)(1 + Q.we);
+    uint32_t stopped = 0;
+    const uint32_t all_stopped = (1u << Q.wl) - 1u;
+    for (int j = 0;; ++j) {
+      const int lw = j % Q.wl;
+      if (Q.dynamic) {
+        if (stopped == all_stopped) break;
+        if ((stopped >> lw) & 1u) continue;
+      } else if (j >= my_tiles) {
+        break;
+      }
+      volatile uint32_t* cnt = s_parts + (j & (kDoneRing - 1));
+      while (*cnt < parts) __nanosleep(128);
+      __threadfence_block();
+      const uint32_t tile = s_ptile[j & (kDoneRing - 1)];
+      *cnt = 0;
+      __threadfence_block();
+      *s_pub = (uint32_t)(j + 1);
+      if (tile == kStopTile) {
+        stopped |= 1u << lw;
+        continue;
+      }
+      asm volatile("fence.proxy.async;" ::: "memory");
+      __threadfence();
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.tile_done + tile), "r"(p.seq) : "memory");
+    }
   }
   if (p.prof && lane == 0)
     for (int k = 0; k < 5; ++k)
       if (pp[k]) atomicAdd(p.prof + 8 + k, (unsigned long long)pp[k]);
 #undef CBX_PPROF
-  if (Q.dynamic) {  // the last CTA to finish leaves the ticket counter at zero for the next launch
-    __syncthreads();
-    if (tid == 0) {
-      __threadfence();
-      if (atomicAdd(tickets + 1, 1) == (int)gridDim.x - 1) {
-        tickets[0] = 0;
-        tickets[1] = 0;
-        __threadfence();
-      }
-    }
-  }
   // stream order for whatever follows the NEXT launch: a grid that ends implies the grid before it has ended (it has, long
   // ago -- its tiles were consumed above -- so this never waits in practice)
   if (overlap) asm volatile("griddepcontrol.wait;" ::: "memory");

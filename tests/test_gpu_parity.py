@@ -119,31 +119,95 @@ def _toyctf_pair_cfg(**kw):
 @pytest.mark.parametrize("n", [257, 513, 4099])
 @pytest.mark.parametrize("mask_mode", [_abi.MASK_DENSE, _abi.MASK_FACTORED])
 def test_pipe_kernel_dynamic_tile_order_vs_oracle(monkeypatch, n, mask_mode):
-    """The pipelined kernel's DYNAMIC tile order (global ticket counter, stop markers, counter reset by the last CTA) is what
-    every batch of >= 24 tiles per CTA runs (>= 113 664 envs per GPU: the 1M-env and multi-GPU figures).  Forced on here at
-    small ragged sizes: every array and the state against the oracle, int16 bulk actions, a masked reset mid-run, short
-    episodes so that terminal observations and auto-resets occur, and the ticket counter back at {0, 0} after every launch."""
+    """The pipelined kernel's DYNAMIC tile order (global ticket counter, stop markers, counter reset by the last CTA) with
+    SERIALISED launches -- round 1's configuration above 113 664 envs per GPU.  Forced on here at small ragged sizes: every
+    array and the state against the oracle, int16 bulk actions, a masked reset mid-run, short episodes so that terminal
+    observations and auto-resets occur, and the ticket counter back at {0, 0} after every launch."""
     monkeypatch.setenv("CBX_PIPE_DYNAMIC", "1")
+    monkeypatch.setenv("CBX_PIPE_OVERLAP", "0")
     comp = scenario.compile_scenario(scenarios.toyctf_environment())
     cfg = _toyctf_pair_cfg(mask_mode=mask_mode, emit_terminal_obs=True, attacker_max_timesteps=23, defender_max_timesteps=17)
     _run_against_oracle(comp, cfg, n, 90, seed=41 + n, check_every=5, expect_order="dynamic", i16=(n != 513), reset_at=31)
 
 
+@pytest.mark.parametrize("mode", ["overlap-dynamic", "overlap-static", "serial-static"])
+def test_pipe_kernel_launch_modes_vs_oracle(monkeypatch, mode):
+    """Every combination of launch mode (overlapped: programmatic dependent launch + per-tile completion counters + publisher
+    warp / serialised) and tile order the library can be put in, against the oracle (overlap-dynamic is the default)."""
+    ov, order = mode.split("-")
+    monkeypatch.setenv("CBX_PIPE_OVERLAP", "1" if ov == "overlap" else "0")
+    monkeypatch.setenv("CBX_PIPE_DYNAMIC", "1" if order == "dynamic" else "0")
+    comp = scenario.compile_scenario(scenarios.toyctf_environment())
+    cfg = _toyctf_pair_cfg(emit_terminal_obs=True, attacker_max_timesteps=23, defender_max_timesteps=17)
+    _run_against_oracle(comp, cfg, 4099, 60, seed=47, check_every=5, expect_order=order, i16=True, reset_at=20)
+
+
 def test_pipe_kernel_dynamic_tile_order_default_threshold_vs_oracle():
-    """131 072 envs on one GPU: 4 096 tiles >= 24 per CTA, so the library picks the dynamic order BY DEFAULT (no environment
-    override) -- the configuration of the 1M-env / multi-GPU runs.  Every array of every env against the oracle."""
+    """131 072 envs on one GPU (the per-GPU share of the 1M-env / 8-GPU runs), default settings: overlapped launches, dynamic
+    tile order.  Every array of every env against the oracle."""
     comp = scenario.compile_scenario(scenarios.toyctf_environment())
     _run_against_oracle(comp, _toyctf_pair_cfg(), 131072, 14, seed=43, check_every=13, expect_order="dynamic")
 
 
-def test_static_tile_order_is_the_default_at_bench_size():
+def test_default_launch_mode_at_bench_size(monkeypatch):
     from marlon_b200.batch import Batch
 
     comp = scenario.compile_scenario(scenarios.toyctf_environment())
     b = Batch(comp, _toyctf_pair_cfg(), 65536)
     info = b.kernel_info()
-    assert info["name"] == "cbx_pipe_kernel" and info["tile_order"] == "static", info
+    assert info["name"] == "cbx_pipe_kernel" and info["overlapped_launches"] and info["tile_order"] == "dynamic", info
     b.close()
+    monkeypatch.setenv("CBX_PIPE_OVERLAP", "0")  # serialised launches: the static order below 24 tiles per CTA
+    b = Batch(comp, _toyctf_pair_cfg(), 65536)
+    info = b.kernel_info()
+    assert not info["overlapped_launches"] and info["tile_order"] == "static", info
+    b.close()
+
+
+@pytest.mark.parametrize("n,steps", [(4099, 700), (65536, 150), (96, 300)])
+def test_overlapped_launches_back_to_back_match_serialised(monkeypatch, n, steps):
+    """The overlap protocol under real overlap: `steps` steps enqueued back to back (no host synchronisation in between, actions
+    from a device-resident tape) on a batch with overlapped launches must end exactly where a batch with serialised launches
+    ends -- state, every observation array, statistics -- and both must agree with the oracle.  A launch that took a tile
+    before the previous launch's writes to it had landed would show up here.  4 099 envs = 129 CTAs on 148 SMs and 96 envs =
+    3 CTAs: grids smaller than the machine, where MANY launches are in flight at once (each launch draws its tile tickets from
+    its own counter; 700 launches also wrap the ring of those counters); 65 536 envs = the bench size."""
+    import torch
+
+    from marlon_b200.batch import Batch
+    from oracle import OracleBatch
+
+    comp = scenario.compile_scenario(scenarios.toyctf_environment())
+    cfg = _toyctf_pair_cfg(attacker_max_timesteps=29, defender_max_timesteps=31)
+    monkeypatch.setenv("CBX_PIPE_OVERLAP", "0")
+    serial = Batch(comp, cfg, n)
+    assert not serial.kernel_info()["overlapped_launches"]
+    serial.reset()
+    tape = []
+    for s in range(steps):  # record: valid actions for the evolving state
+        att, dfn = serial.sample_actions(seed=51)
+        tape.append((att.clone(), dfn.clone()))
+        serial.step(att, dfn)
+    monkeypatch.setenv("CBX_PIPE_OVERLAP", "1")
+    ov = Batch(comp, cfg, n)
+    assert ov.kernel_info()["overlapped_launches"]
+    ov.reset()
+    torch.cuda.synchronize()
+    for att, dfn in tape:  # replay back to back
+        ov.step(att, dfn)
+    torch.cuda.synchronize()
+    assert ov.tile_counter() == (0, 0)
+    assert np.array_equal(ov.export_state(), serial.export_state())
+    for k in serial.tensors:
+        assert torch.equal(ov.tensors[k], serial.tensors[k]), k
+    assert np.array_equal(ov.stats(), serial.stats())
+    if n <= 8192:
+        o = OracleBatch(comp, cfg, n)
+        o.reset()
+        for att, dfn in tape:
+            o.step(att.cpu().numpy(), dfn.cpu().numpy())
+        _compare_all(ov, o, steps)
+    serial.close(); ov.close()
 
 
 def test_chain10_attacker_only_4096_envs_vs_oracle():
