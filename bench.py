@@ -406,6 +406,7 @@ def measure_device(args, workload, n_req, K, W, world, rank, local, dev, clocks=
     ev0.record()
     for s in range(W, W + K):
         b.step(tape_a[s], tape_d[s])
+    b.enable_timing(False)  # closes the kernel-time bracket here (an event on the stream, no synchronisation)
     evc.record()
     # the only collective of the path: one SUM all-reduce of the 16-slot episode-statistics vector per rollout
     stats = b.stats_tensor.clone()
@@ -424,7 +425,6 @@ def measure_device(args, workload, n_req, K, W, world, rank, local, dev, clocks=
     launches = b.launch_count - launches0
     kernel_ms, kernel_n = b.step_kernel_ms()
     kinfo = b.kernel_info()
-    b.enable_timing(False)
     b.close()
     out = {"comp": comp, "cfg": cfg, "counts": counts, "n": n, "tape_a": tape_a, "tape_d": tape_d, "aw": aw, "has_def": has_def,
            "factored": factored, "multi": multi, "total_ms": total_ms, "collective_ms": coll_ms, "launches": launches,

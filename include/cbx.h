@@ -419,7 +419,8 @@ int64_t cbx_batch_launch_count(const cbx_batch* b);
 /* Average duration (ms) of the step kernel over the launches recorded since the last call, measured with CUDA events
  * on the launch stream when timing is enabled.  When consecutive launches overlap (cbx_batch_kernel_info bit 2) an event
  * between two launches would serialise them: the events then bracket the whole run of step launches since timing was
- * enabled (or since the last call) and the mean is that span divided by the launches in it. */
+ * enabled (or since the last call) and the mean is that span divided by the launches in it; the bracket closes when timing
+ * is switched off (an event on the launch stream, nothing synchronised) or, failing that, at cbx_batch_step_kernel_ms. */
 int cbx_batch_enable_timing(cbx_batch* b, int enabled);
 int cbx_batch_step_kernel_ms(cbx_batch* b, double* mean_ms, int64_t* launches);
 

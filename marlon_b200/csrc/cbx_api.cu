@@ -715,7 +715,7 @@ static int timed_launch(cbx_batch* b, int op, cudaStream_t st) {
     b->ev_used += 2;
     CUDA_TRY(cudaEventRecord(e0, st));
   }
-  if (region && !b->region_open) {
+  if (region && b->region_open != 1) {
     if (b->ev.size() < 2) { for (int k = 0; k < 2; ++k) { cudaEvent_t e; CUDA_TRY(cudaEventCreate(&e)); b->ev.push_back(e); } }
     CUDA_TRY(cudaEventRecord(b->ev[0], st));
     b->region_open = 1; b->region_count = 0; b->region_stream = st;
@@ -1129,6 +1129,11 @@ int cbx_batch_kernel_info(const cbx_batch* b, int32_t* out8) {
 
 int cbx_batch_enable_timing(cbx_batch* b, int enabled) {
   if (!b) return fail(CBX_ERR_INVALID, "null batch");
+  if (!enabled && b->region_open == 1) {  // overlapped launches: the bracket ends HERE (an event on the launch stream, no sync)
+    CUDA_TRY(cudaSetDevice(b->device));
+    CUDA_TRY(cudaEventRecord(b->ev[1], b->region_stream));
+    b->region_open = 2;
+  }
   b->timing = enabled;
   return CBX_OK;
 }
@@ -1137,7 +1142,7 @@ int cbx_batch_step_kernel_ms(cbx_batch* b, double* mean_ms, int64_t* launches) {
   if (!b || !mean_ms || !launches) return fail(CBX_ERR_INVALID, "null argument");
   CUDA_TRY(cudaSetDevice(b->device));
   if (b->region_open) {  // overlapped launches: one bracket around the whole run, averaged over its launches
-    CUDA_TRY(cudaEventRecord(b->ev[1], b->region_stream));
+    if (b->region_open == 1) CUDA_TRY(cudaEventRecord(b->ev[1], b->region_stream));
     CUDA_TRY(cudaEventSynchronize(b->ev[1]));
     float ms = 0;
     CUDA_TRY(cudaEventElapsedTime(&ms, b->ev[0], b->ev[1]));
