@@ -400,8 +400,10 @@ int cbx_batch_step_i16(cbx_batch* b, const int16_t* attacker_actions, const int1
 int cbx_batch_step_host_i16(cbx_batch* b, const int16_t* host_attacker_actions, const int16_t* host_defender_actions,
                             void* host_out, size_t host_out_bytes, void* cuda_stream);
 
-/* Fill device action buffers with uniformly sampled VALID actions for the current state (benchmark load;
- * cyberbattle_env.py:1041-1047 semantics: resample until the mask admits the action), Philox keyed by (seed, env, step). */
+/* Fill device action buffers with VALID attacker actions drawn the way CyberBattleEnv.sample_valid_action draws them
+ * (cyberbattle_env.py:959-1047: whole proposals -- kind, then coordinates uniform over their ranges, kind 1 = local and kind 0 =
+ * remote as in the reference -- are redrawn until the action mask admits one) and uniform defender actions; Philox4x32-10 keyed
+ * by (seed; env, call number).  The oracle's orc_sample_actions produces the same actions from the same state. */
 int cbx_batch_sample_actions(cbx_batch* b, int32_t* attacker_actions, int32_t* defender_actions, uint64_t seed,
                              void* cuda_stream);
 

@@ -249,7 +249,14 @@ __global__ void __launch_bounds__(CBX_THREADS, CBX_MIN_CTAS) cbx_step_kernel(con
 
 namespace cbx {
 
-// ---- uniformly sampled valid actions (benchmark load; ENV:959-1047 semantics) -------------------------------------------
+// ---- valid actions with CyberBattleEnv.sample_valid_action's distribution (ENV:959-1047) ------------------------------------
+// The reference draws whole proposals until the action mask admits one (ENV:1041-1047): kind uniform over [0, 1, 2] (no 2 while
+// the credential cache is empty, ENV:972-976); quirk B.9: kind 1 builds a LOCAL action, kind 0 a REMOTE one; sources uniform
+// over the nodes with privilege >= LocalUser (ENV:832-838), targets over the discovered nodes, vulnerability / port ids over the
+// whole id range, credentials over the cache.  The mask wants agent_installed on the source and, for a local action, the
+// vulnerability on that node (ENV:643-677): rejected proposals are redrawn kind and all, so local actions come out rarer than
+// 1 / kinds.  Draws: Philox4x32-10 keyed (seed; env, step, 0x5A170000 + attempt); the oracle's orc_sample_actions does the
+// same arithmetic (tests compare the two bit for bit and the oracle's frequencies with the live reference's).
 // One thread per env reads its state words straight from HBM (column access is coalesced across the warp).
 __global__ void cbx_sample_kernel(const __grid_constant__ cbx_params p, int32_t* att, int32_t* def, uint64_t seed, uint32_t step) {
   const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -257,40 +264,46 @@ __global__ void cbx_sample_kernel(const __grid_constant__ cbx_params p, int32_t*
   const cbx_layout& L = p.lay;
   const uint32_t* tables = p.tables + (size_t)(p.tile_scn ? p.tile_scn[env / CBX_TILE] : 0) * p.table_stride;
   auto W = [&](int off) { return p.state[((env / CBX_TILE) * L.S + off) * CBX_TILE + (env % CBX_TILE)]; };
-  uint32_t r[4];
-  philox4x32_10((uint32_t)env, (uint32_t)(env >> 32), step, 0x5A17u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
-  uint32_t r2[4];
-  philox4x32_10((uint32_t)env, (uint32_t)(env >> 32), step, 0x5A18u, (uint32_t)seed, (uint32_t)(seed >> 32), r2);
   const uint32_t hdr = W(L.o_hdr);
   const int nd = hdr & 0xFF, nc = (hdr >> 8) & 0xFFFF;
-  // owned discovery indices
+  auto node_at = [&](int s) { return (int)((W(L.o_disc_order + (s >> 2)) >> ((s & 3) * 8)) & 0xFFu); };
+  // discovery indices of the owned nodes (privilege >= LocalUser), in discovery order
   int owned[256];
   int n_owned = 0;
   for (int s = 0; s < nd; ++s) {
-    uint32_t node = (W(L.o_disc_order + (s >> 2)) >> ((s & 3) * 8)) & 0xFFu;
-    if ((W(L.o_installed + (node >> 5)) >> (node & 31)) & 1u) owned[n_owned++] = s;
+    const int node = node_at(s);
+    if ((W(L.o_priv + (node >> 4)) >> ((node & 15) * 2)) & 3u) owned[n_owned++] = s;
   }
-  int kind = (int)(__umulhi(r[0], nc > 0 ? 3u : 2u));  // 0 local, 1 remote, 2 connect (connect needs a cached credential)
-  int src = n_owned ? owned[__umulhi(r[1], (uint32_t)n_owned)] : 0;
-  int a[4] = {src, 0, 0, 0};
-  if (kind == CBX_KIND_LOCAL) {
-    // resample until the mask admits the action: pick uniformly among the vulnerabilities present on the node
-    uint32_t node = (W(L.o_disc_order + (src >> 2)) >> ((src & 3) * 8)) & 0xFFu;
-    int present[64];
-    int np = 0;
-    for (int v = 0; v < L.L && v < 64; ++v)
-      if (tables[tables[CBX_H_OFF_VULN] + (node * (L.L + L.R) + v) * CBX_VULN_WORDS] & 1u) present[np++] = v;
-    if (np) a[1] = present[__umulhi(r[2], (uint32_t)np)];
-    else { kind = CBX_KIND_REMOTE; }
+  int kind = CBX_KIND_REMOTE;
+  int a[4] = {0, 0, 0, 0};
+  for (uint32_t it = 0; it < 64u; ++it) {
+    uint32_t r[4];
+    philox4x32_10((uint32_t)env, (uint32_t)(env >> 32), step, 0x5A170000u + it, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    const uint32_t k = __umulhi(r[0], nc > 0 ? 3u : 2u);
+    const int src = n_owned ? owned[__umulhi(r[1], (uint32_t)n_owned)] : 0;
+    const int node = nd ? node_at(src) : 0;
+    bool valid = n_owned && ((W(L.o_installed + (node >> 5)) >> (node & 31)) & 1u);
+    a[0] = src; a[1] = a[2] = a[3] = 0;
+    if (k == 1u) {
+      kind = CBX_KIND_LOCAL;
+      a[1] = (int)__umulhi(r[2], (uint32_t)L.L);
+      valid = valid && (tables[tables[CBX_H_OFF_VULN] + (node * (L.L + L.R) + a[1]) * CBX_VULN_WORDS] & 1u);
+    } else if (k == 0u) {
+      kind = CBX_KIND_REMOTE;
+      a[1] = (int)__umulhi(r[2], (uint32_t)max(nd, 1));
+      a[2] = (int)__umulhi(r[3], (uint32_t)L.R);
+    } else {
+      uint32_t q[4];
+      philox4x32_10((uint32_t)env, (uint32_t)(env >> 32), step, 0x5A180000u + it, (uint32_t)seed, (uint32_t)(seed >> 32), q);
+      kind = CBX_KIND_CONNECT;
+      a[1] = (int)__umulhi(r[2], (uint32_t)max(nd, 1));
+      a[2] = (int)__umulhi(r[3], (uint32_t)L.P);
+      a[3] = (int)__umulhi(q[0], (uint32_t)nc);
+    }
+    if (valid) break;
   }
-  if (kind == CBX_KIND_REMOTE) {
-    a[1] = (int)__umulhi(r[2], (uint32_t)max(nd, 1));
-    a[2] = (int)__umulhi(r[3], (uint32_t)L.R);
-  } else if (kind == CBX_KIND_CONNECT) {
-    a[1] = (int)__umulhi(r[2], (uint32_t)max(nd, 1));
-    a[2] = (int)__umulhi(r[3], (uint32_t)L.P);
-    a[3] = (int)__umulhi(r2[0], (uint32_t)max(nc, 1));
-  }
+  uint32_t r2[4] = {0, 0, 0, 0};
+  if (def) philox4x32_10((uint32_t)env, (uint32_t)(env >> 32), step, 0x5A190000u, (uint32_t)seed, (uint32_t)(seed >> 32), r2);
   if (p.cfg.mode == CBX_MODE_MARLON) {
     int32_t* o = att + env * 10;
     for (int k = 0; k < 10; ++k) o[k] = 0;

@@ -1013,6 +1013,88 @@ void orc_step(orc_batch* b, const int32_t* aa, const int32_t* da, const double* 
 
 void orc_stats_reset(orc_batch* b) { memset(b->stats, 0, sizeof(b->stats)); }
 
+/* ---- CyberBattleEnv.sample_valid_action (ENV:959-1047), restated over a counter-based stream --------------------------
+ * The reference draws proposals until the action mask admits one (ENV:1041-1047): kind uniform over [0, 1, 2] -- without 2
+ * while the credential cache is empty (ENV:972-976) --, then, quirk B.9, kind 1 builds a LOCAL action (owned source, any local
+ * vulnerability id) and kind 0 a REMOTE one (owned source, discovered target, any remote id); kind 2 a connect (owned source,
+ * discovered target, any port, a cached credential; ENV:935-957).  "Owned" for the proposal is privilege >= LocalUser
+ * (ENV:832-838); the mask wants agent_installed and, for a local action, the vulnerability on that node (ENV:643-677).  The whole
+ * proposal -- kind included -- is redrawn after a rejection, so local actions are rarer than 1 / kinds.
+ * Draws: Philox4x32-10, counter (env, step, 0x5A170000 + attempt) (+ 0x5A180000 + attempt for the credential), key = seed; an
+ * integer in [0, n) is the high word of r * n.  The CUDA sampler (cbx_sample_kernel) does the same arithmetic: equal outputs.
+ * The defender's action is uniform over its MultiDiscrete space (words of counter 0x5A190000, stepped by an LCG). */
+static inline uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+
+void orc_sample_actions(orc_batch* b, int32_t* att, int32_t* def, uint64_t seed, uint32_t step) {
+  const scn_t* s = &b->s;
+  const int marlon = b->cfg.mode == CBX_MODE_MARLON;
+  const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+  for (int64_t i = 0; i < b->n; ++i) {
+    const oenv_t* e = &b->envs[i];
+    int owned[256], n_owned = 0;
+    for (int k = 0; k < e->n_discovered; ++k)
+      if (e->nodes[e->discovered[k]].privilege_level >= 1) owned[n_owned++] = k;
+    const int nd = e->n_discovered, nc = e->n_cache;
+    int kind = CBX_KIND_REMOTE, a[4] = {0, 0, 0, 0};
+    for (uint32_t it = 0; it < 64; ++it) {
+      uint32_t ctr[4] = {(uint32_t)i, (uint32_t)((uint64_t)i >> 32), step, 0x5A170000u + it}, r[4];
+      philox4x32_10(ctr, key, r);
+      const uint32_t k = mulhi32(r[0], nc > 0 ? 3u : 2u);
+      const int src = n_owned ? owned[mulhi32(r[1], (uint32_t)n_owned)] : 0;
+      const int node = nd ? e->discovered[src] : 0;
+      int valid = n_owned && e->nodes[node].agent_installed;
+      a[0] = src; a[1] = a[2] = a[3] = 0;
+      if (k == 1u) {
+        kind = CBX_KIND_LOCAL;
+        a[1] = (int)mulhi32(r[2], (uint32_t)s->L);
+        valid = valid && (scn_vuln(s, node, a[1])[CBX_V_FLAGS] & 1u);
+      } else if (k == 0u) {
+        kind = CBX_KIND_REMOTE;
+        a[1] = (int)mulhi32(r[2], (uint32_t)(nd > 0 ? nd : 1));
+        a[2] = (int)mulhi32(r[3], (uint32_t)s->R);
+      } else {
+        uint32_t ctr2[4] = {ctr[0], ctr[1], step, 0x5A180000u + it}, q[4];
+        philox4x32_10(ctr2, key, q);
+        kind = CBX_KIND_CONNECT;
+        a[1] = (int)mulhi32(r[2], (uint32_t)(nd > 0 ? nd : 1));
+        a[2] = (int)mulhi32(r[3], (uint32_t)s->P);
+        a[3] = (int)mulhi32(q[0], (uint32_t)nc);
+      }
+      if (valid) break;
+    }
+    if (marlon) {
+      int32_t* o = att + i * 10;
+      for (int k = 0; k < 10; ++k) o[k] = 0;
+      for (int k = 0; k < 3; ++k)
+        if (b->cfg.kind_of_index[k] == kind) o[0] = k;
+      const int width = kind == CBX_KIND_LOCAL ? 2 : kind == CBX_KIND_REMOTE ? 3 : 4;
+      for (int k = 0; k < width; ++k) o[b->slice_of_kind[kind] + k] = a[k];
+      if (def) {
+        uint32_t ctr3[4] = {(uint32_t)i, (uint32_t)((uint64_t)i >> 32), step, 0x5A190000u}, w[4];
+        philox4x32_10(ctr3, key, w);
+        int32_t* d = def + i * 12;
+        const uint32_t n = (uint32_t)s->n;
+        uint32_t x = w[2], y = w[3];
+        d[0] = (int32_t)mulhi32(w[1], 5u);
+        d[1] = (int32_t)mulhi32(x, n); x = x * 1664525u + 1013904223u;
+        d[2] = (int32_t)mulhi32(x, n); x = x * 1664525u + 1013904223u;
+        d[3] = (int32_t)mulhi32(x, 6u); x = x * 1664525u + 1013904223u;
+        d[4] = (int32_t)mulhi32(x, 2u); x = x * 1664525u + 1013904223u;
+        d[5] = (int32_t)mulhi32(x, n);
+        d[6] = (int32_t)mulhi32(y, 6u); y = y * 1664525u + 1013904223u;
+        d[7] = (int32_t)mulhi32(y, 2u); y = y * 1664525u + 1013904223u;
+        d[8] = (int32_t)mulhi32(y, n); y = y * 1664525u + 1013904223u;
+        d[9] = (int32_t)mulhi32(y, 3u); y = y * 1664525u + 1013904223u;
+        d[10] = (int32_t)mulhi32(y, n); y = y * 1664525u + 1013904223u;
+        d[11] = (int32_t)mulhi32(y, 3u);
+      }
+    } else {
+      int32_t* o = att + i * 5;
+      o[0] = kind; o[1] = a[0]; o[2] = a[1]; o[3] = a[2]; o[4] = a[3];
+    }
+  }
+}
+
 int64_t orc_export_words(const orc_batch* b) {
   const scn_t* s = &b->s;
   return CBX_X_HEADER_WORDS + 10 * (int64_t)s->n + b->C + s->Ws;

@@ -45,6 +45,7 @@ def lib():
         L.orc_export_words.argtypes = [C.c_void_p]
         L.orc_export_state.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
         L.orc_philox.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_sample_actions.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32]
         for f in (L.orc_l1_local, L.orc_l1_remote, L.orc_l1_connect):
             f.restype = C.c_double
         L.orc_l1_local.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int)]
@@ -117,6 +118,19 @@ class OracleBatch:
 
     def stats_reset(self):
         self._lib.orc_stats_reset(self._h)
+
+    def sample_actions(self, seed=0, step=None):
+        """CyberBattleEnv.sample_valid_action's distribution (+ a uniform defender action) for the current state of every env;
+        the same draws as ``Batch.sample_actions`` (its k-th call uses step k, counted from 0)."""
+        if step is None:
+            step = getattr(self, "_sample_step", 0)
+            self._sample_step = step + 1
+        marlon = self.cfg.mode == _abi.MODE_MARLON
+        att = np.zeros((self.n_envs, 10 if marlon else 5), dtype=np.int32)
+        dfn = np.zeros((self.n_envs, 12), dtype=np.int32) if marlon and self.cfg.def_enabled else None
+        self._lib.orc_sample_actions(self._h, att.ctypes.data, None if dfn is None else dfn.ctypes.data,
+                                     int(seed) & 0xFFFFFFFFFFFFFFFF, int(step) & 0xFFFFFFFF)
+        return att, dfn
 
     def export_state(self, begin=0, end=None):
         end = self.n_envs if end is None else end

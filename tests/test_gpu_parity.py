@@ -210,6 +210,42 @@ def test_overlapped_launches_back_to_back_match_serialised(monkeypatch, n, steps
     serial.close(); ov.close()
 
 
+@pytest.mark.parametrize("mode", ["marlon", "cyberbattle"])
+def test_device_sampler_equals_oracle_sampler(mode):
+    """cbx_sample_kernel against the oracle's restatement of sample_valid_action (rejection sampling over whole proposals,
+    swapped-kind quirk; the oracle's frequencies are pinned on the live reference by tests/test_sampler_distribution.py): the
+    same actions for the same state and call number, over runs that visit states with and without cached credentials."""
+    from oracle import OracleBatch
+
+    comp = scenario.compile_scenario(scenarios.toyctf_environment())
+    if mode == "marlon":
+        cfg = _toyctf_pair_cfg(attacker_max_timesteps=40, defender_max_timesteps=35)
+    else:
+        cfg = config.make_config(_abi.MODE_CYBERBATTLE, maximum_node_count=12, maximum_total_credentials=10,
+                                 throws_on_invalid_actions=False, attacker_goal=config.AttackerGoal(own_atleast=6),
+                                 defender_agent=config.ScanAndReimageCompromisedMachines(0.6, 2, 5),
+                                 defender_constraint=config.DefenderConstraint(0.80), seed=5, auto_reset=True)
+    n = 777
+    b, o = _batch(comp, cfg, n), OracleBatch(comp, cfg, n)
+    b.reset(); o.reset()
+    kinds = np.zeros(3, dtype=np.int64)
+    for s in range(120):
+        att, dfn = b.sample_actions(seed=77)
+        oa, od = o.sample_actions(seed=77)
+        att = att.cpu().numpy()
+        assert np.array_equal(att, oa), (s, np.argwhere(att != oa)[:4])
+        if dfn is not None:
+            dfn = dfn.cpu().numpy()
+            assert np.array_equal(dfn, od), s
+        kinds += np.bincount(np.array(cfg.kind_of_index)[att[:, 0]] if mode == "marlon" else att[:, 0], minlength=3)
+        b.step(att, dfn)
+        o.step(att, dfn)
+    assert np.array_equal(b.export_state(), o.export_state())
+    assert b.stats()[_abi.STAT_ATT_INVALID] == 0  # every sampled action passed the wrapper's range check
+    assert kinds.min() > 0 and kinds[_abi.KIND_LOCAL] < kinds[_abi.KIND_REMOTE]  # local proposals are rejected more often
+    b.close()
+
+
 def test_chain10_attacker_only_4096_envs_vs_oracle():
     """BASELINE.json configs[1]: CyberBattleChain-10 attacker-only, 4096 batched envs, bit-exact."""
     comp = scenario.compile_scenario(scenarios.chain_environment(10))
