@@ -635,6 +635,41 @@ def e2e_vecenv(m, K, W, world, local, dev, observations):
     return _max_over_ranks(secs, world, dev)
 
 
+def device_rollout(m, world, local, dev, T=32, rounds=3):
+    """rollout collection with everything resident in HBM -- observations are the batch's own tensors, two small
+    MLP actor-critics (marlon_b200.ppo.MultiDiscretePolicy) pick both agents' MultiDiscrete actions on the device, one fused
+    attacker+defender launch per step, rewards / values / log-probabilities into [T, n] device buffers, GAE by cbx_gae.
+    -> seconds for rounds x T steps (CUDA events, max over ranks)."""
+    import torch
+    import torch.distributed as dist
+
+    from marlon_b200 import ppo
+    from marlon_b200.rollout import DeviceRolloutBuffer, collect_rollouts
+    from marlon_b200.universe import MultiAgentUniversalEnv
+
+    n = m["n"]
+    torch.manual_seed(7)
+    u = MultiAgentUniversalEnv("CyberBattleToyCtf-v0", n, device=local, maximum_node_count=12, maximum_total_credentials=10,
+                               maximum_discoverable_credentials_per_action=5, max_timesteps=2000)
+    aobs, dobs = u.reset()
+    apol = ppo.MultiDiscretePolicy.for_space(aobs, u.attacker_action_space.nvec, ppo.ATTACKER_FEATURES).to(dev)
+    dpol = ppo.MultiDiscretePolicy.for_space(dobs, u.defender_action_space.nvec, ppo.DEFENDER_FEATURES).to(dev)
+    ab, db = DeviceRolloutBuffer(T, n, 10, dev), DeviceRolloutBuffer(T, n, 12, dev)
+    collect_rollouts(u, apol, ab, dpol, db)  # warm-up: allocator, cuBLAS handles
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(rounds):
+        collect_rollouts(u, apol, ab, dpol, db)
+    e1.record()
+    torch.cuda.synchronize()
+    secs = e0.elapsed_time(e1) * 1e-3
+    u.close()
+    return _max_over_ranks(secs, world, dev), T * rounds
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -666,9 +701,10 @@ def run_ours(args):
         Ko = min(K, 200)
         obs2_s, d2h_obs = e2e_obs_factored(m, Ko, W, world, local, dev, halves=2)
         obs1_s, _ = e2e_obs_factored(m, Ko, W, world, local, dev, halves=1)
-        vt_s = vn_s = None
-        Kv, Kn = min(K, 100), min(K, 5)
+        vt_s = vn_s = roll_s = None
+        Kv, Kn, Kr = min(K, 100), min(K, 5), 0
         if args.workload == "toyctf" and not m["factored"]:
+            roll_s, Kr = device_rollout(m, world, local, dev)
             vt_s = e2e_vecenv(m, Kv, W, world, local, dev, "torch")
             if world == 1:
                 vn_s = e2e_vecenv(m, Kn, min(W, 3), world, local, dev, "numpy")
@@ -683,6 +719,8 @@ def run_ours(args):
                        "value": total_envs * Ko / obs2_s, "steps": Ko, "h2d_bytes_per_step": act_b * 2, "d2h_bytes_per_step": d2h_obs},
                    "obs_factored_sequential": None if obs1_s is None else {
                        "value": total_envs * Ko / obs1_s, "steps": Ko, "h2d_bytes_per_step": act_b * 2, "d2h_bytes_per_step": d2h_obs},
+                   "device_rollout_mlp_policies": None if roll_s is None else {
+                       "value": total_envs * Kr / roll_s, "steps": Kr, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                    "vecenv_torch_obs": None if vt_s is None else {
                        "value": total_envs * Kv / vt_s, "steps": Kv, "h2d_bytes_per_step": act_b * 4, "d2h_bytes_per_step": n * 24},
                    "vecenv_numpy_dense_obs": None if vn_s is None else {
@@ -694,7 +732,8 @@ def run_ours(args):
                        "observations stay in HBM as torch tensors (the consumer is a GPU-resident policy).  For a HOST-side policy "
                        "the observation has to cross PCIe as well: obs_factored_* bring every small field + the factored masks + the "
                        "defender observation to pinned host memory each step (cbx_batch_fetch_host; two_halves overlaps one half "
-                       "batch's copies with the other's step), vecenv_* go through the SB3 VecEnv adapter (attacker step + defender "
+                       "batch's copies with the other's step), device_rollout_mlp_policies is rollout.collect_rollouts with two small MLP "
+                       "actor-critics choosing both agents' actions on the device and GAE by cbx_gae (nothing crosses PCIe), vecenv_* go through the SB3 VecEnv adapter (attacker step + defender "
                        "step, int64 numpy actions, infos built; numpy_dense_obs copies the full dense observation, 12.4 KB per env, "
                        "every step).  All variants: allocations and W warm-up calls of the same entry point before the clock starts."}
 

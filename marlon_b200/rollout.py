@@ -77,6 +77,24 @@ class DeviceRolloutBuffer:
                                  self.n_steps, self.n_envs, p(self.advantages), p(self.returns), stream))
         self._keep = (lv, ld)
 
+    def get(self, batch_size: Optional[int] = None, generator=None):
+        """SB3 ``RolloutBuffer.get``: shuffled minibatches of ``RolloutBufferSamples`` over the whole buffer (device tensors; the
+        flat sample index is SB3's env-major ``swap_and_flatten`` order, drawn with ``torch.randperm`` on the device)."""
+        from .ppo import RolloutBufferSamples
+
+        torch = self._torch
+        assert self.full, "rollout buffer not full"
+        T, n = self.n_steps, self.n_envs
+        total = T * n
+        perm = torch.randperm(total, device=self.device, generator=generator)
+        batch_size = total if batch_size is None else int(batch_size)
+        for start in range(0, total, batch_size):
+            idx = perm[start:start + batch_size]
+            e, t = idx // T, idx % T  # swap_and_flatten: sample i = (env i // n_steps, step i % n_steps)
+            obs = {k: v[t, e] for k, v in self.observations.items()}
+            yield RolloutBufferSamples(obs, self.actions[t, e], self.values[t, e], self.log_probs[t, e], self.advantages[t, e],
+                                       self.returns[t, e])
+
 
 def collect_rollouts(universe, attacker_policy: Policy, attacker_buffer: DeviceRolloutBuffer,
                      defender_policy: Optional[Policy] = None, defender_buffer: Optional[DeviceRolloutBuffer] = None,
