@@ -391,6 +391,9 @@ def measure_device(args, workload, n_req, K, W, world, rank, local, dev, clocks=
     b.reset()
     for s in range(W):
         b.step(tape_a[s], tape_d[s])
+    warm = b.stats_tensor.clone()  # the collective's path once before the clock starts (allocator, NCCL channel set-up)
+    if world > 1:
+        dist.all_reduce(warm, op=dist.ReduceOp.SUM)
     b.stats_reset()
     b.enable_timing(True)
     launches0 = b.launch_count

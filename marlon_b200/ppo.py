@@ -44,7 +44,10 @@ def flatten_observation(obs: Dict[str, torch.Tensor], keys: Sequence[str]) -> to
 
 
 class MultiDiscretePolicy(nn.Module):
-    """Actor-critic with one categorical head per component of a ``MultiDiscrete`` action space."""
+    """Actor-critic with one categorical head per component of a ``MultiDiscrete`` action space.  All heads are evaluated
+    together: the logits are scattered into a padded [n, components, max choices] tensor (-inf padding), so sampling
+    (Gumbel-max), log-probabilities and entropies are a handful of kernels whatever the number of components -- the same
+    distribution as one ``torch.distributions.Categorical`` per head, without its per-head launches and argument checks."""
 
     def __init__(self, n_features: int, nvec: Sequence[int], feature_keys: Sequence[str], hidden: int = 64):
         super().__init__()
@@ -53,37 +56,44 @@ class MultiDiscretePolicy(nn.Module):
         self.body = nn.Sequential(nn.Linear(n_features, hidden), nn.Tanh(), nn.Linear(hidden, hidden), nn.Tanh())
         self.pi = nn.Linear(hidden, sum(self.nvec))
         self.vf = nn.Linear(hidden, 1)
+        A, K = len(self.nvec), max(self.nvec)
+        index = torch.zeros(A, K, dtype=torch.long)   # column of the flat logits that feeds padded slot (a, k)
+        valid = torch.zeros(A, K, dtype=torch.bool)
+        off = 0
+        for a, n in enumerate(self.nvec):
+            index[a, :n] = torch.arange(off, off + n)
+            valid[a, :n] = True
+            off += n
+        self.register_buffer("_index", index.reshape(-1), persistent=False)
+        self.register_buffer("_valid", valid, persistent=False)
 
     @classmethod
     def for_space(cls, observation: Dict[str, torch.Tensor], nvec, feature_keys, hidden: int = 64) -> "MultiDiscretePolicy":
         n_features = flatten_observation({k: observation[k][:1] for k in feature_keys}, feature_keys).shape[1]
         return cls(n_features, nvec, feature_keys, hidden)
 
-    def _heads(self, obs):
+    def _log_probs(self, obs):
+        """-> (log-probabilities [n, A, K] with -inf at the padding, values [n])"""
         x = obs if torch.is_tensor(obs) else flatten_observation(obs, self.feature_keys)
         h = self.body(x)
-        return torch.split(self.pi(h), self.nvec, dim=1), self.vf(h).squeeze(1)
+        A, K = self._valid.shape
+        logits = self.pi(h).index_select(1, self._index).reshape(-1, A, K).masked_fill(~self._valid, float("-inf"))
+        return torch.log_softmax(logits, dim=2), self.vf(h).squeeze(1)
 
     def forward(self, obs, action_masks=None):
         """-> (actions int32 [n, A], values [n], log_probs [n]); the call signature ``rollout.collect_rollouts`` expects."""
-        logits, values = self._heads(obs)
-        acts, logp = [], 0.0
-        for lg in logits:
-            d = torch.distributions.Categorical(logits=lg)
-            a = d.sample()
-            acts.append(a)
-            logp = logp + d.log_prob(a)
-        return torch.stack(acts, dim=1).to(torch.int32), values, logp
+        logp, values = self._log_probs(obs)
+        u = torch.rand_like(logp).clamp_(1e-20, 1.0)
+        actions = torch.argmax(logp - torch.log(-torch.log(u)), dim=2)  # Gumbel-max: a sample of each head's categorical
+        return actions.to(torch.int32), values, logp.gather(2, actions.unsqueeze(2)).squeeze(2).sum(1)
 
     def evaluate_actions(self, obs, actions):
         """-> (values, log_prob, entropy) of `actions` under the current policy (SB3 ``ActorCriticPolicy.evaluate_actions``)."""
-        logits, values = self._heads(obs)
-        logp, ent = 0.0, 0.0
-        for k, lg in enumerate(logits):
-            d = torch.distributions.Categorical(logits=lg)
-            logp = logp + d.log_prob(actions[:, k].long())
-            ent = ent + d.entropy()
-        return values, logp, ent
+        logp, values = self._log_probs(obs)
+        chosen = logp.gather(2, actions.long().unsqueeze(2)).squeeze(2).sum(1)
+        p = torch.exp(logp)
+        entropy = -(torch.where(self._valid, p * logp, torch.zeros_like(p))).sum((1, 2))
+        return values, chosen, entropy
 
 
 def ppo_loss(policy, s: RolloutBufferSamples, clip_range: float = 0.2, ent_coef: float = 0.0, vf_coef: float = 0.5,
