@@ -44,7 +44,7 @@
 extern "C" {
 #endif
 
-#define CBX_ABI_VERSION 1
+#define CBX_ABI_VERSION 2
 
 typedef enum {
   CBX_OK = 0,
@@ -83,6 +83,15 @@ enum { /* word indices inside the header */
   CBX_H_OFF_TRIPLE, /* n_triples * 3 : node index, port index, secret id */
   CBX_H_WORDS = 24
 };
+
+/* firewall extension tables (cbx_scenario_set_firewall_tables; `live` defender binding) */
+#define CBX_FWX_MAGIC 0x46584243u /* "CBXF" */
+enum { CBX_FX_MAGIC = 0,
+       CBX_FX_N_NAMES,  /* port names that matter: RDP, SSH, HTTPS, HTTP, su, sudo (defend_wrapper.py:31), then the attacker's ports */
+       CBX_FX_N_GROUPS, /* distinct firewall rule LIST objects (several (node, direction) pairs may share one) */
+       CBX_FX_RESERVED,
+       CBX_FX_WORDS };  /* then: name index of every attacker port [n_ports] | per node: incoming group | outgoing group << 16 [n]
+                           | per group: names with a rule, names whose first rule ALLOWs [2 * groups] (the initial per-env state) */
 
 #define CBX_NODE_WORDS 8
 enum { /* per-node record */
@@ -169,7 +178,17 @@ typedef struct cbx_config {
   double def_sla_worsening_penalty_scale;
   int32_t mask_mode;                 /* CBX_MASK_* */
   int32_t emit_terminal_obs;         /* 1: keep a second observation buffer holding the pre-reset observation of done envs */
+  int32_t def_binding;               /* CBX_DEF_BINDING_*: which environment the LearningDefender acts on */
+  int32_t reserved0;
 } cbx_config;
+
+enum { CBX_DEF_BINDING_STALE = 0, /* the reference AS EXECUTED: DefenderEnvWrapper / LearningDefender keep the actuator and
+                                     environment they saw at construction (defend_wrapper.py:51, defender.py:29-30), which every
+                                     CyberBattleEnv.reset() replaces: re-imaging, blocking and allowing hit a dead copy */
+       CBX_DEF_BINDING_LIVE = 1 };/* the binding refreshed at every CyberBattleEnv.reset(): the defender re-images nodes of, and
+                                     edits the firewall rule lists of, the environment the attacker plays in (rule lists shared
+                                     between nodes stay shared; allow always appends to INCOMING, B.3; stop / start
+                                     service stay no-ops, B.4).  Needs cbx_scenario_set_firewall_tables. */
 
 /* ---------------------------------------------------------------------------------------------
  * Views: device pointers of every per-env output array (row-major, batch dimension first).
@@ -308,6 +327,10 @@ int cbx_abi_version(void);
 
 int cbx_scenario_create(const void* tables, size_t nbytes, cbx_scenario** out);
 int cbx_scenario_destroy(cbx_scenario* s);
+/* Firewall extension tables of a scenario (marlon_b200/scenario.py FWX_* layout: port-name indices, the rule-list alias group
+ * of every (node, direction), two bits per (group, name)): required by CBX_DEF_BINDING_LIVE, where firewall rule lists
+ * (model.FirewallConfiguration, model.py:240-262) become per-env state. */
+int cbx_scenario_set_firewall_tables(cbx_scenario* s, const void* words, size_t nbytes);
 
 int cbx_config_default(cbx_config* cfg);
 int cbx_batch_create(const cbx_scenario* s, int64_t n_envs, const cbx_config* cfg, int device, cbx_batch** out);

@@ -2,7 +2,7 @@
 ``tests/test_abi.py`` checks sizes/offsets against the compiled library (``cbx_abi_sizeof``)."""
 import ctypes as C
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 MODE_CYBERBATTLE, MODE_MARLON = 0, 1
 KIND_LOCAL, KIND_REMOTE, KIND_CONNECT = 0, 1, 2
@@ -10,6 +10,7 @@ KIND_NAMES = {KIND_LOCAL: "local_vulnerability", KIND_REMOTE: "remote_vulnerabil
 KIND_WIDTH = {KIND_LOCAL: 2, KIND_REMOTE: 3, KIND_CONNECT: 4}
 MASK_DENSE, MASK_FACTORED = 0, 1
 BUILTIN_NONE, BUILTIN_SCAN_AND_REIMAGE = 0, 1
+DEF_BINDING_STALE, DEF_BINDING_LIVE = 0, 1
 
 (STAT_EPISODES, STAT_ATT_RETURN, STAT_ATT_RETURN_SQ, STAT_EP_LEN, STAT_EP_LEN_SQ, STAT_DEF_RETURN,
  STAT_DEF_RETURN_SQ, STAT_ATT_VALID, STAT_ATT_INVALID, STAT_DEF_VALID, STAT_DEF_INVALID, STAT_ATT_WINS,
@@ -74,6 +75,8 @@ class Config(C.Structure):
         ("def_sla_worsening_penalty_scale", C.c_double),
         ("mask_mode", C.c_int32),
         ("emit_terminal_obs", C.c_int32),
+        ("def_binding", C.c_int32),
+        ("reserved0", C.c_int32),
     ]
 
 

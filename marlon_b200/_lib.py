@@ -19,7 +19,7 @@ SYMBOLS = [
     "cbx_batch_sample_actions", "cbx_batch_views", "cbx_batch_stats_reset", "cbx_export_words",
     "cbx_batch_export_state", "cbx_batch_launch_count", "cbx_batch_enable_timing", "cbx_batch_step_kernel_ms",
     "cbx_abi_sizeof", "cbx_batch_step_ex", "cbx_batch_reset_ex", "cbx_batch_phase_cycles", "cbx_batch_notify_reset", "cbx_batch_kernel_info", "cbx_batch_create_multi", "cbx_batch_export_words", "cbx_gae",
-    "cbx_batch_host_prepare", "cbx_batch_fetch_host_layout", "cbx_batch_fetch_host", "cbx_batch_step_host_ex", "cbx_batch_tile_counter",
+    "cbx_batch_host_prepare", "cbx_batch_fetch_host_layout", "cbx_batch_fetch_host", "cbx_batch_step_host_ex", "cbx_batch_tile_counter", "cbx_scenario_set_firewall_tables",
 ]
 
 
@@ -44,6 +44,7 @@ def load():
     L.cbx_abi_version.restype = C.c_int
     L.cbx_scenario_create.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
     L.cbx_scenario_destroy.argtypes = [vp]
+    L.cbx_scenario_set_firewall_tables.argtypes = [vp, vp, C.c_size_t]
     L.cbx_config_default.argtypes = [C.POINTER(_abi.Config)]
     L.cbx_batch_create.argtypes = [vp, i64, C.POINTER(_abi.Config), C.c_int, C.POINTER(vp)]
     L.cbx_batch_destroy.argtypes = [vp]

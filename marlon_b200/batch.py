@@ -67,6 +67,9 @@ class Batch:
                 h = C.c_void_p()
                 _lib.check(self._L.cbx_scenario_create(blob, len(blob), C.byref(h)))
                 self._scns.append(h)
+                if getattr(comp, "fw_ext", None) is not None:  # rule-list alias groups: what the `live` defender binding edits
+                    ext = np.ascontiguousarray(comp.fw_ext, dtype="<u4").tobytes()
+                    _lib.check(self._L.cbx_scenario_set_firewall_tables(h, ext, len(ext)))
             with torch.cuda.device(self.device):
                 torch.cuda.init()
                 if multi:

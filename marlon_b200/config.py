@@ -80,6 +80,7 @@ def make_config(
     defender_reset_on_constraint_broken: bool = True,
     defender_loss_reward: float = -5000.0,
     defender_sla_worsening_penalty_scale: float = 200.0,
+    defender_binding: str = "reference_stale",
     # batched-only knobs
     auto_reset: bool = True,
     mask_mode: int = _abi.MASK_DENSE,
@@ -137,6 +138,9 @@ def make_config(
     c.def_sla_worsening_penalty_scale = float(defender_sla_worsening_penalty_scale)
     c.mask_mode = int(mask_mode)
     c.emit_terminal_obs = int(bool(emit_terminal_obs))
+    if defender_binding not in ("reference_stale", "live"):
+        raise ValueError("defender_binding: 'reference_stale' (the reference as executed, SURVEY.md B.1) or 'live'")
+    c.def_binding = _abi.DEF_BINDING_LIVE if defender_binding == "live" else _abi.DEF_BINDING_STALE
     return c
 
 

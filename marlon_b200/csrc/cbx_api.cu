@@ -176,6 +176,7 @@ constexpr int kTicketRing = 1024;
 
 struct cbx_scenario {
   std::vector<uint32_t> blob;
+  std::vector<uint32_t> fwx;  // firewall extension tables (cbx_scenario_set_firewall_tables), empty if never set
   int n, P, nprops, L, R, nsecrets, ntriples, nservices, max_leak, flags;
 };
 
@@ -255,6 +256,23 @@ int cbx_scenario_destroy(cbx_scenario* s) {
   return CBX_OK;
 }
 
+int cbx_scenario_set_firewall_tables(cbx_scenario* s, const void* words, size_t nbytes) {
+  if (!s || !words || nbytes < 16 || nbytes % 16) return fail(CBX_ERR_INVALID, "firewall tables: null, too small or not a multiple of 16 bytes");
+  const uint32_t* w = (const uint32_t*)words;
+  if (w[CBX_FX_MAGIC] != CBX_FWX_MAGIC) return fail(CBX_ERR_INVALID, "bad firewall-table magic");
+  const size_t need = (size_t)CBX_FX_WORDS + s->P + s->n + 2 * (size_t)w[CBX_FX_N_GROUPS];
+  if (w[CBX_FX_N_NAMES] < 6 || w[CBX_FX_N_NAMES] > 32 || w[CBX_FX_N_GROUPS] < 1 || w[CBX_FX_N_GROUPS] > 2u * s->n || need * 4 > nbytes)
+    return fail(CBX_ERR_INVALID, "firewall tables: header out of range");
+  for (int p = 0; p < s->P; ++p)
+    if (w[CBX_FX_WORDS + p] >= w[CBX_FX_N_NAMES]) return fail(CBX_ERR_INVALID, "firewall tables: port name index out of range");
+  for (int i = 0; i < s->n; ++i) {
+    const uint32_t g = w[CBX_FX_WORDS + s->P + i];
+    if ((g & 0xFFFFu) >= w[CBX_FX_N_GROUPS] || (g >> 16) >= w[CBX_FX_N_GROUPS]) return fail(CBX_ERR_INVALID, "firewall tables: group out of range");
+  }
+  s->fwx.assign(w, w + nbytes / 4);
+  return CBX_OK;
+}
+
 int cbx_config_default(cbx_config* c) {
   if (!c) return fail(CBX_ERR_INVALID, "null config");
   memset(c, 0, sizeof(*c));
@@ -283,6 +301,9 @@ int cbx_config_default(cbx_config* c) {
 
 static int compute_layout(const cbx_scenario* s, const cbx_config* cfg, int64_t n_envs, cbx_layout* L) {
   memset(L, 0, sizeof(*L));
+  const bool live = cfg->mode == CBX_MODE_MARLON && cfg->def_enabled && cfg->def_binding == CBX_DEF_BINDING_LIVE;
+  if (live && s->fwx.empty())
+    return fail(CBX_ERR_INVALID, "the live defender binding needs the scenario's firewall tables (cbx_scenario_set_firewall_tables)");
   L->n = s->n; L->N = cfg->maximum_node_count; L->C = cfg->maximum_total_credentials;
   L->LEAK = cfg->maximum_discoverable_credentials_per_action;
   L->P = s->P; L->L = s->L; L->R = s->R; L->nprops = s->nprops; L->nsecrets = s->nsecrets; L->ntriples = s->ntriples;
@@ -315,6 +336,8 @@ static int compute_layout(const cbx_scenario* s, const cbx_config* cfg, int64_t 
   L->o_notrunning = o; o += L->Wn;
   L->o_priv = o; o += (L->n + 15) / 16;
   if (s->flags & 1) { L->o_tags = o; o += (L->n + 7) / 8; } else L->o_tags = -1;
+  L->o_fw = -1; L->n_fw_groups = 0;
+  if (live) { L->n_fw_groups = (int)s->fwx[CBX_FX_N_GROUPS]; L->o_fw = o; o += 2 * L->n_fw_groups; }
   L->o_cd_live = o; o += (L->n + 3) / 4;
   L->o_disc_order = o; o += (L->n + 3) / 4;
   L->o_disc_idx = o; o += (L->n + 3) / 4;
@@ -363,6 +386,10 @@ static void build_init_state(const cbx_scenario* s, const cbx_layout& L, std::ve
     st[L.o_priv + i / 16] |= (uint32_t)priv << ((i % 16) * 2);
   }
   st[L.o_hdr] = (uint32_t)nd;
+  if (L.o_fw >= 0) {  // live defender binding: the rule lists as the scenario defines them
+    const uint32_t* g0 = s->fwx.data() + CBX_FX_WORDS + s->P + s->n;
+    for (int k = 0; k < 2 * L.n_fw_groups; ++k) st[L.o_fw + k] = g0[k];
+  }
 }
 
 static int create_impl(const cbx_scenario* const* scns, int n_scn, const int64_t* counts, int64_t n_envs, const cbx_config* cfg, int device,
@@ -437,7 +464,10 @@ static int create_impl(const cbx_scenario* const* scns, int n_scn, const int64_t
   b->p.n_tiles = (int)(b->p.n_pad / CBX_TILE);
   b->p.table_words = (int)max_blob;
   b->p.n_scenarios = n_scn;
-  b->p.table_stride = (int)max_blob + ((b->p.lay.S + 3) & ~3);
+  const bool live = L.o_fw >= 0;
+  if (live && n_scn > 1) { delete b; return fail(CBX_ERR_UNSUPPORTED, "the live defender binding is single-scenario"); }
+  b->p.fwx_words = live ? (int)scns[0]->fwx.size() : 0;
+  b->p.table_stride = (int)max_blob + ((b->p.lay.S + 3) & ~3) + b->p.fwx_words;
   b->p.tile_scn = nullptr;
   int col = 1;
   for (int k = 0; k < 3; ++k) {
@@ -485,7 +515,7 @@ static int create_impl(const cbx_scenario* const* scns, int n_scn, const int64_t
   // shared-memory plan
   cbx_smem_plan& pl = b->p.plan;
   int o = 0;
-  pl.tables = o; o = align_up(o + b->p.table_words + ((L.S + 3) & ~3), 32);
+  pl.tables = o; o = align_up(o + b->p.table_words + ((L.S + 3) & ~3) + b->p.fwx_words, 32);
   pl.lut = o; o = align_up(o + 512, 32);
   pl.bars = o; o = align_up(o + 8, 32);
   pl.state = o; o = align_up(o + L.S * CBX_TILE, 32);
@@ -518,7 +548,7 @@ static int create_impl(const cbx_scenario* const* scns, int n_scn, const int64_t
   b->p.pipe.enabled = 0; b->pipe_grid = 0;
   {
     const char* pe = getenv("CBX_PIPE");
-    if (b->use_tma && n_scn == 1 && !(pe && pe[0] == '0')) {
+    if (b->use_tma && n_scn == 1 && !live && !(pe && pe[0] == '0')) {  // live binding: per-env firewall rows -> the fused kernel
       const char *ewl = getenv("CBX_PIPE_WL"), *ewe = getenv("CBX_PIPE_WE"), *ect = getenv("CBX_PIPE_CTAS");
       const int cand[4][2] = {{4, 8}, {3, 8}, {2, 8}, {2, 4}};
       cbx_pipe_plan Q;
@@ -550,7 +580,7 @@ static int create_impl(const cbx_scenario* const* scns, int n_scn, const int64_t
 
   // warp-per-tile kernel: large per-env state (or several scenarios) with factored masks; CBX_WIDE=0/1 overrides the choice
   b->p.wide.enabled = 0; b->wide_grid = 0;
-  if (!b->p.pipe.enabled && b->use_tma) {
+  if (!b->p.pipe.enabled && b->use_tma && !live) {
     const char* we = getenv("CBX_WIDE");
     const bool want = we ? we[0] == '1' : (b->p.lay.S >= 128 || n_scn > 1);
     cbx_wide_plan Q;
@@ -589,6 +619,7 @@ static int create_impl(const cbx_scenario* const* scns, int n_scn, const int64_t
       tab.insert(tab.end(), scns[k]->blob.begin(), scns[k]->blob.end());
       tab.resize(tab.size() + (max_blob - scns[k]->blob.size()), 0u);
       tab.insert(tab.end(), init.begin(), init.end());
+      if (b->p.fwx_words) tab.insert(tab.end(), scns[k]->fwx.begin(), scns[k]->fwx.end());
     }
     void* pt = nullptr;
     cudaError_t e = dalloc(&pt, tab.size() * 4);
@@ -1048,7 +1079,7 @@ int cbx_batch_export_state(cbx_batch* b, int64_t begin, int64_t end, int32_t* ou
     p += n;
     for (int k = 0; k < n; ++k) p[k] = byte(L.o_cd_live, k);
     p += n;
-    for (int k = 0; k < n; ++k) p[k] = byte(L.o_cd_shadow, k);
+    for (int k = 0; k < n; ++k) p[k] = byte(L.o_fw >= 0 ? L.o_cd_live : L.o_cd_shadow, k);  // the actuator the defender's wrapper is bound to
     p += n;
     for (int k = 0; k < n; ++k) p[k] = bit(L.o_everowned, k);
     p += n;

@@ -58,6 +58,7 @@ struct Ctx {
   const cbx_layout* L;
   const cbx_config* cfg;
   int64_t env;           // global env index
+  const uint32_t* fx = nullptr;  // firewall extension tables (cbx.h CBX_FX_*) under the LIVE defender binding, else nullptr
 
   __device__ __forceinline__ uint32_t& w(int off) const { return st[off * CBX_TILE]; }
   __device__ __forceinline__ uint32_t& g(int off) const { return sg[off * CBX_TILE]; }
@@ -108,6 +109,40 @@ struct Ctx {
   }
   __device__ __forceinline__ const uint32_t* triple(int t) const { return tb + tb[CBX_H_OFF_TRIPLE] + 3 * t; }
   __device__ __forceinline__ const uint32_t* payload(const uint32_t* rec) const { return tb + tb[CBX_H_OFF_PAYLOAD] + rec[CBX_V_PAYLOAD_OFF]; }
+
+  // ---- firewall rule lists as per-env state (live defender binding) ------------------------------
+  // One list object may serve several (node, direction) pairs: the unit of state is the list (alias group), two words each:
+  // port names that have a rule, names whose FIRST rule allows (ACT:504-515 asks nothing else of a list).
+  __device__ __forceinline__ int fw_group(int node, bool incoming) const {
+    const uint32_t g = fx[CBX_FX_WORDS + tb[CBX_H_N_PORTS] + node];
+    return (int)(incoming ? (g & 0xFFFFu) : (g >> 16));
+  }
+  __device__ __forceinline__ bool fw_has_rule(int node, bool incoming, int name) const {
+    return (w(L->o_fw + 2 * fw_group(node, incoming)) >> name) & 1u;
+  }
+  // ACT:504-515 __is_passing_firewall_rules for an attacker port: static pass bits, or the env's own lists when the defender
+  // edits them
+  __device__ __forceinline__ bool fw_passes(int node, bool incoming, int port) const {
+    if (!fx) return (node_rec(node)[incoming ? CBX_N_FW_IN : CBX_N_FW_OUT] >> port) & 1u;
+    const int g = fw_group(node, incoming), name = (int)fx[CBX_FX_WORDS + port];
+    return ((w(L->o_fw + 2 * g) & w(L->o_fw + 2 * g + 1)) >> name) & 1u;  // a rule exists and the first one allows
+  }
+  // LDF:50-58 block_traffic: every rule of that name leaves the list the (node, direction) pair points at
+  __device__ __forceinline__ void fw_block(int node, bool incoming, int name) const {
+    const int g = fw_group(node, incoming);
+    w(L->o_fw + 2 * g) &= ~(1u << name);
+    w(L->o_fw + 2 * g + 1) &= ~(1u << name);
+  }
+  // LDF:60-69 allow_traffic: when the selected list has no rule of that name, an ALLOW rule is appended -- to the node's
+  // INCOMING list whatever the direction (both arms of the conditional expression append to incoming); appended behind an
+  // existing rule of that name it changes neither "has a rule" nor "first rule allows"
+  __device__ __forceinline__ void fw_allow(int node, bool incoming, int name) const {
+    if (fw_has_rule(node, incoming, name)) return;
+    const int gi = fw_group(node, true);
+    if ((w(L->o_fw + 2 * gi) >> name) & 1u) return;
+    w(L->o_fw + 2 * gi) |= 1u << name;
+    w(L->o_fw + 2 * gi + 1) |= 1u << name;
+  }
 
   // ---- AgentActions -------------------------------------------------------------------------------------
   __device__ int discover(int node) const {  // ACT:227-232 + ENV:866-869: append to the discovery order
@@ -243,8 +278,9 @@ struct Ctx {
     if (!bit(L->o_gathered, secret)) return invalid(CBX_E_CREDENTIAL_NOT_GATHERED);
     const uint32_t* rs = node_rec(src);
     const uint32_t* rt = node_rec(tgt);
-    if (!((rs[CBX_N_FW_OUT] >> port) & 1u)) { r.reward = -10.0; return r; }
-    if (!((rt[CBX_N_FW_IN] >> port) & 1u)) { r.reward = -10.0; return r; }
+    (void)rs;
+    if (!fw_passes(src, false, port)) { r.reward = -10.0; return r; }
+    if (!fw_passes(tgt, true, port)) { r.reward = -10.0; return r; }
     if (!((rt[CBX_N_LISTEN] >> port) & 1u)) { r.reward = -10.0; return r; }
     if (bit(L->o_notrunning, tgt)) { r.reward = 0.0; return r; }
     const int Ws = (n_secrets() + 31) >> 5;
@@ -343,7 +379,9 @@ struct Ctx {
     for (int k = L->o_cyber_begin; k < L->S; ++k) w(k) = init[k];
     uint32_t flags = w(L->o_hdr) & (HDR_ATT_RR | HDR_DEF_RR | HDR_BREACHED | HDR_HAS_CYBER | HDR_HAS_REWARD);
     w(L->o_hdr) = (init[L->o_hdr] & 0x00FFFFFFu) | flags;
-    w(L->o_avail) &= ~0xFFu;  // fresh DefenderAgentActions: availability 1.0
+    // fresh DefenderAgentActions: availability 1.0 -- of the live env (bits 0-7) and, under the live binding, of the
+    // actuator the defender's wrapper reads (bits 8-15: it is the same object there)
+    w(L->o_avail) &= fx ? ~0xFFFFu : ~0xFFu;
   }
   __device__ void snapshot_for_obs() const {
     for (int k = 0; k < L->Wn; ++k) g(L->g_inst + k) = w(L->o_installed + k);
@@ -446,7 +484,9 @@ struct Ctx {
     setf32(L->o_last_att, 0.f);
     w(L->o_def_ts) = 0; w(L->o_def_valid) = 0; w(L->o_def_invalid) = 0;
     uint32_t a = w(L->o_avail);
-    w(L->o_avail) = (a & ~0xFF0000u) | (((a >> 8) & 0xFFu) << 16);  // _prev_network_availability = stale actuator's value
+    // _prev_network_availability = the bound actuator's value: the stale copy's (it outlives resets), or, live, the fresh
+    // actuator's 1.0 (bits 8-15 were just cleared with the env)
+    w(L->o_avail) = (a & ~0xFF0000u) | (((a >> 8) & 0xFFu) << 16);
     setf32(L->o_def_return, 0.f);
   }
   __device__ bool defender_action_valid(const int32_t* a) const {  // DWR:329-412, on the LIVE env
@@ -456,7 +496,8 @@ struct Ctx {
     auto node_ok = [&](int x) { return x >= 0 && x < n && !bit(L->o_notrunning, x); };
     switch (a[0]) {
       case 0: return node_ok(a[1]) && (node_rec(a[1])[CBX_N_FLAGS] & 1u);
-      case 1: return node_ok(a[2]) && a[3] >= 0 && a[3] < 6 && ((node_rec(a[2])[CBX_N_DEFOBS] >> ((a[4] ? 0 : 8) + a[3])) & 1u);
+      case 1: return node_ok(a[2]) && a[3] >= 0 && a[3] < 6 &&
+                     (fx ? fw_has_rule(a[2], a[4] != 0, a[3]) : (bool)((node_rec(a[2])[CBX_N_DEFOBS] >> ((a[4] ? 0 : 8) + a[3])) & 1u));
       case 2: return node_ok(a[5]);
       case 3: return node_ok(a[8]) && a[9] >= 0 && a[9] < (int)((node_rec(a[8])[CBX_N_FLAGS] >> 8) & 0xFFu);
       case 4: return node_ok(a[10]) && a[11] >= 0 && a[11] < (int)((node_rec(a[10])[CBX_N_FLAGS] >> 8) & 0xFFu);

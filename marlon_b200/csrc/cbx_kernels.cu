@@ -41,7 +41,8 @@ __global__ void __launch_bounds__(CBX_THREADS, CBX_MIN_CTAS) cbx_step_kernel(con
   const int DW = p.enc.desc_words;
   const int AW = marlon ? 10 : 5;  // attacker action words per env
   const uint32_t* s_init = s_tb + p.table_words;  // initial per-env state follows the scenario blob
-  const uint32_t table_bytes = (uint32_t)(p.table_words + ((L.S + 3) & ~3)) * 4u;
+  const uint32_t table_bytes = (uint32_t)(p.table_words + ((L.S + 3) & ~3) + p.fwx_words) * 4u;
+  const uint32_t* s_fx = p.fwx_words ? s_init + ((L.S + 3) & ~3) : nullptr;  // live defender binding: firewall extension tables
 
   // bits -> bytes expansion table: 8 mask bits to 8 bytes of 0/1
   for (int k = tid; k < 256; k += CBX_THREADS) {
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(CBX_THREADS, CBX_MIN_CTAS) cbx_step_kernel(con
     CBX_PROF(1)  // state tile + action load
     const bool active = tid < n_valid;
     Ctx c;
-    c.st = s_st + tid; c.sg = s_sg + tid; c.tb = s_tb; c.L = &L; c.cfg = &cfg; c.env = e0 + tid;
+    c.st = s_st + tid; c.sg = s_sg + tid; c.tb = s_tb; c.L = &L; c.cfg = &cfg; c.env = e0 + tid; c.fx = s_fx;
 
     // ---- (1) game logic, phase 1: attacker move (or reset); one thread per env ----
     if (tid < CBX_TILE) {
@@ -151,6 +152,7 @@ __global__ void __launch_bounds__(CBX_THREADS, CBX_MIN_CTAS) cbx_step_kernel(con
     for (int k = 0; k < kGroups; ++k) { att_done_mask.w[k] = s_masks[0][k]; keep1.w[k] = s_masks[1][k]; }
     Tile t;
     t.L = &L; t.tb = s_tb; t.st = s_st; t.sg = s_sg; t.desc = s_desc; t.lut = s_lut; t.K = &p.enc; t.DW = DW;
+    t.fx = s_fx; t.init = s_init;
 
     // ---- (1b) terminal observations of the envs that finished (rare): encode BEFORE the auto-reset ----
     if (att_done_mask.any() && cfg.auto_reset && cfg.emit_terminal_obs && !reset_only) {

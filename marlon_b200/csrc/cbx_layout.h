@@ -63,6 +63,9 @@ struct cbx_layout {
   int o_gathered;     // ceil(nsecrets/32)
   int o_cached;       // ceil(ntriples/32): triple already in the cache
   int o_cache;        // 16 bits per cache slot: triple id
+  int o_fw;           // live defender binding only (else -1): 2 words per firewall rule-list group -- port names with a rule,
+                      // names whose first rule allows (cbx.h CBX_FX_*); part of the CyberBattleEnv's state (reset with it)
+  int n_fw_groups;
   int o_cyber_begin;  // words [o_cyber_begin, S) (+ parts of hdr / avail) belong to the CyberBattleEnv and are re-initialised
                       // by CyberBattleEnv.reset(); the words before it belong to the MARLon wrappers and the stale copy
   int S;              // words per env
@@ -149,7 +152,8 @@ struct cbx_params {
   int table_words;        // scenario blob words (multiple of 4; the largest blob of a multi-scenario batch, others are padded)
   int slice_of_kind[3];
   int n_scenarios;        // > 1: cbx_batch_create_multi -- envs grouped by scenario in whole tiles
-  int table_stride;       // words between the tables of consecutive scenarios (table_words + padded S)
+  int table_stride;       // words between the tables of consecutive scenarios (table_words + padded S + fwx_words)
+  int fwx_words;          // firewall extension tables staged behind the initial state (live defender binding; else 0)
   const int32_t* tile_scn;  // [n_tiles] scenario of each tile (NULL for a single scenario)
   const uint32_t* tables; // per scenario: blob followed by the S-word initial state
   uint32_t* state;

@@ -130,11 +130,24 @@ struct Tile {
   const uint2* lut;
   const cbx_enc_consts* K;
   int DW;
+  const uint32_t* fx = nullptr;    // live defender binding: firewall extension tables (cbx.h CBX_FX_*), else nullptr
+  const uint32_t* init = nullptr;  //   and the initial per-env state (what a defender observation shows right after its auto-reset)
   __device__ __forceinline__ uint32_t w(int e, int off) const { return st[off * CBX_TILE + e]; }
   __device__ __forceinline__ uint32_t g(int e, int off) const { return sg[off * CBX_TILE + e]; }
   __device__ __forceinline__ uint32_t d(int e, int k) const { return desc[e * DW + k]; }
   __device__ __forceinline__ uint32_t byte(int e, int off, int i) const { return (w(e, off + (i >> 2)) >> ((i & 3) * 8)) & 0xFFu; }
   __device__ __forceinline__ bool owned(int e, int s) const { return (d(e, D_OWNED + (s >> 5)) >> (s & 31)) & 1u; }
+  // DWR:506-517: does (node, direction) have a rule named `r` (one of the defender's six)?  Static per scenario under the
+  // reference's stale binding; under the live binding the env's own rule lists -- the initial ones when the defender's episode
+  // has just been auto-reset (D_FLAGS bit 0: the observation shows the fresh environment, DWR:477)
+  __device__ __forceinline__ uint32_t fw_rule_bit(int e, int node, int r, bool outgoing, int n_own) const {
+    if (node >= n_own) return 0u;
+    if (!fx) return (tb[tb[CBX_H_OFF_NODE] + node * CBX_NODE_WORDS + CBX_N_DEFOBS] >> ((outgoing ? 8 : 0) + r)) & 1u;
+    const uint32_t gw = fx[CBX_FX_WORDS + tb[CBX_H_N_PORTS] + node];
+    const int g = (int)(outgoing ? (gw >> 16) : (gw & 0xFFFFu));
+    const uint32_t present = (d(e, D_FLAGS) & 1u) ? init[L->o_fw + 2 * g] : w(e, L->o_fw + 2 * g);
+    return (present >> r) & 1u;
+  }
 };
 
 // generic writer for int32 fields: `wpe` words per env, f(e, wi) -> value
@@ -553,9 +566,8 @@ __device__ __forceinline__ void encode_defender_by_warp(const Tile& t, const Tar
 #pragma unroll
     for (int i = lane; i < 6 * n; i += 32) {
       const int node = i / 6, r = i - node * 6;
-      const uint32_t dob = node < n_own ? t.tb[t.tb[CBX_H_OFF_NODE] + node * CBX_NODE_WORDS + CBX_N_DEFOBS] : 0u;
-      o.fw_in[(size_t)e * 6 * n + i] = (int8_t)((dob >> r) & 1u);
-      o.fw_out[(size_t)e * 6 * n + i] = (int8_t)((dob >> (8 + r)) & 1u);
+      o.fw_in[(size_t)e * 6 * n + i] = (int8_t)t.fw_rule_bit(e, node, r, false, n_own);
+      o.fw_out[(size_t)e * 6 * n + i] = (int8_t)t.fw_rule_bit(e, node, r, true, n_own);
     }
 #pragma unroll
     for (int i = lane; i < nsvc; i += 32) o.services[(size_t)e * nsvc + i] = (int8_t)(i < nsvc_own);
@@ -615,13 +627,13 @@ __device__ __forceinline__ void encode_defender(const Tile& t, const Target& o, 
            [&](int e, int i) -> uint32_t { return (t.d(e, D_OWNED + L->OW + (i >> 5)) >> (i & 31)) & 1u; });
   if (!static_too) return;
   const int n_own = (int)t.tb[CBX_H_N_NODES], nsvc_own = (int)t.tb[CBX_H_N_SERVICES];
-  write_i8(o.fw_in, 6 * L->n, K.d_6n, n_valid, enc_mask, [&](int, int i) -> uint32_t {
+  write_i8(o.fw_in, 6 * L->n, K.d_6n, n_valid, enc_mask, [&](int e, int i) -> uint32_t {
     int node = i / 6, r = i - node * 6;
-    return node < n_own ? (t.tb[t.tb[CBX_H_OFF_NODE] + node * CBX_NODE_WORDS + CBX_N_DEFOBS] >> r) & 1u : 0u;
+    return t.fw_rule_bit(e, node, r, false, n_own);
   });
-  write_i8(o.fw_out, 6 * L->n, K.d_6n, n_valid, enc_mask, [&](int, int i) -> uint32_t {
+  write_i8(o.fw_out, 6 * L->n, K.d_6n, n_valid, enc_mask, [&](int e, int i) -> uint32_t {
     int node = i / 6, r = i - node * 6;
-    return node < n_own ? (t.tb[t.tb[CBX_H_OFF_NODE] + node * CBX_NODE_WORDS + CBX_N_DEFOBS] >> (8 + r)) & 1u : 0u;
+    return t.fw_rule_bit(e, node, r, true, n_own);
   });
   write_i8(o.services, L->nservices, K.d_svc, n_valid, enc_mask, [&](int, int i) -> uint32_t { return i < nsvc_own ? 1u : 0u; });
 }
@@ -718,6 +730,7 @@ static __device__ void build_desc(const Ctx& c, uint32_t* d, int DW, const uint3
     }
   }
   for (int k = 0; k < L->Wn; ++k) d[D_OWNED + L->OW + k] = def_inst_override ? def_inst_override[k] : c.w(L->o_installed + k);
+  if (def_inst_override) d[D_FLAGS] |= 1u;  // the defender's observation shows the fresh environment (firewall rows too, live binding)
   (void)DW;
 }
 
@@ -812,8 +825,21 @@ static __device__ void defender_wrapper_step(const Ctx& c, const cbx_params& p, 
   const bool valid = empty ? true : c.defender_action_valid(da);
   if (!valid) { c.w(L->o_def_invalid) += 1; reward += cfg->def_invalid_action_reward; }
   else c.w(L->o_def_valid) += 1;
-  int down = c.tick(L->o_cd_shadow, -1);  // on_attacker_step_taken() of the stale actuator: availability BEFORE the action
-  if (valid && !empty && da[0] == 0) c.setbyte(L->o_cd_shadow, da[1], 16);
+  int down;
+  if (c.fx) {
+    // LIVE binding: LearningDefender.executeAction on the environment the attacker plays in (LDF:31-107).  First
+    // on_attacker_step_taken() of the live actuator -- the only place it ticks in MARLon, CyberBattleEnv.step calls it only for
+    // a built-in defender agent (ENV:1156-1158) -- so availability is the one BEFORE this action
+    down = c.tick(L->o_cd_live, L->o_notrunning);
+    if (valid && !empty) {
+      if (da[0] == 0) c.reimage_live(da[1]);                       // ACT:700-712 on the live env
+      else if (da[0] == 1) c.fw_block(da[2], da[4] != 0, da[3]);  // LDF:50-58
+      else if (da[0] == 2) c.fw_allow(da[5], da[7] != 0, da[6]);  // LDF:60-69 (stop / start service: no-ops)
+    }
+  } else {
+    down = c.tick(L->o_cd_shadow, -1);  // on_attacker_step_taken() of the stale actuator: availability BEFORE the action
+    if (valid && !empty && da[0] == 0) c.setbyte(L->o_cd_shadow, da[1], 16);
+  }
   uint32_t a = c.w(L->o_avail);
   const int prev_down = (int)((a >> 16) & 0xFFu);
   const double cur = c.availability(down), prev = c.availability(prev_down);
@@ -827,7 +853,8 @@ static __device__ void defender_wrapper_step(const Ctx& c, const cbx_params& p, 
       acc.v[CBX_STAT_SLA_BREACHES] += 1;
     } else if (worsening > 0) reward += -cfg->def_sla_worsening_penalty_scale * worsening;
   } else c.setflag(HDR_BREACHED, false);
-  c.w(L->o_avail) = (a & 0xFFu) | ((uint32_t)down << 8) | ((uint32_t)down << 16);
+  // bits 0-7: the live env's count at its last tick (info["network_availability"]) -- under the live binding that is this tick
+  c.w(L->o_avail) = (c.fx ? (uint32_t)down : (a & 0xFFu)) | ((uint32_t)down << 8) | ((uint32_t)down << 16);
   if (c.defender_goal_reached()) { reward = cfg->winning_reward; term = 1; }
   c.w(L->o_def_ts) += 1;
   if (c.flag(HDR_DEF_RR)) { trunc = 1; reward = -1.0 * (double)c.f32(L->o_last_att); }

@@ -25,7 +25,7 @@ from __future__ import annotations
 
 import struct
 from dataclasses import dataclass
-from typing import Any, Dict, List, Tuple
+from typing import Optional, Any, Dict, List, Tuple
 
 import numpy as np
 
@@ -108,6 +108,7 @@ class CompiledScenario:
     services_per_node: List[int]
     max_leak: int
     alias_groups: Dict[str, List[Tuple[str, str]]]
+    fw_ext: Optional[np.ndarray] = None  # firewall extension tables for the `live` defender binding (FWX_* layout below)
 
     @property
     def n_nodes(self) -> int:
@@ -123,6 +124,12 @@ class CompiledScenario:
         import hashlib
 
         return hashlib.sha256(self.tobytes()).hexdigest()
+
+    def fw_fingerprint(self) -> str:
+        """Of the firewall extension tables (alias groups, rule lists as the `live` binding sees them)."""
+        import hashlib
+
+        return hashlib.sha256(np.asarray(self.fw_ext, dtype="<u4").tobytes()).hexdigest()
 
 
 def compile_scenario(env) -> CompiledScenario:
@@ -293,6 +300,8 @@ def compile_scenario(env) -> CompiledScenario:
             g = seen.setdefault(id(lst), f"g{len(seen)}")
             alias_groups.setdefault(g, []).append((k, direction))
 
+    fw_ext = _firewall_extension(node_ids, infos, ports, alias_groups)
+
     # ---- assemble
     sections = [node_tab.ravel(), auth.ravel(), vuln_tab.ravel(),
                 np.asarray(payload if payload else [0], dtype=np.uint32), triple_tab.ravel()]
@@ -323,4 +332,49 @@ def compile_scenario(env) -> CompiledScenario:
         inv_triples[i] = t
     return CompiledScenario(blob=blob, node_ids=node_ids, identifiers=ident, secrets=inv_secrets, triples=inv_triples,
                             n_services=svc_off, services_per_node=services_per_node, max_leak=max_leak,
-                            alias_groups=alias_groups)
+                            alias_groups=alias_groups, fw_ext=fw_ext)
+
+
+# ---- firewall extension tables (`live` defender binding) -------------------------------------------------
+# Under the live binding the LearningDefender edits the firewall rule LISTS of the environment the attacker plays in
+# (marlon/defender_agents/defender.py:50-69), and several (node, direction) pairs share one list object (toy_ctf.py:14-19,
+# chainpattern.py:48-53; deepcopy keeps the sharing), so the unit of state is the list = alias group.  What the path ever asks of
+# a list is, per port NAME: is there a rule for it (defend_wrapper.py:360-372, :506-517) and does the first one ALLOW
+# (actions.py:504-515); block removes every rule of a name, allow appends an ALLOW rule only where none exists -- so two bits
+# per (group, name) carry the whole list.  Names: the defender's six first (its actions index them), then the attacker's ports.
+# Layout (uint32 words): [0] magic "CBXF"  [1] names  [2] groups  [3] 0
+#   [4, 4 + P)           name index of every attacker port
+#   [.., + n)            per node: incoming group | outgoing group << 16
+#   [.., + 2 * groups)   per group: names present, names whose first rule allows      (the initial per-env state)
+FWX_MAGIC = 0x46584243
+
+
+def _firewall_extension(node_ids, infos, ports, alias_groups) -> np.ndarray:
+    names = list(DEFENDER_FIREWALL_RULE_LIST) + [p for p in ports if p not in DEFENDER_FIREWALL_RULE_LIST]
+    if len(names) > 32:
+        raise UnsupportedScenario("more than 32 firewall port names")
+    group_ids = list(alias_groups)
+    group_of = {}
+    for g, members in alias_groups.items():
+        for node, direction in members:
+            group_of[(node, direction)] = group_ids.index(g)
+    if len(group_ids) > 0xFFFF:
+        raise UnsupportedScenario("too many firewall rule lists")
+    node_words = [group_of[(k, "incoming")] | (group_of[(k, "outgoing")] << 16) for k in node_ids]
+    init = []
+    by_node = dict(zip(node_ids, infos))
+    for g in group_ids:
+        node, direction = alias_groups[g][0]
+        rules = getattr(by_node[node].firewall, direction)
+        present = allow = 0
+        for i, nm in enumerate(names):
+            if any(r.port == nm for r in rules):
+                present |= 1 << i
+                if _passes(rules, nm):
+                    allow |= 1 << i
+        init += [present, allow]
+    words = [FWX_MAGIC, len(names), len(group_ids), 0] + [names.index(p) for p in ports] + node_words + init
+    while len(words) % 4:
+        words.append(0)
+    return np.asarray(words, dtype=np.uint32)
+

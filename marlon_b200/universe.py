@@ -78,9 +78,11 @@ class MultiAgentUniversalEnv:
         (configs[4]); `n_envs` is then the env count per network (an int, or one count per seed; every count but the last a
         multiple of 32).  Node / credential / service counts differ between networks: the observation spaces are those of the
         bounds and of the largest network, smaller ones are zero-padded."""
-        if defender_binding != "reference_stale":
-            raise NotImplementedError("only the reference's stale defender binding is on the batched path (SURVEY.md B.1); "
-                                      "the 'live' semantics are a later row of the scope table (8f.4)")
+        if defender_binding not in ("reference_stale", "live"):
+            raise ValueError("defender_binding: 'reference_stale' (the reference as executed: the LearningDefender acts on a dead copy "
+                             "of the environment, SURVEY.md B.1; default) or 'live' (its binding refreshed at every reset)")
+        if defender_binding == "live" and scenario_seeds is not None:
+            raise NotImplementedError("the live defender binding is single-scenario")
         del attacker_invalid_action_reward_multiplier, attacker_loss_reward  # stored but unused by the reference (attack_wrapper.py:51-52)
         kw = dict(env_kwargs)
         for k, v in (("maximum_node_count", maximum_node_count), ("maximum_total_credentials", maximum_total_credentials),
@@ -111,7 +113,7 @@ class MultiAgentUniversalEnv:
             action_kind_order=action_kind_order, defender_enabled=defender, defender_max_timesteps=max_timesteps,
             defender_invalid_action_reward=defender_invalid_action_reward_modifier,
             defender_reset_on_constraint_broken=defender_reset_on_constraint_broken, defender_loss_reward=defender_loss_reward,
-            auto_reset=True, mask_mode=_abi.MASK_DENSE if mask_mode == "dense" else _abi.MASK_FACTORED,
+            defender_binding=defender_binding, auto_reset=True, mask_mode=_abi.MASK_DENSE if mask_mode == "dense" else _abi.MASK_FACTORED,
             emit_terminal_obs=emit_terminal_obs, seed=seed, env_index_base=env_index_base, **merged)
         from .batch import Batch
 

@@ -110,6 +110,9 @@ typedef struct {
   int stepcount, done;
   double episode_reward_sum; /* numpy.sum(__episode_rewards) */
   double availability;      /* live DefenderAgentActions.network_availability */
+  /* LIVE defender binding: model.FirewallConfiguration rule lists as the LearningDefender edits them (LDF:50-69), one list
+     object per alias group (several (node, direction) pairs may share one); a rule = (port-name index, ALLOW?) */
+  struct fwlist { int n; uint8_t name[96]; uint8_t allow[96]; } * fw;
   /* the stale copy the MARLon defender acts on: initial environment + its own actuator */
   uint8_t* sh_running;
   int* sh_progress;
@@ -134,7 +137,37 @@ typedef struct orc_batch {
   cbx_views v; /* HOST pointers */
   double stats[CBX_STAT_COUNT];
   int slice_of_kind[3]; /* column where kind k's coordinates start inside the MARLon MultiDiscrete action */
+  /* firewall extension tables (cbx.h CBX_FX_*), NULL unless given; `live` = cfg.def_binding == LIVE with a MARLon defender */
+  uint32_t* fwx;
+  int live, n_fw_groups;
 } orc_batch;
+
+/* ---- firewall rule lists (live binding) ---- */
+static int fw_group_of(const orc_batch* b, int node, int incoming) {
+  uint32_t g = b->fwx[CBX_FX_WORDS + b->s.P + node];
+  return incoming ? (int)(g & 0xFFFFu) : (int)(g >> 16);
+}
+/* ACT:504-515 __is_passing_firewall_rules: the first rule of that port name decides; no rule -> blocked */
+static int fw_list_passes(const struct fwlist* l, int name) {
+  for (int k = 0; k < l->n; ++k)
+    if (l->name[k] == name) return l->allow[k];
+  return 0;
+}
+static int fw_list_has(const struct fwlist* l, int name) {
+  for (int k = 0; k < l->n; ++k)
+    if (l->name[k] == name) return 1;
+  return 0;
+}
+static void fw_lists_init(const orc_batch* b, oenv_t* e) {
+  const uint32_t* g0 = b->fwx + CBX_FX_WORDS + b->s.P + b->s.n;
+  const int names = (int)b->fwx[CBX_FX_N_NAMES];
+  for (int g = 0; g < b->n_fw_groups; ++g) {
+    struct fwlist* l = &e->fw[g];
+    l->n = 0;
+    for (int nm = 0; nm < names; ++nm)
+      if (g0[2 * g] >> nm & 1u) { l->name[l->n] = (uint8_t)nm; l->allow[l->n] = (uint8_t)(g0[2 * g + 1] >> nm & 1u); l->n++; }
+  }
+}
 
 static int64_t now(oenv_t* e) { return ++e->clock; }
 
@@ -369,8 +402,14 @@ static result_t connect_to_remote(orc_batch* b, oenv_t* e, int src, int tgt, int
   if (!e->nodes[src].agent_installed) return invalid_action(b, CBX_E_SOURCE_NOT_OWNED);
   if (!e->nodes[tgt].tracked) return invalid_action(b, CBX_E_TARGET_NOT_DISCOVERED);
   if (!e->gathered[secret]) return invalid_action(b, CBX_E_CREDENTIAL_NOT_GATHERED);
-  if (!(scn_node(s, src)[CBX_N_FW_OUT] >> port & 1)) { r.reward = -10.0; return r; }
-  if (!(scn_node(s, tgt)[CBX_N_FW_IN] >> port & 1)) { r.reward = -10.0; return r; }
+  if (b->live) {
+    const int name = (int)b->fwx[CBX_FX_WORDS + port];
+    if (!fw_list_passes(&e->fw[fw_group_of(b, src, 0)], name)) { r.reward = -10.0; return r; }
+    if (!fw_list_passes(&e->fw[fw_group_of(b, tgt, 1)], name)) { r.reward = -10.0; return r; }
+  } else {
+    if (!(scn_node(s, src)[CBX_N_FW_OUT] >> port & 1)) { r.reward = -10.0; return r; }
+    if (!(scn_node(s, tgt)[CBX_N_FW_IN] >> port & 1)) { r.reward = -10.0; return r; }
+  }
   if (!(scn_node(s, tgt)[CBX_N_LISTEN] >> port & 1)) { r.reward = -10.0; return r; }
   if (!e->nodes[tgt].running) { r.reward = 0.0; return r; }
   const uint32_t* auth = s->auth + ((size_t)tgt * s->P + port) * s->Ws;
@@ -487,6 +526,10 @@ static void cyber_reset(orc_batch* b, oenv_t* e, obs_t* o) {
   e->done = 0;
   e->episode_reward_sum = 0;
   e->availability = 1.0;
+  if (b->live) {
+    fw_lists_init(b, e);      /* deepcopy of the initial environment: its rule lists, sharing preserved */
+    e->sh_availability = 1.0; /* the defender wrapper's actuator IS the fresh live one */
+  }
   /* AgentActions.__init__ (ACT:149-152): owned nodes are marked owned (LocalUser) */
   for (int i = 0; i < s->n; ++i)
     if (e->nodes[i].agent_installed) { int64_t last; mark_node_as_owned(s, e, i, 1, &last); }
@@ -612,7 +655,12 @@ static void defender_observe(orc_batch* b, oenv_t* e, int64_t i, int term) { /* 
   int8_t* svc = b->v.def_services_status + i * s->nservices;
   for (int k = 0; k < s->n; ++k) {
     uint32_t d = scn_node(s, k)[CBX_N_DEFOBS];
-    for (int r = 0; r < 6; ++r) { fin[6 * k + r] = d >> r & 1; fout[6 * k + r] = d >> (8 + r) & 1; }
+    for (int r = 0; r < 6; ++r) {
+      if (b->live) { /* DWR:506-517 on the env's own lists */
+        fin[6 * k + r] = (int8_t)fw_list_has(&e->fw[fw_group_of(b, k, 1)], r);
+        fout[6 * k + r] = (int8_t)fw_list_has(&e->fw[fw_group_of(b, k, 0)], r);
+      } else { fin[6 * k + r] = d >> r & 1; fout[6 * k + r] = d >> (8 + r) & 1; }
+    }
   }
   for (int k = 0; k < s->nservices; ++k) svc[k] = 1;
 }
@@ -681,7 +729,10 @@ static int defender_action_valid(const orc_batch* b, const oenv_t* e, const int3
 #define NODE_OK(x) ((x) >= 0 && (x) < s->n && e->nodes[(x)].running)
   switch (a[0]) {
     case 0: return NODE_OK(a[1]) && (scn_node(s, a[1])[CBX_N_FLAGS] & 1u);
-    case 1: return NODE_OK(a[2]) && a[3] >= 0 && a[3] < 6 && (scn_node(s, a[2])[CBX_N_DEFOBS] >> ((a[4] ? 0 : 8) + a[3]) & 1u);
+    case 1:
+      if (!(NODE_OK(a[2]) && a[3] >= 0 && a[3] < 6)) return 0;
+      if (b->live) return fw_list_has(&e->fw[fw_group_of(b, a[2], a[4] != 0)], a[3]);
+      return (scn_node(s, a[2])[CBX_N_DEFOBS] >> ((a[4] ? 0 : 8) + a[3]) & 1u);
     case 2: return NODE_OK(a[5]);
     case 3: return NODE_OK(a[8]) && a[9] >= 0 && a[9] < (int)(scn_node(s, a[8])[CBX_N_FLAGS] >> 8 & 0xFF);
     case 4: return NODE_OK(a[10]) && a[11] >= 0 && a[11] < (int)(scn_node(s, a[10])[CBX_N_FLAGS] >> 8 & 0xFF);
@@ -783,10 +834,33 @@ static void defender_half_step(orc_batch* b, int64_t i, const int32_t* da) {
   int valid = empty ? 1 : defender_action_valid(b, e, da);
   if (!valid) { e->def_invalid += 1; dreward += c->def_invalid_action_reward; }
   else e->def_valid += 1;
-  /* LearningDefender.executeAction on the STALE copy, LDF:31-107 */
-  e->sh_availability = tick_and_availability(b->s.n, e->sh_running, e->sh_progress, sizeof(uint8_t), sizeof(int), &b->s);
-  if (valid && !empty && da[0] == 0) { e->sh_progress[da[1]] = 15; e->sh_running[da[1]] = 0; }
-  double cur = e->sh_availability;
+  double cur;
+  if (b->live) {
+    /* LearningDefender.executeAction on the LIVE environment (binding refreshed at every CyberBattleEnv.reset), LDF:31-107 */
+    e->availability = tick_and_availability(b->s.n, &e->nodes[0].running, &e->nodes[0].progress, sizeof(onode_t), sizeof(onode_t), &b->s);
+    if (valid && !empty) {
+      if (da[0] == 0) reimage_node_live(e, da[1]);
+      else if (da[0] == 1) { /* block_traffic: every rule of that name leaves the selected list */
+        struct fwlist* l = &e->fw[fw_group_of(b, da[2], da[4] != 0)];
+        int m = 0;
+        for (int k = 0; k < l->n; ++k)
+          if (l->name[k] != da[3]) { l->name[m] = l->name[k]; l->allow[m] = l->allow[k]; m++; }
+        l->n = m;
+      } else if (da[0] == 2) { /* allow_traffic: no rule of that name in the selected list -> append ALLOW to INCOMING */
+        if (!fw_list_has(&e->fw[fw_group_of(b, da[5], da[7] != 0)], da[6])) {
+          struct fwlist* l = &e->fw[fw_group_of(b, da[5], 1)];
+          if (l->n < 96) { l->name[l->n] = (uint8_t)da[6]; l->allow[l->n] = 1; l->n++; }
+        }
+      } /* stop / start service: DefenderAgentActions compares a ListeningService object with a name, never equal (B.4) */
+    }
+    cur = e->availability;
+    e->sh_availability = cur; /* the wrapper's _actuator IS the live one */
+  } else {
+    /* LearningDefender.executeAction on the STALE copy, LDF:31-107 */
+    e->sh_availability = tick_and_availability(b->s.n, e->sh_running, e->sh_progress, sizeof(uint8_t), sizeof(int), &b->s);
+    if (valid && !empty && da[0] == 0) { e->sh_progress[da[1]] = 15; e->sh_running[da[1]] = 0; }
+    cur = e->sh_availability;
+  }
   double worsening = e->prev_availability - cur;
   if (e->n_cyber_rewards > 0) dreward += -1.0 * e->last_cyber_reward;
   if (cur < c->maintain_sla) {
@@ -939,13 +1013,30 @@ orc_batch* orc_create(const uint32_t* blob, size_t nwords, const cbx_config* cfg
   return b;
 }
 
+/* Firewall extension tables (marlon_b200/scenario.py FWX layout): call right after orc_create, before the first reset.  Turns
+ * the live defender binding on when the config asks for it. */
+int orc_set_firewall_tables(orc_batch* b, const uint32_t* words, size_t nwords) {
+  if (!b || !words || nwords < CBX_FX_WORDS || words[CBX_FX_MAGIC] != CBX_FWX_MAGIC) return -1;
+  b->fwx = (uint32_t*)zalloc(nwords * 4);
+  memcpy(b->fwx, words, nwords * 4);
+  b->n_fw_groups = (int)words[CBX_FX_N_GROUPS];
+  b->live = b->cfg.mode == CBX_MODE_MARLON && b->cfg.def_enabled && b->cfg.def_binding == CBX_DEF_BINDING_LIVE;
+  for (int64_t i = 0; i < b->n; ++i) {
+    free(b->envs[i].fw);
+    b->envs[i].fw = (struct fwlist*)zalloc(sizeof(struct fwlist) * (size_t)b->n_fw_groups);
+    if (b->live) fw_lists_init(b, &b->envs[i]);
+  }
+  return 0;
+}
+
 void orc_destroy(orc_batch* b) {
   if (!b) return;
   for (int64_t i = 0; i < b->n; ++i) {
     oenv_t* e = &b->envs[i];
     free(e->nodes); free(e->actuator_order); free(e->discovered); free(e->cache); free(e->gathered);
-    free(e->sh_running); free(e->sh_progress);
+    free(e->sh_running); free(e->sh_progress); free(e->fw);
   }
+  free(b->fwx);
   cbx_views* v = &b->v;
   void* ptrs[] = {v->scalars, v->leaked_credentials, v->credential_cache_matrix, v->discovered_nodes_properties,
                   v->nodes_privilegelevel, v->local_vulnerability, v->remote_vulnerability, v->connect, v->owned_bits,
@@ -1131,7 +1222,10 @@ void orc_export_state(orc_batch* b, int64_t begin, int64_t end, int32_t* out) {
     p += n;
     for (int k = 0; k < n; ++k) p[k] = e->nodes[k].progress < 0 ? 0 : e->nodes[k].progress + 1;
     p += n;
-    for (int k = 0; k < n; ++k) p[k] = e->sh_progress[k] < 0 ? 0 : e->sh_progress[k] + 1;
+    for (int k = 0; k < n; ++k) {
+      const int pr = b->live ? e->nodes[k].progress : e->sh_progress[k]; /* the actuator the defender's wrapper is bound to */
+      p[k] = pr < 0 ? 0 : pr + 1;
+    }
     p += n;
     for (int k = 0; k < n; ++k) p[k] = e->nodes[k].tracked && e->nodes[k].last_owned_at != 0;
     p += n;

@@ -363,9 +363,13 @@ def record_raw(name, env_id, env_kwargs, n_tapes, steps, seed, p_valid=0.5, scri
 
 # ---- MARLon attacker+defender tapes ------------------------------------------------------------------------
 def record_marlon(name, env_id, env_kwargs, att_kwargs, def_kwargs, n_tapes, steps, seed, with_defender=True,
-                  p_att_valid=0.0, p_def_empty=0.0, factory=None, meta_kwargs=None, masked=False):
+                  p_att_valid=0.0, p_def_empty=0.0, factory=None, meta_kwargs=None, masked=False, live=False):
     """`masked`: the attacker is driven through the reference's MaskedDiscreteAttackerWrapper (action_masking.py:30-165): per step
-    its action_masks() (CRC + count) and the Discrete action fed to its step() are recorded next to the MultiDiscrete encoding."""
+    its action_masks() (CRC + count) and the Discrete action fed to its step() are recorded next to the MultiDiscrete encoding.
+    `live`: the LIVE defender binding -- after every CyberBattleEnv.reset() the DefenderEnvWrapper's and the LearningDefender's
+    cached actuator / environment (defend_wrapper.py:51, defender.py:29-30) are pointed at the objects that reset just created,
+    so the defender acts on the environment the attacker plays in.  No reference file is modified: the instance's `reset` is
+    wrapped."""
     rec = Recorder()
     units = []
     for t in range(n_tapes):
@@ -373,6 +377,16 @@ def record_marlon(name, env_id, env_kwargs, att_kwargs, def_kwargs, n_tapes, ste
         es = EnvironmentEventSource()
         att = AttackerEnvWrapper(env, es, **att_kwargs)
         dfn = DefenderEnvWrapper(env, att, es, defender=True, **def_kwargs) if with_defender else None
+        if live:
+            def _rebinding_reset(*a, _orig=env.reset, _env=env, _dfn=dfn, **k):
+                out = _orig(*a, **k)
+                base = _env.unwrapped
+                _dfn._actuator = base._defender_actuator
+                _dfn.defender._actuator = base._defender_actuator
+                _dfn.defender._environment = base.environment
+                return out
+
+            env.reset = _rebinding_reset
         # SB3 learn() resets every env once before the first step: attacker first, then defender
         aobs, _ = att.reset()
         dobs = dfn.reset()[0] if dfn else None
@@ -469,7 +483,8 @@ def record_marlon(name, env_id, env_kwargs, att_kwargs, def_kwargs, n_tapes, ste
     meta = dict(kind="marlon", env_id=env_id, env_kwargs=env_kwargs_meta(dict(env_kwargs, **(meta_kwargs or {}))), att_kwargs=att_kwargs,
                 def_kwargs=def_kwargs, with_defender=with_defender, n_tapes=n_tapes, steps=steps, N=N, C=C, LEAK=LEAK,
                 fingerprint=comp.fingerprint(), node_ids=comp.node_ids, kind_of_index=kind_of_index,
-                att_nvec=att_nvec, def_nvec=def_nvec)
+                att_nvec=att_nvec, def_nvec=def_nvec, defender_binding="live" if live else "reference_stale",
+                fw_fingerprint=comp.fw_fingerprint())
     save(name, meta, rec)
 
 
@@ -720,6 +735,27 @@ def main_round2(only_masked=False):
     record_raw("raw_chain100_scan", "CyberBattleChain-v0", c100s, 2, 300, seed=9100, p_valid=0.95)
 
 
+def main_live():
+    """Tapes of the LIVE defender binding: the reference's own DefenderEnvWrapper / LearningDefender
+    classes with their binding refreshed at every reset, so re-imaging, block_traffic and allow_traffic act on the environment
+    the attacker plays in -- rule lists shared between nodes included (toy_ctf.py:14-19)."""
+    DC = ref_env.DefenderConstraint
+    t1 = dict(maximum_node_count=12, maximum_total_credentials=10, maximum_discoverable_credentials_per_action=5,
+              throws_on_invalid_actions=False, defender_constraint=DC(maintain_sla=0.60), losing_reward=-5000.0)
+    akw = dict(max_timesteps=90, invalid_action_reward_modifier=-1.0, invalid_action_reward_multiplier=1.0, loss_reward=-5000.0)
+    dkw = dict(max_timesteps=70, invalid_action_reward=-1, reset_on_constraint_broken=True, loss_reward=-5000.0)
+    record_marlon("marlon_toyctf_live", "CyberBattleToyCtf-v0", t1, akw, dkw, 8, 700, seed=9500, p_att_valid=0.85, p_def_empty=0.35,
+                  live=True)
+    # SLA breaches do not end the episode here, so long stretches with several nodes re-imaging and many firewall edits occur
+    dkw2 = dict(dkw, max_timesteps=200, reset_on_constraint_broken=False)
+    record_marlon("marlon_toyctf_live_long", "CyberBattleToyCtf-v0", t1, dict(akw, max_timesteps=200), dkw2, 4, 700, seed=9600,
+                  p_att_valid=0.9, p_def_empty=0.2, live=True)
+    c1 = dict(size=10, maximum_node_count=12, maximum_total_credentials=12, throws_on_invalid_actions=False,
+              defender_constraint=DC(maintain_sla=0.60), losing_reward=-5000.0)
+    record_marlon("marlon_chain10_live", "CyberBattleChain-v0", c1, akw, dkw, 6, 600, seed=9700, p_att_valid=0.9, p_def_empty=0.5,
+                  live=True)
+
+
 if __name__ == "__main__":
     if "--random" in sys.argv:
         main_random()
@@ -727,5 +763,7 @@ if __name__ == "__main__":
         main_round2()
     elif "--masked" in sys.argv:
         main_round2(only_masked=True)
+    elif "--live" in sys.argv:
+        main_live()
     else:
         main()

@@ -45,6 +45,7 @@ def lib():
         L.orc_export_words.argtypes = [C.c_void_p]
         L.orc_export_state.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
         L.orc_philox.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_set_firewall_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.orc_sample_actions.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32]
         for f in (L.orc_l1_local, L.orc_l1_remote, L.orc_l1_connect):
             f.restype = C.c_double
@@ -75,6 +76,10 @@ class OracleBatch:
         self._h = self._lib.orc_create(blob.ctypes.data, blob.size, C.byref(cfg), self.n_envs)
         if not self._h:
             raise ValueError("oracle rejected the scenario/config (node count > maximum_node_count or credentials > maximum_total_credentials?)")
+        if getattr(compiled, "fw_ext", None) is not None:  # rule-list alias groups (the `live` defender binding edits them)
+            ext = np.ascontiguousarray(compiled.fw_ext, dtype=np.uint32)
+            if self._lib.orc_set_firewall_tables(self._h, ext.ctypes.data, ext.size):
+                raise ValueError("oracle rejected the firewall tables")
         v = _abi.Views()
         self._lib.orc_views(self._h, C.byref(v))
         self.views = v

@@ -74,7 +74,10 @@ def config_from_meta(meta, **overrides):
             defender_reset_on_constraint_broken=d.get("reset_on_constraint_broken", True),
             defender_loss_reward=d.get("loss_reward", -5000.0),
             defender_sla_worsening_penalty_scale=d.get("sla_worsening_penalty_scale", 200.0),
+            defender_binding=meta.get("defender_binding", "reference_stale"),
             **env_kw, **overrides)
+        if meta.get("fw_fingerprint"):
+            assert comp.fw_fingerprint() == meta["fw_fingerprint"], "firewall rule-list groups differ from the ones the tape was recorded on"
     return comp, cfg
 
 

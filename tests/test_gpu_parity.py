@@ -246,6 +246,29 @@ def test_device_sampler_equals_oracle_sampler(mode):
     b.close()
 
 
+@pytest.mark.parametrize("scn", ["toyctf", "chain10"])
+def test_live_defender_binding_vs_oracle(scn):
+    """the LIVE LearningDefender binding -- re-imaging, block_traffic and allow_traffic act on the environment
+    the attacker plays in; firewall rule lists are per-env state, one per alias group.  The oracle's version (explicit rule
+    lists) is pinned on tapes recorded from the reference's classes with their binding refreshed at every reset
+    (tests/golden/marlon_*_live*.npz); here the CUDA version (two bits per group and port name) against it at scale."""
+    if scn == "toyctf":
+        comp = scenario.compile_scenario(scenarios.toyctf_environment())
+        cfg = _toyctf_pair_cfg(defender_binding="live", attacker_max_timesteps=70, defender_max_timesteps=55, emit_terminal_obs=True)
+    else:
+        comp = scenario.compile_scenario(scenarios.chain_environment(10))
+        cfg = config.make_config(_abi.MODE_MARLON, maximum_node_count=12, maximum_total_credentials=12, throws_on_invalid_actions=False,
+                                 defender_constraint=config.DefenderConstraint(0.60), losing_reward=-5000.0, defender_enabled=True,
+                                 defender_max_timesteps=90, attacker_max_timesteps=120, defender_invalid_action_reward=-1,
+                                 defender_reset_on_constraint_broken=False, defender_binding="live", emit_terminal_obs=True)
+    from marlon_b200.batch import Batch
+
+    b = Batch(comp, cfg, 32)
+    assert b.kernel_info()["name"] == "cbx_step_kernel"  # per-env firewall rows: the fused kernel
+    b.close()
+    _run_against_oracle(comp, cfg, 2051, 260, seed=61, check_every=7, reset_at=100)
+
+
 def test_chain10_attacker_only_4096_envs_vs_oracle():
     """BASELINE.json configs[1]: CyberBattleChain-10 attacker-only, 4096 batched envs, bit-exact."""
     comp = scenario.compile_scenario(scenarios.chain_environment(10))
