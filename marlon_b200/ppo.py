@@ -91,8 +91,8 @@ class MultiDiscretePolicy(nn.Module):
         """-> (values, log_prob, entropy) of `actions` under the current policy (SB3 ``ActorCriticPolicy.evaluate_actions``)."""
         logp, values = self._log_probs(obs)
         chosen = logp.gather(2, actions.long().unsqueeze(2)).squeeze(2).sum(1)
-        p = torch.exp(logp)
-        entropy = -(torch.where(self._valid, p * logp, torch.zeros_like(p))).sum((1, 2))
+        safe = logp.masked_fill(~self._valid, 0.0)  # not where(valid, p * logp, 0): 0 * -inf poisons the gradient
+        entropy = -(torch.exp(safe) * safe).masked_fill(~self._valid, 0.0).sum((1, 2))
         return values, chosen, entropy
 
 

@@ -5,6 +5,8 @@ import torch, bench
 from marlon_b200.batch import Batch
 comp, cfg = bench.workload_config(workload=os.environ.get("WORKLOAD", "toyctf"))
 n = int(os.environ.get("ENVS", 65536))
+if isinstance(comp, list):  # multi-scenario workload: envs per scenario
+    n = [n // len(comp)] * len(comp)
 b = Batch(comp, cfg, n); b.reset()
 acts = []
 for s in range(25):

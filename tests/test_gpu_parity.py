@@ -40,7 +40,7 @@ def _compare_all(b, o, step, names=None):
 
 
 def _run_against_oracle(comp, cfg, n, steps, seed, uniform_every=3, check_every=8, tape_rng=None, expect_order=None, i16=False,
-                        reset_at=None):
+                        reset_at=None, stats_rtol=1e-9):
     """`expect_order`: the tile order the batch must be running ("dynamic" / "static"); the ticket counter must then be back at
     zero after every launch.  `i16`: int16 device actions (bulk action loads of half the size).  `reset_at`: a masked explicit
     reset of half the envs after that step, followed by more steps."""
@@ -102,7 +102,7 @@ def _run_against_oracle(comp, cfg, n, steps, seed, uniform_every=3, check_every=
             _compare_all(b, o, s)
         if s % check_every == 0 or s == steps - 1:
             _compare_all(b, o, s)
-    assert np.allclose(b.stats(), o.stats, rtol=1e-9, atol=1e-6), (b.stats(), o.stats)
+    assert np.allclose(b.stats(), o.stats, rtol=stats_rtol, atol=1e-6), (b.stats(), o.stats)
     assert b.stats()[_abi.STAT_ENV_STEPS] == n * steps
     b.close()
 
@@ -266,7 +266,9 @@ def test_live_defender_binding_vs_oracle(scn):
     b = Batch(comp, cfg, 32)
     assert b.kernel_info()["name"] == "cbx_step_kernel"  # per-env firewall rows: the fused kernel
     b.close()
-    _run_against_oracle(comp, cfg, 2051, 260, seed=61, check_every=7, reset_at=100)
+    # Chain-10 here keeps playing after an SLA breach: the worsening penalty -200 * k / 12 is not a whole number, and the running
+    # returns are fp32 on the device (fp64 in the oracle): per-step rewards agree to 1e-6 relative, sums of returns likewise
+    _run_against_oracle(comp, cfg, 2051, 260, seed=61, check_every=7, reset_at=100, stats_rtol=1e-6)
 
 
 def test_chain10_attacker_only_4096_envs_vs_oracle():

@@ -25,6 +25,13 @@ def test_ppo_loss_is_sb3s():
     want = (-torch.min(adv * ratio, adv * ratio.clamp(0.8, 1.2)).mean() + 0.01 * (-ent.mean()) + 0.5 * ((s.returns - v2) ** 2).mean())
     assert torch.allclose(loss, want, atol=1e-6)
     assert set(log) == {"policy_loss", "value_loss", "entropy_loss", "approx_kl"}
+    loss.backward()  # heads of different sizes are padded with -inf logits: the padding must not poison the gradient
+    assert all(torch.isfinite(p.grad).all() for p in pol.parameters())
+    # the batched heads against one torch.distributions.Categorical per head
+    logits = torch.split(pol.pi(pol.body(obs["x"])), nvec, dim=1)
+    dists = [torch.distributions.Categorical(logits=lg) for lg in logits]
+    assert torch.allclose(ent, sum(d.entropy() for d in dists), atol=1e-5)
+    assert torch.allclose(lp2, sum(d.log_prob(a[:, k].long()) for k, d in enumerate(dists)), atol=1e-5)
 
 
 def test_rollout_buffer_get_covers_every_sample_once_in_sb3_order():
