@@ -28,8 +28,17 @@ def golden_tapes(kind=None):
     return out
 
 
+class _Tape(dict):
+    """The arrays of one .npz, decompressed once (NpzFile inflates a member again at every ``z[key]``)."""
+
+    @property
+    def files(self):
+        return list(self)
+
+
 def load_tape(name):
-    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    with np.load(os.path.join(GOLDEN, name + ".npz")) as npz:
+        z = _Tape((k, npz[k]) for k in npz.files)
     meta = json.loads(bytes(z["meta"]).decode())
     return meta, z
 
