@@ -465,7 +465,9 @@ int cbx_gae(const float* rewards, const float* values, const uint8_t* episode_st
  * [3] dynamic shared memory bytes per CTA; [4] logic warps; [5] encoder warps; [6] encoder variant (0 generic, 1 warp per
  * env, 2 ToyCtf(12,10) static, 3 Chain-10(12,12) static); [7] bit 0 TMA staging enabled, bit 1 dynamic tile order (tiles after a warp's first are drawn
  * from a global ticket counter instead of a fixed stride), bit 2 consecutive launches overlap (programmatic dependent launch, accesses
- * ordered tile by tile through completion counters in HBM). */
+ * ordered tile by tile through completion counters in HBM), bits 4-7 the L2 cache policies on the pipelined kernel's bulk
+ * copies (1 state tiles evict_last, 2 dense masks evict_first, 4 other observations and the actions evict_first, 8 scenario
+ * tables evict_last; chosen from the batch size, CBX_L2_HINTS overrides). */
 int cbx_batch_kernel_info(const cbx_batch* b, int32_t* out8);
 
 /* Parity instrumentation of the dynamic tile order; both words must read 0 between launches.  Warp-per-tile kernel: the

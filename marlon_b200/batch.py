@@ -324,6 +324,8 @@ class Batch:
         d = {k: int(out[i]) for i, k in enumerate(keys)}
         d["tile_order"] = "dynamic" if d["tma"] & 2 else "static"
         d["overlapped_launches"] = bool(d["tma"] & 4)
+        # L2 cache policies on the bulk copies: 1 state evict_last, 2 masks / 4 other observations + actions evict_first, 8 tables
+        d["l2_policies"] = (d["tma"] >> 4) & 15
         d["tma"] &= 1
         d["name"] = {1: "cbx_pipe_kernel", 2: "cbx_wide_kernel"}.get(d["pipelined"], "cbx_step_kernel")
         return d

@@ -178,6 +178,8 @@ struct cbx_params {
   uint32_t* tile_done;
   uint32_t seq;           // sequence number of this launch (1, 2, ...), counted per batch
   int overlap;            // 1: the protocol above is on (cbx_pipe_kernel only)
+  int l2_hints;           // cbx_pipe_kernel: bit 0 = state tiles loaded / stored with L2 evict_last, bit 1 = the dense masks
+                          // stored with evict_first
   unsigned long long* prof;  // optional: 16 cycle counters accumulated per phase by thread 0 of every CTA (NULL = off)
 };
 

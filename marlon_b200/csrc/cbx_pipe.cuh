@@ -139,7 +139,8 @@ __device__ __forceinline__ void build_field_images(const Ctx& c, const uint32_t*
 template <class D>
 __device__ __forceinline__ void encode_masks_pipe(const uint32_t* de, const uint2* lut, const cbx_layout* L, const cbx_enc_consts& K,
                                                   int8_t* remote_env, int8_t* connect_env, uint8_t* wb, const cbx_pipe_plan& Q,
-                                                  const uint8_t* zero, const int lane, const bool prof, long long (&pacc)[3]) {
+                                                  const uint8_t* zero, const int lane, const bool prof, long long (&pacc)[3], const bool hint,
+                                                  const uint64_t pol) {
   long long pt = prof ? clock64() : 0;
 #define CBX_EPROF(slot)                                                  \
   if (prof) {                                                            \
@@ -193,18 +194,18 @@ __device__ __forceinline__ void encode_masks_pipe(const uint32_t* de, const uint
   CBX_EPROF(14)  // building the rows in shared memory
   // ---- hand the rows to the TMA engine (lanes issue in parallel; every lane closes its own bulk group) ----
   if (!(skip & 256)) {
-    if (lane == 31) tma_store_1d(remote_env, wb + Q.b_remote, (uint32_t)(N * ROWR));
+    if (lane == 31) tma_store_1d_pol(remote_env, wb + Q.b_remote, (uint32_t)(N * ROWR), hint, pol);
     if (skip & 128) {
     } else if (Q.gs == 1) {
       for (int s = lane; s < N; s += 32) {
         const bool own = (de[D_OWNED + (s >> 5)] >> (s & 31)) & 1u;
-        tma_store_1d(connect_env + (size_t)s * ROWC, own ? cb : zero, (uint32_t)ROWC);
+        tma_store_1d_pol(connect_env + (size_t)s * ROWC, own ? cb : zero, (uint32_t)ROWC, hint, pol);
       }
     } else {
       for (int j = lane; j < N / 2; j += 32) {
         const uint32_t pr = (de[D_OWNED + ((2 * j) >> 5)] >> ((2 * j) & 31)) & 3u;  // bit 0: row 2j owned, bit 1: row 2j+1
         const uint8_t* src = pr == 3u ? cb + 4 * ROWC : pr == 1u ? cb + 2 * ROWC : pr == 2u ? cb : zero;
-        tma_store_1d(connect_env + (size_t)j * 2 * ROWC, src, (uint32_t)(2 * ROWC));
+        tma_store_1d_pol(connect_env + (size_t)j * 2 * ROWC, src, (uint32_t)(2 * ROWC), hint, pol);
       }
     }
   }
@@ -217,7 +218,7 @@ __device__ __forceinline__ void encode_masks_pipe(const uint32_t* de, const uint
 // scenario (the LearningDefender acts on a stale copy) and leave from a CTA-wide image built once.
 template <class D>
 __device__ __forceinline__ void encode_defender_tile(const Tile& t, const Target& o, const int n_valid, uint8_t* wb, const cbx_pipe_plan& Q,
-                                                     const uint8_t* def_static, const int lane) {
+                                                     const uint8_t* def_static, const int lane, const bool hint, const uint64_t pol) {
   const cbx_layout* L = t.L;
   const int n = CBX_DIM(D, NN, L->n), nsvc = CBX_DIM(D, NSVC, L->nservices);
   const int OW = D::kStatic ? (D::N + 31) / 32 : L->OW;
@@ -236,10 +237,10 @@ __device__ __forceinline__ void encode_defender_tile(const Tile& t, const Target
   }
   fence_async_smem();
   __syncwarp();
-  if (lane == 0) tma_store_1d(o.infected, img, (uint32_t)(CBX_TILE * n));
-  if (lane == 1) tma_store_1d(o.fw_in, def_static, (uint32_t)(CBX_TILE * 6 * n));
-  if (lane == 2) tma_store_1d(o.fw_out, def_static + CBX_TILE * 6 * n, (uint32_t)(CBX_TILE * 6 * n));
-  if (lane == 3 && nsvc > 0) tma_store_1d(o.services, def_static + 2 * CBX_TILE * 6 * n, (uint32_t)(CBX_TILE * nsvc));
+  if (lane == 0) tma_store_1d_pol(o.infected, img, (uint32_t)(CBX_TILE * n), hint, pol);
+  if (lane == 1) tma_store_1d_pol(o.fw_in, def_static, (uint32_t)(CBX_TILE * 6 * n), hint, pol);
+  if (lane == 2) tma_store_1d_pol(o.fw_out, def_static + CBX_TILE * 6 * n, (uint32_t)(CBX_TILE * 6 * n), hint, pol);
+  if (lane == 3 && nsvc > 0) tma_store_1d_pol(o.services, def_static + 2 * CBX_TILE * 6 * n, (uint32_t)(CBX_TILE * nsvc), hint, pol);
   tma_store_commit();
 }
 
@@ -291,6 +292,8 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
   // dynamic tile order: this launch's OWN ticket counter (a fresh slot of a ring the host re-zeroes in halves: any number of
   // launches may be in flight at once when the grid is smaller than the machine, so no counter is shared or reset in-kernel)
   int* const tickets = p.tickets;
+  const bool keep_state = p.l2_hints & 1, stream_masks = p.l2_hints & 2, stream_rest = p.l2_hints & 4, keep_tables = p.l2_hints & 8;
+  const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
 
   // the scenario tables are on their way (one bulk copy, ~2 us from L2 / HBM) while the CTA fills its constant buffers
   if (tid == 0) {
@@ -299,7 +302,7 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
     for (int s = 0; s < Q.nslot; ++s) { mbar_init(&bar_ready[s], 1); mbar_init(&bar_empty[s], Q.we); mbar_init(&bar_rdef[s], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     mbar_expect_tx(&bars[0], table_bytes);
-    tma_load_1d(s_tb, p.tables, table_bytes, &bars[0]);
+    tma_load_1d_pol(s_tb, p.tables, table_bytes, &bars[0], keep_tables, pol_keep);
   }
   for (int k = tid; k < 256; k += nthreads) {
     uint32_t lo = ((k & 0xF) * 0x00204081u) & 0x01010101u, hi = (((k >> 4) & 0xF) * 0x00204081u) & 0x01010101u;
@@ -412,13 +415,13 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
           const uint32_t att_bytes = (bulk_acts && need_att) ? (uint32_t)(CBX_TILE * AW) * asz : 0u;
           const uint32_t def_bytes = (bulk_acts && need_def) ? (uint32_t)(CBX_TILE * 12) * asz : 0u;
           mbar_expect_tx(&bar_load[warp], (uint32_t)L.S * kRowBytes + att_bytes + def_bytes);
-          tma_load_1d(lb, gstate, (uint32_t)L.S * kRowBytes, &bar_load[warp]);
+          tma_load_1d_pol(lb, gstate, (uint32_t)L.S * kRowBytes, &bar_load[warp], keep_state, pol_keep);
           if (att_bytes)
-            tma_load_1d(reinterpret_cast<char*>(act) + half * att_bytes, reinterpret_cast<const char*>(p.att_actions) + e0 * AW * asz,
-                        att_bytes, &bar_load[warp]);
+            tma_load_1d_pol(reinterpret_cast<char*>(act) + half * att_bytes, reinterpret_cast<const char*>(p.att_actions) + e0 * AW * asz,
+                            att_bytes, &bar_load[warp], stream_rest, pol_stream);
           if (def_bytes)
-            tma_load_1d(reinterpret_cast<char*>(act + CBX_TILE * 10) + half * def_bytes,
-                        reinterpret_cast<const char*>(p.def_actions) + e0 * 12 * asz, def_bytes, &bar_load[warp]);
+            tma_load_1d_pol(reinterpret_cast<char*>(act + CBX_TILE * 10) + half * def_bytes,
+                            reinterpret_cast<const char*>(p.def_actions) + e0 * 12 * asz, def_bytes, &bar_load[warp], stream_rest, pol_stream);
         }
       } else {
         uint4* d = reinterpret_cast<uint4*>(lb);
@@ -544,14 +547,14 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
         const Target tm = make_target(p.v, L, e0, false);
         const bool full = n_valid == CBX_TILE && enc_mask == 0xFFFFFFFFu;
         if (Q.logic_tma) {
-          if (lane == 0) tma_store_1d(p.state + (int64_t)tile * L.S * CBX_TILE, lb, (uint32_t)L.S * kRowBytes);
+          if (lane == 0) tma_store_1d_pol(p.state + (int64_t)tile * L.S * CBX_TILE, lb, (uint32_t)L.S * kRowBytes, keep_state, pol_keep);
           if (full) {
-            if (lane == 1) tma_store_1d(tm.scalars, im.scal, CBX_TILE * 32u);
-            if (lane == 2) tma_store_1d(tm.leaked, im.leak, (uint32_t)(CBX_TILE * 4 * wpe_leak));
-            if (lane == 3) tma_store_1d(tm.cachem, im.cachem, (uint32_t)(CBX_TILE * 4 * wpe_cachem));
-            if (lane == 4) tma_store_1d(tm.props, im.props, (uint32_t)(CBX_TILE * 4 * wpe_props));
-            if (lane == 5) tma_store_1d(tm.priv, im.priv, (uint32_t)(CBX_TILE * 4 * wpe_priv));
-            if (lane == 6 && dense) tma_store_1d(tm.local, im.local, (uint32_t)(CBX_TILE * 4 * wpe_local));
+            if (lane == 1) tma_store_1d_pol(tm.scalars, im.scal, CBX_TILE * 32u, stream_rest, pol_stream);
+            if (lane == 2) tma_store_1d_pol(tm.leaked, im.leak, (uint32_t)(CBX_TILE * 4 * wpe_leak), stream_rest, pol_stream);
+            if (lane == 3) tma_store_1d_pol(tm.cachem, im.cachem, (uint32_t)(CBX_TILE * 4 * wpe_cachem), stream_rest, pol_stream);
+            if (lane == 4) tma_store_1d_pol(tm.props, im.props, (uint32_t)(CBX_TILE * 4 * wpe_props), stream_rest, pol_stream);
+            if (lane == 5) tma_store_1d_pol(tm.priv, im.priv, (uint32_t)(CBX_TILE * 4 * wpe_priv), stream_rest, pol_stream);
+            if (lane == 6 && dense) tma_store_1d_pol(tm.local, im.local, (uint32_t)(CBX_TILE * 4 * wpe_local), stream_rest, pol_stream);
           }
           if (lane < 7) tma_store_commit();
           if (overlap) {  // the tile before this one: its bulk copies (one group per lane) have completed -> report it
@@ -640,7 +643,7 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
         for (int e = wid; e < n_valid; e += Q.we)
           if ((enc_mask >> e) & 1u) {
             encode_masks_pipe<D>(desc + e * DW, s_lut, &L, p.enc, p.v.remote_vulnerability + (e0 + e) * L.sz_remote,
-                                 p.v.connect + (e0 + e) * (int64_t)L.sz_connect, wb, Q, s_zero, lane, p.prof != nullptr, pacc);
+                                 p.v.connect + (e0 + e) * (int64_t)L.sz_connect, wb, Q, s_zero, lane, p.prof != nullptr, pacc, stream_masks, pol_stream);
             ++groups;
           }
       }
@@ -649,7 +652,7 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
         Tile t;
         t.L = &L; t.tb = s_tb; t.st = nullptr; t.sg = nullptr; t.desc = desc; t.lut = s_lut; t.K = &p.enc; t.DW = DW;
         const Target tm = make_target(p.v, L, e0, false);
-        encode_defender_tile<D>(t, tm, n_valid, wb, Q, s_defst, lane);
+        encode_defender_tile<D>(t, tm, n_valid, wb, Q, s_defst, lane, stream_rest, pol_stream);
         if (n_valid == CBX_TILE) ++groups;
       }
       __syncwarp();

@@ -49,6 +49,37 @@ __device__ __forceinline__ void tma_store_1d(void* dst_gmem, const void* src_sme
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes)
                : "memory");
 }
+// L2 cache policies for bulk copies: the per-env state is re-read by the next launch (evict_last keeps its lines while the
+// observation stream, 50x its size, passes through L2 -- evict_first), cbx_params.l2_hints selects which are applied
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_load_1d_hint(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_1d_hint(void* dst_gmem, const void* src_smem, uint32_t bytes, uint64_t pol) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+               "r"(bytes), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_1d_pol(void* dst_gmem, const void* src_smem, uint32_t bytes, bool hint, uint64_t pol) {
+  if (hint) tma_store_1d_hint(dst_gmem, src_smem, bytes, pol);
+  else tma_store_1d(dst_gmem, src_smem, bytes);
+}
+__device__ __forceinline__ void tma_load_1d_pol(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, bool hint, uint64_t pol) {
+  if (hint) tma_load_1d_hint(dst_smem, src_gmem, bytes, bar, pol);
+  else tma_load_1d(dst_smem, src_gmem, bytes, bar);
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
