@@ -30,8 +30,9 @@ timeout 400 ncu --set full --clock-control none --import-source on -k regex:cbx_
 ncu -i gpurun_out/wide.ncu-rep --page raw --csv > gpurun_out/wide_raw.csv 2>/dev/null; python scripts/ncu_summary.py gpurun_out/wide_raw.csv > gpurun_out/wide_summary.txt 2>&1
 ncu -i gpurun_out/wide.ncu-rep --page source --csv --print-source cuda,sass > gpurun_out/wide_src.csv 2>/dev/null; python scripts/ncu_lines.py gpurun_out/wide_src.csv 50 | cut -c1-220 > gpurun_out/wide_lines.txt; rm -f gpurun_out/wide_src.csv
 CMD3="python bench.py --workload random16 --envs-per-gpu 131072 --steps 5 --warmup 3 --no-cpu-baseline --no-e2e"
-timeout 400 ncu --set full --clock-control none -k regex:cbx_wide_kernel -s 5 -c 1 -f -o gpurun_out/wide16 $CMD3 > gpurun_out/ncu_wide16.log 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:cbx_wide_kernel -s 5 -c 1 -f -o gpurun_out/wide16 $CMD3 > gpurun_out/ncu_wide16.log 2>&1
 ncu -i gpurun_out/wide16.ncu-rep --page raw --csv > gpurun_out/wide16_raw.csv 2>/dev/null; python scripts/ncu_summary.py gpurun_out/wide16_raw.csv > gpurun_out/wide16_summary.txt 2>&1
+ncu -i gpurun_out/wide16.ncu-rep --page source --csv --print-source cuda,sass > gpurun_out/wide16_src.csv 2>/dev/null; python scripts/ncu_lines.py gpurun_out/wide16_src.csv 50 | cut -c1-220 > gpurun_out/wide16_lines.txt; rm -f gpurun_out/wide16_src.csv
 rm -f gpurun_out/*.ncu-rep
 grep -E "dram__bytes_(read|write).sum  |time_duration" gpurun_out/pipe_summary.txt gpurun_out/wide_summary.txt gpurun_out/wide16_summary.txt
 ls -la gpurun_out | tail -30
