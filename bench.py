@@ -638,7 +638,7 @@ def e2e_vecenv(m, K, W, world, local, dev, observations):
     return _max_over_ranks(secs, world, dev)
 
 
-def device_rollout(m, world, local, dev, T=32, rounds=3):
+def device_rollout(m, world, local, dev, T=32, rounds=3, workload="toyctf"):
     """rollout collection with everything resident in HBM -- observations are the batch's own tensors, two small
     MLP actor-critics (marlon_b200.ppo.MultiDiscretePolicy) pick both agents' MultiDiscrete actions on the device, one fused
     attacker+defender launch per step, rewards / values / log-probabilities into [T, n] device buffers, GAE by cbx_gae.
@@ -652,8 +652,13 @@ def device_rollout(m, world, local, dev, T=32, rounds=3):
 
     n = m["n"]
     torch.manual_seed(7)
-    u = MultiAgentUniversalEnv("CyberBattleToyCtf-v0", n, device=local, maximum_node_count=12, maximum_total_credentials=10,
-                               maximum_discoverable_credentials_per_action=5, max_timesteps=2000)
+    if workload == "random16":  # configs[4]: 16 generated networks side by side, factored masks (workload_config("random16"))
+        u = MultiAgentUniversalEnv("CyberBattleRandom-v0", n // 16, device=local, scenario_seeds=range(16), maximum_node_count=72,
+                                   maximum_total_credentials=192, maximum_discoverable_credentials_per_action=32,
+                                   max_timesteps=2000, mask_mode="factored")
+    else:
+        u = MultiAgentUniversalEnv("CyberBattleToyCtf-v0", n, device=local, maximum_node_count=12, maximum_total_credentials=10,
+                                   maximum_discoverable_credentials_per_action=5, max_timesteps=2000)
     aobs, dobs = u.reset()
     apol = ppo.MultiDiscretePolicy.for_space(aobs, u.attacker_action_space.nvec, ppo.ATTACKER_FEATURES).to(dev)
     dpol = ppo.MultiDiscretePolicy.for_space(dobs, u.defender_action_space.nvec, ppo.DEFENDER_FEATURES).to(dev)
@@ -751,6 +756,21 @@ def run_ours(args):
                     "value": m4["value"], "unit": "env-steps/s", "ms_per_step": m4["ms_per_step"], "collective_ms": m4["collective_ms"],
                     "roofline": m4["roofline"], "algorithmic_bytes_per_env_step": m4["ab"], "gpu_launches": m4["launches"]}
 
+    # ---- config 5 as BASELINE.json names it (generated networks, PPO rollout across the GPUs): the step kernel on 16 networks
+    # side by side, then rollout collection with MLP policies on the device (rollout.collect_rollouts + cbx_gae) ----
+    cfg5 = None
+    if (world > 1 and not args.no_config4) or args.config5:
+        K5 = min(K, 50)
+        m5 = measure_device(args, "random16", 131072, K5, W, world, rank, local, dev)
+        roll5_s, Kr5 = device_rollout(m5, world, local, dev, T=16, rounds=2, workload="random16")
+        if rank == 0:
+            cfg5 = {"workload": workload_label("random16", True), "envs_per_gpu": m5["n"], "total_envs": m5["total_envs"], "steps": K5,
+                    "value": m5["value"], "unit": "env-steps/s", "ms_per_step": m5["ms_per_step"], "collective_ms": m5["collective_ms"],
+                    "roofline": m5["roofline"], "algorithmic_bytes_per_env_step": m5["ab"], "gpu_launches": m5["launches"],
+                    "device_rollout_mlp_policies": {"value": m5["total_envs"] * Kr5 / roll5_s, "unit": "env-steps/s", "steps": Kr5,
+                                                    "note": "rollout.collect_rollouts: two MLP actor-critics choose both agents' actions on "
+                                                            "the device, one fused launch per step, GAE by cbx_gae; nothing crosses PCIe"}}
+
     if rank == 0:
         ab = m["ab"]
         line = {
@@ -773,6 +793,8 @@ def run_ours(args):
             line["e2e"] = e2e
         if cfg4:
             line["config4"] = cfg4
+        if cfg5:
+            line["config5"] = cfg5
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(seconds=args.cpu_seconds)
             pr = python_reference_baseline()
@@ -822,7 +844,8 @@ def main():
     ap.add_argument("--workload", default="toyctf", choices=sorted(WORKLOADS), help="toyctf = the headline configuration")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer legs (kernel experiments)")
-    ap.add_argument("--no-config4", action="store_true", help="multi-GPU runs: skip the Chain-100 / 1M-env block")
+    ap.add_argument("--no-config4", action="store_true", help="multi-GPU runs: skip the Chain-100 / 1M-env and generated-network blocks")
+    ap.add_argument("--config5", action="store_true", help="add the generated-network block (config 5) on a single GPU too")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -18,6 +18,9 @@ if e:
 if d.get("config4"):
     c = d["config4"]
     print("   config4 value %.4g  frac %.3f  collective_ms %.4f" % (c["value"], c["roofline"]["frac"], c["collective_ms"]))
+if d.get("config5"):
+    c = d["config5"]
+    print("   config5 value %.4g  frac %.3f  device_rollout %.4g" % (c["value"], c["roofline"]["frac"], c["device_rollout_mlp_policies"]["value"]))
 if d.get("cpu_baseline"):
     c = d["cpu_baseline"]
     print("   cpu_baseline %.4g on %d cores (%s); python_reference %s" % (c["value"], c["cores"], c["kind"], (c.get("python_reference") or {}).get("value")))

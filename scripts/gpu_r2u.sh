@@ -1,0 +1,4 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python bench.py --steps 20 --warmup 5 --config5 --no-cpu-baseline --no-e2e > gpurun_out/u.log 2> gpurun_out/u.err; echo "rc=$?"; tail -c 2500 gpurun_out/u.err
+python scripts/bench_line.py c5 < gpurun_out/u.log
