@@ -536,6 +536,68 @@ def e2e_results_only(m, K, W, dtype, world, local, dev):
     return _max_over_ranks(secs, world, dev)
 
 
+def e2e_results_two_halves(m, K, W, world, local, dev):
+    """The results-only host-buffer step as a double-buffered host loop drives it: the envs are two half batches on two
+    streams; the loop waits for half A's results of step s-1 (they are in host memory then: the point where a policy would
+    read them and write A's next actions), submits A's step s, and does the same for B -- so the GPU works on one half while
+    the host handles the other.  Every step of a half is submitted only after that half's previous results have reached
+    the host.  -> seconds for K steps of all envs, max over ranks (None when the batch does not split)."""
+    import copy
+
+    import torch
+    import torch.distributed as dist
+
+    from marlon_b200.batch import Batch
+
+    n = m["n"]
+    if m["multi"] or n % 128:
+        return None
+    h = n // 2
+    parts = []
+    for q in range(2):
+        cfg = copy.copy(m["cfg"])
+        cfg.env_index_base = m["cfg"].env_index_base + q * h
+        bq = Batch(m["comp"], cfg, h, device=local)
+        bq.reset()
+        bq.host_prepare()
+        parts.append((bq, HostTape(m, torch.int16, rows=slice(q * h, (q + 1) * h)), torch.cuda.Stream(device=dev)))
+    outs = [None, None]
+
+    def one(s):
+        for q, (bq, tape, st) in enumerate(parts):
+            a, d = tape.get(s)
+            st.synchronize()  # this half's previous results are on the host
+            with torch.cuda.stream(st):
+                outs[q] = bq.step_host(a, d, sync=False)
+
+    for s in range(W):
+        one(s)
+    for _, tape, st in parts:
+        st.synchronize()
+        tape.get(W)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    secs, s = 0.0, W
+    CH = parts[0][1].CH
+    while s < W + K:
+        for _, tape, st in parts:
+            st.synchronize()
+            tape.get(s)
+        e = min(W + K, (s // CH + 1) * CH)
+        t0 = time.perf_counter()
+        for q in range(s, e):
+            one(q)
+        for _, _, st in parts:
+            st.synchronize()
+        secs += time.perf_counter() - t0
+        s = e
+    for (bq, _, _), out in zip(parts, outs):
+        assert (out["att_reward"] == bq.numpy("att_reward")).all() and (out["def_truncated"] == bq.numpy("def_truncated")).all()
+        bq.close()
+    return _max_over_ranks(secs, world, dev)
+
+
 def e2e_obs_factored(m, K, W, world, local, dev, halves):
     """Host-buffer steps that also bring the observation a host-side policy needs to page-locked host memory every step:
     scalars, leaked credentials, credential cache, property matrix, privilege levels, owned bits (= the factored action masks,
@@ -706,6 +768,7 @@ def run_ours(args):
         Ke = K
         e2e_s = e2e_results_only(m, Ke, W, torch.int16, world, local, dev)
         e2e32_s = e2e_results_only(m, Ke, W, torch.int32, world, local, dev)
+        e2e2h_s = e2e_results_two_halves(m, Ke, W, world, local, dev)
         Ko = min(K, 200)
         obs2_s, d2h_obs = e2e_obs_factored(m, Ko, W, world, local, dev, halves=2)
         obs1_s, _ = e2e_obs_factored(m, Ko, W, world, local, dev, halves=1)
@@ -723,6 +786,8 @@ def run_ours(args):
                "variants": {
                    "results_only_int16": {"value": total_envs * Ke / e2e_s, "steps": Ke, "h2d_bytes_per_step": act_b * 2, "d2h_bytes_per_step": n * 12},
                    "results_only_int32": {"value": total_envs * Ke / e2e32_s, "steps": Ke, "h2d_bytes_per_step": act_b * 4, "d2h_bytes_per_step": n * 12},
+                   "results_only_int16_two_halves": None if e2e2h_s is None else {
+                       "value": total_envs * Ke / e2e2h_s, "steps": Ke, "h2d_bytes_per_step": act_b * 2, "d2h_bytes_per_step": n * 12},
                    "obs_factored_two_halves": None if obs2_s is None else {
                        "value": total_envs * Ko / obs2_s, "steps": Ko, "h2d_bytes_per_step": act_b * 2, "d2h_bytes_per_step": d2h_obs},
                    "obs_factored_sequential": None if obs1_s is None else {
@@ -737,7 +802,10 @@ def run_ours(args):
                "note": "value = results_only_int16: cbx_batch_step_host_i16 per step with HOST action buffers (int16 elements) in "
                        "page-locked memory -- the kernel reads each tile's actions over PCIe in place (TMA bulk loads from the mapped "
                        "host buffers) and writes rewards + done flags straight into a rotating page-locked result block, stream sync; "
-                       "observations stay in HBM as torch tensors (the consumer is a GPU-resident policy).  For a HOST-side policy "
+                       "observations stay in HBM as torch tensors (the consumer is a GPU-resident policy); results_only_int16_two_halves is the "
+                       "same work as a double-buffered host loop submits it: two half batches on two streams, a half's next step "
+                       "goes out only after its previous results have reached the host, so the GPU steps one half while the host "
+                       "handles the other (the single-batch figure pays a full launch + pipeline fill + sync per step).  For a HOST-side policy "
                        "the observation has to cross PCIe as well: obs_factored_* bring every small field + the factored masks + the "
                        "defender observation to pinned host memory each step (cbx_batch_fetch_host; two_halves overlaps one half "
                        "batch's copies with the other's step), device_rollout_mlp_policies is rollout.collect_rollouts with two small MLP "
