@@ -36,6 +36,8 @@ WORKLOADS = {
     "toyctf_scan": "CyberBattleToyCtf-v0 (N=12,C=10) CyberBattleEnv step with the built-in ScanAndReimageCompromisedMachines(0.6, 2, 5) "
                    "defender (configs[2] to the letter: notebook_withdefender.py:57-63 parameters, SLA 0.80, Philox detection draws, "
                    "auto-reset as under the SB3 VecEnv adapter)",
+    "toyctf_live": "CyberBattleToyCtf-v0 (N=12,C=10) MARLon attacker+defender pair step with the LIVE LearningDefender binding (SURVEY 8f row 4: "
+                   "the defender re-images / blocks / allows on the environment the attacker plays in; firewall rule lists are per-env state)",
     "random16": "CyberBattleRandom-v0, 16 generated 65-node networks (seeds 0-15) side by side in one batch (config 5: padded layout, "
                 "N=72, C=192, 32 leak slots), MARLon attacker+defender pair step",
 }
@@ -82,7 +84,8 @@ def workload_config(mask_mode=0, workload="toyctf"):
         defender_constraint=config.DefenderConstraint(0.60), losing_reward=-5000.0,
         attacker_max_timesteps=2000, attacker_invalid_action_reward_modifier=-1.0,
         defender_enabled=True, defender_max_timesteps=2000, defender_invalid_action_reward=-1,
-        defender_reset_on_constraint_broken=True, defender_loss_reward=-5000.0, mask_mode=mask_mode)
+        defender_reset_on_constraint_broken=True, defender_loss_reward=-5000.0, mask_mode=mask_mode,
+        **({"defender_binding": "live"} if workload == "toyctf_live" else {}))
     return comp, cfg
 
 
@@ -896,7 +899,8 @@ def _packed_state_words(comp, cfg):
     Wn, PW, AW = (n + 31) // 32, (props + 31) // 32, (2 * (L + R) + 31) // 32
     nsec, ntr = max(1, len(comp.secrets)), len(comp.triples)
     has_tags = int(comp.blob[12]) & 1
-    return (13 + (n + 3) // 4 + 2 + 3 * Wn + (n + 15) // 16 + (((n + 7) // 8) if has_tags else 0) + 3 * ((n + 3) // 4)
+    fw = 2 * int(comp.fw_ext[2]) if getattr(cfg, "def_binding", 0) and getattr(comp, "fw_ext", None) is not None else 0  # live: 2 words per rule-list group
+    return (13 + (n + 3) // 4 + 2 + 3 * Wn + (n + 15) // 16 + (((n + 7) // 8) if has_tags else 0) + 3 * ((n + 3) // 4) + fw
             + n * PW + n * AW + (nsec + 31) // 32 + max(1, (ntr + 31) // 32) + (ntr + 2) // 2)
 
 

@@ -543,6 +543,14 @@ static int create_impl(const cbx_scenario* const* scns, int n_scn, const int64_t
   if (b->grid > b->p.n_tiles) b->grid = b->p.n_tiles;
   const char* gridenv = getenv("CBX_GRID");
   if (gridenv && atoi(gridenv) > 0) b->grid = atoi(gridenv) < b->p.n_tiles ? atoi(gridenv) : b->p.n_tiles;
+  // L2 policies of the bulk copies (see the pipelined kernel's plan below): on while the state is at most half of L2
+  int l2_default = 0;
+  { const char* lh = getenv("CBX_L2_HINTS");
+    int l2_bytes = 0;
+    cudaDeviceGetAttribute(&l2_bytes, cudaDevAttrL2CacheSize, device);
+    const int64_t state_bytes = (int64_t)b->p.n_pad * b->p.lay.S * 4;
+    l2_default = lh ? atoi(lh) : (state_bytes * 2 <= (int64_t)l2_bytes ? 7 : 0); }
+  b->p.l2_hints = l2_default & 1;  // the fused kernel: the state tile's bulk load / store only (its observation stores are plain)
   // pipelined kernel (logic warps ahead of TMA-storing encoder warps) when the configuration qualifies; CBX_PIPE=0 forces the
   // fused kernel, CBX_PIPE_WL / CBX_PIPE_WE / CBX_PIPE_CTAS (CTAs per SM) are tuning knobs
   b->p.pipe.enabled = 0; b->pipe_grid = 0;
@@ -571,18 +579,14 @@ static int create_impl(const cbx_scenario* const* scns, int n_scn, const int64_t
         // tiles), so it is always on.  CBX_PIPE_DYNAMIC=0/1 overrides.
         { const char* dy = getenv("CBX_PIPE_DYNAMIC");
           Q.dynamic = dy ? atoi(dy) != 0 : (b->p.overlap || b->p.n_tiles >= 24 * b->pipe_grid); }
-        // L2 cache policies on the bulk copies (cbx_params.l2_hints; CBX_L2_HINTS=0..15 overrides).  The per-env state is the
+        // L2 cache policies on the bulk copies (cbx_params.l2_hints, decided above; CBX_L2_HINTS=0..15 overrides).  The per-env state is the
         // only data a step reads that an earlier step wrote: with evict_last on its tiles and evict_first on everything that
         // streams (observations, masks, actions) it stays in L2 under a write stream 50x its size, so a launch's first
         // state loads are L2 hits instead of HBM reads queued behind the previous launch's writes.  Measured (ToyCtf, B200,
         // profiles/r02_l2_policy_sweep.txt): roofline fraction 0.874 -> 0.972 at 65 536 envs, 0.931 -> 0.994 at 131 072,
         // level at 262 144 (59 MB of state), and -1 % at 1 048 576 envs, where the state (235 MB) cannot stay: policies on
         // while the state is at most half of L2.
-        { const char* lh = getenv("CBX_L2_HINTS");
-          int l2_bytes = 0;
-          cudaDeviceGetAttribute(&l2_bytes, cudaDevAttrL2CacheSize, device);
-          const int64_t state_bytes = (int64_t)b->p.n_pad * b->p.lay.S * 4;
-          b->p.l2_hints = lh ? atoi(lh) : (state_bytes * 2 <= (int64_t)l2_bytes ? 7 : 0); }
+        b->p.l2_hints = l2_default;
         b->p.pipe = Q;
       } else {
         cudaGetLastError();
@@ -1167,7 +1171,7 @@ int cbx_batch_kernel_info(const cbx_batch* b, int32_t* out8) {
   out8[5] = Q.enabled ? Q.we : 0;
   out8[6] = b->p.enc.warp_env;
   out8[7] = b->use_tma | ((Q.enabled ? Q.dynamic : wide ? b->p.wide.dynamic : 0) ? 2 : 0) | ((Q.enabled && b->p.overlap) ? 4 : 0) |
-            ((Q.enabled ? b->p.l2_hints & 15 : 0) << 4);
+            ((wide ? 0 : b->p.l2_hints & 15) << 4);
   return CBX_OK;
 }
 

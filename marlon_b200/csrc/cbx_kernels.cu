@@ -109,7 +109,8 @@ __global__ void __launch_bounds__(CBX_THREADS, CBX_MIN_CTAS) cbx_step_kernel(con
       if (tid < 32) {
         if (tid == 0) {  // the tile's state is one contiguous block (tiled structure of arrays): a single bulk copy
           mbar_expect_tx(&bars[1], (uint32_t)L.S * kRowBytes);
-          tma_load_1d(s_st, p.state + (int64_t)tile * L.S * CBX_TILE, (uint32_t)L.S * kRowBytes, &bars[1]);
+          tma_load_1d_pol(s_st, p.state + (int64_t)tile * L.S * CBX_TILE, (uint32_t)L.S * kRowBytes, &bars[1], (p.l2_hints & 1) != 0,
+                          l2_policy_evict_last());
         }
       }
     } else {
@@ -221,7 +222,8 @@ __global__ void __launch_bounds__(CBX_THREADS, CBX_MIN_CTAS) cbx_step_kernel(con
       fence_async_smem();
       __syncthreads();
       if (tid < 32) {
-        if (tid == 0) tma_store_1d(p.state + (int64_t)tile * L.S * CBX_TILE, s_st, (uint32_t)L.S * kRowBytes);
+        if (tid == 0)
+          tma_store_1d_pol(p.state + (int64_t)tile * L.S * CBX_TILE, s_st, (uint32_t)L.S * kRowBytes, (p.l2_hints & 1) != 0, l2_policy_evict_last());
         tma_store_commit();
         tma_store_wait_read();  // the tile buffer is reused by the next iteration
       }
