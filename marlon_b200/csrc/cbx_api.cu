@@ -80,12 +80,16 @@ bool plan_pipe(const cbx_params& p, int wl, int we, cbx_pipe_plan* Q) {
   const bool defobs = p.cfg.mode == CBX_MODE_MARLON && p.cfg.def_enabled;
   int64_t o = 0;
   auto up = [](int64_t x, int a) { return (x + a - 1) / a * a; };
-  Q->tables = (int)o; o = up(o + p.table_words + ((L.S + 3) & ~3), 32);
+  Q->tables = (int)o; o = up(o + p.table_words + ((L.S + 3) & ~3) + p.fwx_words, 32);
   Q->lut = (int)o; o += 512;
   Q->bars = (int)o; o = up(o + 2 * (1 + wl + 3 * Q->nslot), 32);
   Q->done_ring = (int)o; o += 96;  // overlapped launches: completed parts + tile index of 32 tracked tiles, publisher progress
   Q->zero = (int)o; o = up(o + (dense ? gs * ROWC / 4 : 0), 32);
-  Q->def_static = (int)o; o = up(o + (defobs ? CBX_TILE * (12 * L.n + L.nservices) / 4 : 0), 32);
+  // static parts of the defender observation for a tile: [32][6n] in | [32][6n] out | [32][services]; under the live binding
+  // the firewall rows are per-env state (images in the logic buffers below) and only the service rows remain
+  const bool live = L.o_fw >= 0;
+  Q->def_svc = live ? 0 : 2 * CBX_TILE * 6 * L.n;
+  Q->def_static = (int)o; o = up(o + (defobs ? (Q->def_svc + CBX_TILE * L.nservices + 3) / 4 : 0), 32);
   // logic buffers: state tile | staging | field images [32][words per env] | actions (aliasing the property image when it
   // is large enough: the actions are consumed before the images are laid out)
   Q->lbufs = (int)o;
@@ -99,6 +103,11 @@ bool plan_pipe(const cbx_params& p, int wl, int we, cbx_pipe_plan* Q) {
     Q->i_props = (int)q; q += (int64_t)L.N * L.nprops * CBX_TILE;
     Q->i_priv = (int)q; q += L.N * CBX_TILE;
     Q->i_local = (int)q; q += (int64_t)(L.sz_local / 4) * CBX_TILE;
+    Q->i_fwin = Q->i_fwout = -1;
+    if (live && defobs) {  // 192 n bytes each: whole 16-byte words
+      Q->i_fwin = (int)q; q += CBX_TILE * 6 * L.n / 4;
+      Q->i_fwout = (int)q; q += CBX_TILE * 6 * L.n / 4;
+    }
     if (L.N * L.nprops >= 22) Q->l_acts = Q->i_props;
     else { Q->l_acts = (int)q; q += 22 * CBX_TILE; }
     q = up(q, 32);
@@ -556,7 +565,7 @@ static int create_impl(const cbx_scenario* const* scns, int n_scn, const int64_t
   b->p.pipe.enabled = 0; b->pipe_grid = 0;
   {
     const char* pe = getenv("CBX_PIPE");
-    if (b->use_tma && n_scn == 1 && !live && !(pe && pe[0] == '0')) {  // live binding: per-env firewall rows -> the fused kernel
+    if (b->use_tma && n_scn == 1 && !(pe && pe[0] == '0')) {
       const char *ewl = getenv("CBX_PIPE_WL"), *ewe = getenv("CBX_PIPE_WE"), *ect = getenv("CBX_PIPE_CTAS");
       const int cand[4][2] = {{4, 8}, {3, 8}, {2, 8}, {2, 4}};
       cbx_pipe_plan Q;

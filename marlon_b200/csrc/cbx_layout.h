@@ -114,6 +114,8 @@ struct cbx_pipe_plan {
   int dynamic;              // tiles after a logic warp's first come from a global ticket counter (cbx_params.tile_counter)
   int l_stage, l_acts;      // inside a logic buffer (the state tile is at 0)
   int i_scal, i_leak, i_cachem, i_props, i_priv, i_local;  // field images [32 envs][words per env], inside a logic buffer
+  int i_fwin, i_fwout;      // live defender binding: the tile's firewall rows [32 envs][6 n bytes] (else -1: static CTA image)
+  int def_svc;              // byte offset of the service rows inside the CTA's static defender image
   int slots, slot_words;    // per slot: descriptors [32][desc_words] | header (32 words)
   int s_hdr;
   int wbufs, wbuf_words;    // per encoder warp

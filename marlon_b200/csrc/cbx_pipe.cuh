@@ -222,8 +222,11 @@ __device__ __forceinline__ void encode_defender_tile(const Tile& t, const Target
   const cbx_layout* L = t.L;
   const int n = CBX_DIM(D, NN, L->n), nsvc = CBX_DIM(D, NSVC, L->nservices);
   const int OW = D::kStatic ? (D::N + 31) / 32 : L->OW;
-  if (n_valid != CBX_TILE) {  // ragged last tile: plain stores
-    encode_defender_by_warp<D>(t, o, n_valid, mask_all(), true, 0, 1);
+  if (n_valid != CBX_TILE) {  // ragged last tile: plain stores (live binding: the logic warp writes the firewall rows)
+    encode_defender_by_warp<D>(t, o, n_valid, mask_all(), !t.fx, 0, 1);
+    if (t.fx) {
+      for (int idx = lane; idx < n_valid * nsvc; idx += 32) o.services[idx] = 1;
+    }
     return;
   }
   tma_store_wait_read();
@@ -238,9 +241,9 @@ __device__ __forceinline__ void encode_defender_tile(const Tile& t, const Target
   fence_async_smem();
   __syncwarp();
   if (lane == 0) tma_store_1d_pol(o.infected, img, (uint32_t)(CBX_TILE * n), hint, pol);
-  if (lane == 1) tma_store_1d_pol(o.fw_in, def_static, (uint32_t)(CBX_TILE * 6 * n), hint, pol);
-  if (lane == 2) tma_store_1d_pol(o.fw_out, def_static + CBX_TILE * 6 * n, (uint32_t)(CBX_TILE * 6 * n), hint, pol);
-  if (lane == 3 && nsvc > 0) tma_store_1d_pol(o.services, def_static + 2 * CBX_TILE * 6 * n, (uint32_t)(CBX_TILE * nsvc), hint, pol);
+  if (lane == 1 && !t.fx) tma_store_1d_pol(o.fw_in, def_static, (uint32_t)(CBX_TILE * 6 * n), hint, pol);
+  if (lane == 2 && !t.fx) tma_store_1d_pol(o.fw_out, def_static + CBX_TILE * 6 * n, (uint32_t)(CBX_TILE * 6 * n), hint, pol);
+  if (lane == 3 && nsvc > 0) tma_store_1d_pol(o.services, def_static + Q.def_svc, (uint32_t)(CBX_TILE * nsvc), hint, pol);
   tma_store_commit();
 }
 
@@ -281,7 +284,8 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
   uint8_t* s_zero = reinterpret_cast<uint8_t*>(smem + Q.zero);
   uint8_t* s_defst = reinterpret_cast<uint8_t*>(smem + Q.def_static);
   const uint32_t* s_init = s_tb + p.table_words;
-  const uint32_t table_bytes = (uint32_t)(p.table_words + ((L.S + 3) & ~3)) * 4u;
+  const uint32_t* s_fx = p.fwx_words ? s_init + ((L.S + 3) & ~3) : nullptr;  // live defender binding: firewall extension tables
+  const uint32_t table_bytes = (uint32_t)(p.table_words + ((L.S + 3) & ~3) + p.fwx_words) * 4u;
   const int nthreads = (int)blockDim.x;  // logic + encoder warps (+ the publisher warp when launches overlap)
   constexpr uint32_t kRowBytes = CBX_TILE * 4u;
   // Overlapped launches: the next launch of the stream may start its CTAs on every SM this launch's CTA has left (its CTAs
@@ -292,6 +296,7 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
   // dynamic tile order: this launch's OWN ticket counter (a fresh slot of a ring the host re-zeroes in halves: any number of
   // launches may be in flight at once when the grid is smaller than the machine, so no counter is shared or reset in-kernel)
   int* const tickets = p.tickets;
+  const bool fw_rows = s_fx != nullptr && def_encode && Q.i_fwin >= 0;  // live binding: per-env firewall rows, laid out by the logic warps
   const bool keep_state = p.l2_hints & 1, stream_masks = p.l2_hints & 2, stream_rest = p.l2_hints & 4, keep_tables = p.l2_hints & 8;
   const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
 
@@ -316,13 +321,14 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
   mbar_wait(&bars[0], 0);
   if (def_encode) {  // static parts of the defender observation for a tile of 32 envs: [32][6n] in, [32][6n] out, [32][nsvc]
     const int n6 = 6 * L.n;
-    for (int idx = tid; idx < CBX_TILE * n6; idx += nthreads) {
-      const int i = idx % n6, node = i / 6, r = i - node * 6;
-      const uint32_t dob = s_tb[s_tb[CBX_H_OFF_NODE] + node * CBX_NODE_WORDS + CBX_N_DEFOBS];
-      s_defst[idx] = (uint8_t)((dob >> r) & 1u);
-      s_defst[CBX_TILE * n6 + idx] = (uint8_t)((dob >> (8 + r)) & 1u);
-    }
-    for (int idx = tid; idx < CBX_TILE * L.nservices; idx += nthreads) s_defst[2 * CBX_TILE * n6 + idx] = 1;
+    if (!s_fx)
+      for (int idx = tid; idx < CBX_TILE * n6; idx += nthreads) {
+        const int i = idx % n6, node = i / 6, r = i - node * 6;
+        const uint32_t dob = s_tb[s_tb[CBX_H_OFF_NODE] + node * CBX_NODE_WORDS + CBX_N_DEFOBS];
+        s_defst[idx] = (uint8_t)((dob >> r) & 1u);
+        s_defst[CBX_TILE * n6 + idx] = (uint8_t)((dob >> (8 + r)) & 1u);
+      }
+    for (int idx = tid; idx < CBX_TILE * L.nservices; idx += nthreads) s_defst[Q.def_svc + idx] = 1;
   }
   fence_async_smem();
   __syncthreads();
@@ -461,7 +467,7 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
       CBX_PPROF(9)  // state tile + actions in
       const bool active = lane < n_valid;
       Ctx c;
-      c.st = lb + lane; c.sg = sg + lane; c.tb = s_tb; c.L = &L; c.cfg = &cfg; c.env = e0 + lane;
+      c.st = lb + lane; c.sg = sg + lane; c.tb = s_tb; c.L = &L; c.cfg = &cfg; c.env = e0 + lane; c.fx = s_fx;
       uint32_t att_done = 0, keep = 1;
       if (active) {
         logic_phase1(c, p, op, act + lane * AW, s_init, slice_of_kind, acc);
@@ -475,6 +481,7 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
       CBX_PPROF(8)  // waiting for a free descriptor slot
       Tile t;
       t.L = &L; t.tb = s_tb; t.st = lb; t.sg = sg; t.desc = desc; t.lut = s_lut; t.K = &p.enc; t.DW = DW;
+      t.fx = s_fx; t.init = s_init;
       // terminal observations of the envs that finished: encoded by this warp BEFORE the auto-reset (plain stores)
       if (att_done_mask && cfg.auto_reset && cfg.emit_terminal_obs && !reset_only) {
         if (active && ((att_done_mask >> lane) & 1u)) build_desc(c, desc + lane * DW, DW, nullptr);
@@ -533,6 +540,29 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
             for (int i = 0; i < L.n; ++i) ti[i] = (int8_t)((c.g(STG_DEF_TERM_INST + (i >> 5)) >> (i & 31)) & 1u);
           }
         }
+        if (fw_rows) {
+          // live binding: the defender has just acted on THIS environment -- its observation shows the installed bits after
+          // the move (a re-image removes the agent) and the rule lists as they are now, or the fresh environment's after its
+          // auto-reset (DWR:477)
+          uint32_t* de = desc + lane * DW;
+          if (!def_done)
+            for (int k = 0; k < L.Wn; ++k) de[D_OWNED + L.OW + k] = c.w(L.o_installed + k);
+          // ... and the tile's firewall rows [32][6n] bytes, this env's 6n bytes each way: six rule bytes per node from the six
+          // presence bits of the node's list (the byte LUT of the mask encoder), as three 16-bit stores
+          uint8_t* rin = reinterpret_cast<uint8_t*>(lb + Q.i_fwin) + lane * 6 * L.n;
+          uint8_t* rout = reinterpret_cast<uint8_t*>(lb + Q.i_fwout) + lane * 6 * L.n;
+          const uint32_t* grp = s_fx + CBX_FX_WORDS + s_tb[CBX_H_N_PORTS];
+          for (int node = 0; node < L.n; ++node) {
+            const uint32_t gw = grp[node];
+            const int gi = (int)(gw & 0xFFFFu), go = (int)(gw >> 16);
+            const uint2 bi = s_lut[(def_done ? s_init[L.o_fw + 2 * gi] : c.w(L.o_fw + 2 * gi)) & 63u];
+            const uint2 bo = s_lut[(def_done ? s_init[L.o_fw + 2 * go] : c.w(L.o_fw + 2 * go)) & 63u];
+            uint16_t* pi = reinterpret_cast<uint16_t*>(rin + 6 * node);
+            uint16_t* po = reinterpret_cast<uint16_t*>(rout + 6 * node);
+            pi[0] = (uint16_t)bi.x; pi[1] = (uint16_t)(bi.x >> 16); pi[2] = (uint16_t)bi.y;
+            po[0] = (uint16_t)bo.x; po[1] = (uint16_t)(bo.x >> 16); po[2] = (uint16_t)bo.y;
+          }
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_rdef[slot]);
@@ -556,9 +586,13 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
             if (lane == 5) tma_store_1d_pol(tm.priv, im.priv, (uint32_t)(CBX_TILE * 4 * wpe_priv), stream_rest, pol_stream);
             if (lane == 6 && dense) tma_store_1d_pol(tm.local, im.local, (uint32_t)(CBX_TILE * 4 * wpe_local), stream_rest, pol_stream);
           }
-          if (lane < 7) tma_store_commit();
+          if (fw_rows && n_valid == CBX_TILE) {  // the defender's observation is written for every env, kept attacker rows or not
+            if (lane == 7) tma_store_1d_pol(tm.fw_in, lb + Q.i_fwin, (uint32_t)(CBX_TILE * 6 * L.n), stream_rest, pol_stream);
+            if (lane == 8) tma_store_1d_pol(tm.fw_out, lb + Q.i_fwout, (uint32_t)(CBX_TILE * 6 * L.n), stream_rest, pol_stream);
+          }
+          if (lane < 9) tma_store_commit();
           if (overlap) {  // the tile before this one: its bulk copies (one group per lane) have completed -> report it
-            if (lane < 7) tma_store_wait_all_but(1);
+            if (lane < 9) tma_store_wait_all_but(1);
             __syncwarp();
             if (lane == 0 && done_j >= 0) tile_part_done(s_parts, done_j);
             done_j = j;
@@ -580,6 +614,10 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
             copy16(tm.priv, im.priv, CBX_TILE * wpe_priv / 4);
             if (dense) copy16(tm.local, im.local, CBX_TILE * wpe_local / 4);
           }
+          if (fw_rows && n_valid == CBX_TILE) {
+            copy16(tm.fw_in, lb + Q.i_fwin, CBX_TILE * 6 * L.n / 16);
+            copy16(tm.fw_out, lb + Q.i_fwout, CBX_TILE * 6 * L.n / 16);
+          }
           if (overlap) {
             __syncwarp();
             if (lane == 0 && done_j >= 0) tile_part_done(s_parts, done_j);
@@ -593,6 +631,11 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
           copy_field_rows(tm.props, im.props, wpe_props, n_valid, enc_mask, lane);
           copy_field_rows(tm.priv, im.priv, wpe_priv, n_valid, enc_mask, lane);
           if (dense) copy_field_rows(reinterpret_cast<int32_t*>(tm.local), reinterpret_cast<const int32_t*>(im.local), wpe_local, n_valid, enc_mask, lane);
+        }
+        if (fw_rows && n_valid != CBX_TILE) {  // ragged last tile: the valid envs' rows, byte by byte
+          const uint8_t* si = reinterpret_cast<const uint8_t*>(lb + Q.i_fwin);
+          const uint8_t* so = reinterpret_cast<const uint8_t*>(lb + Q.i_fwout);
+          for (int q = lane; q < n_valid * 6 * L.n; q += 32) { tm.fw_in[q] = (int8_t)si[q]; tm.fw_out[q] = (int8_t)so[q]; }
         }
         __syncwarp();
       }
@@ -651,6 +694,7 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
         mbar_wait(&bar_rdef[slot], (uint32_t)use & 1u);
         Tile t;
         t.L = &L; t.tb = s_tb; t.st = nullptr; t.sg = nullptr; t.desc = desc; t.lut = s_lut; t.K = &p.enc; t.DW = DW;
+        t.fx = s_fx; t.init = s_init;
         const Target tm = make_target(p.v, L, e0, false);
         encode_defender_tile<D>(t, tm, n_valid, wb, Q, s_defst, lane, stream_rest, pol_stream);
         if (n_valid == CBX_TILE) ++groups;

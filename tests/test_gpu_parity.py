@@ -246,12 +246,17 @@ def test_device_sampler_equals_oracle_sampler(mode):
     b.close()
 
 
+@pytest.mark.parametrize("kernel", ["cbx_pipe_kernel", "cbx_step_kernel"])
 @pytest.mark.parametrize("scn", ["toyctf", "chain10"])
-def test_live_defender_binding_vs_oracle(scn):
+def test_live_defender_binding_vs_oracle(scn, kernel, monkeypatch):
     """the LIVE LearningDefender binding -- re-imaging, block_traffic and allow_traffic act on the environment
     the attacker plays in; firewall rule lists are per-env state, one per alias group.  The oracle's version (explicit rule
     lists) is pinned on tapes recorded from the reference's classes with their binding refreshed at every reset
-    (tests/golden/marlon_*_live*.npz); here the CUDA version (two bits per group and port name) against it at scale."""
+    (tests/golden/marlon_*_live*.npz); here the CUDA version (two bits per group and port name) against it at scale -- on the
+    pipelined kernel (the default: the logic thread packs the rule bits into the encoder descriptor after the defender's move,
+    an encoder warp writes the tile's firewall rows) and on the fused kernel (CBX_PIPE=0: rows straight from the state tile)."""
+    if kernel == "cbx_step_kernel":
+        monkeypatch.setenv("CBX_PIPE", "0")
     if scn == "toyctf":
         comp = scenario.compile_scenario(scenarios.toyctf_environment())
         cfg = _toyctf_pair_cfg(defender_binding="live", attacker_max_timesteps=70, defender_max_timesteps=55, emit_terminal_obs=True)
@@ -264,7 +269,7 @@ def test_live_defender_binding_vs_oracle(scn):
     from marlon_b200.batch import Batch
 
     b = Batch(comp, cfg, 32)
-    assert b.kernel_info()["name"] == "cbx_step_kernel"  # per-env firewall rows: the fused kernel
+    assert b.kernel_info()["name"] == kernel
     b.close()
     # Chain-10 here keeps playing after an SLA breach: the worsening penalty -200 * k / 12 is not a whole number, and the running
     # returns are fp32 on the device (fp64 in the oracle): per-step rewards agree to 1e-6 relative, sums of returns likewise
