@@ -276,6 +276,40 @@ def test_live_defender_binding_vs_oracle(scn, kernel, monkeypatch):
     _run_against_oracle(comp, cfg, 2051, 260, seed=61, check_every=7, reset_at=100, stats_rtol=1e-6)
 
 
+class _TiledTape(dict):
+    """A reference tape with every per-env array repeated `reps` times along the env axis, one step at a time (nothing big is
+    materialised): env e of the wide batch replays tape column e % n_tapes."""
+
+    class _Rows:
+        def __init__(self, a, reps):
+            self.a, self.reps = a, reps
+
+        def __getitem__(self, s):
+            row = self.a[s]
+            return np.tile(row, (self.reps,) + (1,) * (row.ndim - 1))
+
+    def __init__(self, z, reps, steps):
+        super().__init__((k, (self._Rows(v, reps) if getattr(v, "ndim", 0) >= 2 and v.shape[0] == steps else v)) for k, v in z.items())
+
+    @property
+    def files(self):
+        return list(self)
+
+
+def test_chain10_attacker_only_4096_envs_replay_the_reference_tape():
+    """BASELINE.json configs[1] to the letter: CyberBattleChain-10 attacker-only, 4096 batched envs on one GPU, bit-exact against
+    the tape recorded from the unmodified reference (8 columns x 600 steps: env e replays column e % 8) -- every reward, flag,
+    observation field, mask checksum, terminal observation and the canonical state, every fourth step."""
+    meta, z = helpers.load_tape("marlon_chain10_attacker_only")
+    comp, cfg = helpers.config_from_meta(meta)
+    reps = 4096 // meta["n_tapes"]
+    b = _batch(comp, cfg, 4096)
+    assert b.kernel_info()["name"] == "cbx_pipe_kernel"
+    steps = helpers.replay(meta, _TiledTape(z, reps, meta["steps"]), b, b.numpy, b.export_state, check_every=4)
+    assert steps == meta["steps"]
+    b.close()
+
+
 def test_chain10_attacker_only_4096_envs_vs_oracle():
     """BASELINE.json configs[1]: CyberBattleChain-10 attacker-only, 4096 batched envs, bit-exact."""
     comp = scenario.compile_scenario(scenarios.chain_environment(10))
