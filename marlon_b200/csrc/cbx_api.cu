@@ -358,7 +358,8 @@ static int compute_layout(const cbx_scenario* s, const cbx_config* cfg, int64_t 
   L->S = o;
   int g = 11 + L->Wn;
   L->LEAKS = s->max_leak < L->LEAK ? s->max_leak : L->LEAK;
-  L->g_leaked = g; g += 4 * L->LEAKS;
+  L->g_leaked = g; g += L->LEAKS;  // one packed word per slot (cbx_device.cuh leak_pack)
+  if (L->C > 32767 || L->P > 255) return fail(CBX_ERR_UNSUPPORTED, "maximum_total_credentials > 32767 or more than 255 ports");
   L->g_inst = g; g += L->Wn;
   L->g_priv = g; g += (L->n + 15) / 16;
   L->G = g;

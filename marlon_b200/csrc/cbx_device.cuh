@@ -51,6 +51,16 @@ struct StepOut {
   int terminated, outcome, error, oob;
 };
 
+// One leaked-credential slot of the staging area (ENV:890-907: the observation row [1, cache index, target discovery index,
+// port]) in one word: bit 0 used | cache index << 1 (15 bits) | target discovery index << 16 (8) | port << 24 (8);
+// cbx_batch_create rejects bounds that do not fit.  leak_field(word, k) is element k of the row.
+__device__ __forceinline__ uint32_t leak_pack(uint32_t cache_index, uint32_t target, uint32_t port) {
+  return 1u | (cache_index << 1) | (target << 16) | (port << 24);
+}
+__device__ __forceinline__ uint32_t leak_field(uint32_t word, int k) {
+  return k == 0 ? (word & 1u) : k == 1 ? ((word >> 1) & 0x7FFFu) : k == 2 ? ((word >> 16) & 0xFFu) : (word >> 24);
+}
+
 struct Ctx {
   uint32_t* st;          // this env's column of the state tile: word w at st[w * CBX_TILE]
   uint32_t* sg;          // this env's column of the staging area
@@ -238,10 +248,7 @@ struct Ctx {
           sethalf(L->o_cache, c, (uint32_t)t);
           w(L->o_hdr) = (w(L->o_hdr) & ~0xFFFF00u) | ((uint32_t)(c + 1) << 8);
           if (slot < L->LEAKS) {    // ENV:890-907; a list never has more than LEAKS entries (target index is final: a node keeps its discovery index)
-            g(L->g_leaked + 4 * slot + 0) = 1;
-            g(L->g_leaked + 4 * slot + 1) = (uint32_t)c;
-            g(L->g_leaked + 4 * slot + 2) = byte(L->o_disc_idx, (int)tr[0]);
-            g(L->g_leaked + 4 * slot + 3) = tr[1];
+            g(L->g_leaked + slot) = leak_pack((uint32_t)c, byte(L->o_disc_idx, (int)tr[0]), tr[1]);
             slot++;
           }
         }
@@ -391,7 +398,7 @@ struct Ctx {
   __device__ void stage_reset_obs() const {  // blank observation + masks/properties of the fresh state (ENV:1197-1200)
     for (int k = 0; k < 8; ++k) g(STG_SCALARS + k) = 0;
     g(STG_SCALARS + 6) = (uint32_t)nd();
-    for (int k = 0; k < 4 * L->LEAKS; ++k) g(L->g_leaked + k) = 0;
+    for (int k = 0; k < L->LEAKS; ++k) g(L->g_leaked + k) = 0;
     g(STG_OBS_KIND) = OBS_NORMAL;
     snapshot_for_obs();
   }
@@ -426,7 +433,7 @@ struct Ctx {
     if (flag(HDR_DONE)) { so.error = CBX_E_STEP_AFTER_DONE; so.terminated = 1; g(STG_OBS_KIND) = OBS_KEEP; return so; }
     w(L->o_stepcount) += 1;
     for (int k = 0; k < 8; ++k) g(STG_SCALARS + k) = 0;
-    for (int k = 0; k < 4 * L->LEAKS; ++k) g(L->g_leaked + k) = 0;
+    for (int k = 0; k < L->LEAKS; ++k) g(L->g_leaked + k) = 0;
     Result r;
     if (execute_action(kind, a, &r)) {  // blank observation, reward 0, the built-in defender does not move
       g(STG_SCALARS + 6) = (uint32_t)nd();

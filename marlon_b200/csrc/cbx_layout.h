@@ -71,7 +71,7 @@ struct cbx_layout {
   int S;              // words per env
   // per-env staging words written by the game-logic thread for the encoder (word-major like the state tile):
   //   [0,8) scalars | 8 obs kind | 9 attacker done | 10 defender done | [11, 11+Wn) installed bits at defender done
-  int g_leaked;       // 4*LEAKS leaked-credential slots
+  int g_leaked;       // LEAKS leaked-credential slots, one packed word each (leak_pack)
   int g_inst;         // Wn: agent_installed bits as the observation sees them (before the built-in defender moves)
   int g_priv;         // ceil(n/16): privilege levels as the observation sees them
   int G;              // staging words per env

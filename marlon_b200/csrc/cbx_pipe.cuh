@@ -83,7 +83,7 @@ __device__ __forceinline__ void build_field_images(const Ctx& c, const uint32_t*
   for (int k = 0; k < 8; ++k) o[k] = (int32_t)c.g(STG_SCALARS + k);
   o = im.leak + e * 4 * LEAK;
 #pragma unroll 4
-  for (int k = 0; k < 4 * LEAK; ++k) o[k] = k < 4 * L->LEAKS ? (int32_t)c.g(L->g_leaked + k) : 0;
+  for (int k = 0; k < 4 * LEAK; ++k) o[k] = k < 4 * L->LEAKS ? (int32_t)leak_field(c.g(L->g_leaked + (k >> 2)), k & 3) : 0;
   o = im.cachem + e * 2 * NC;
 #pragma unroll 2
   for (int k = 0; k < NC; ++k) {

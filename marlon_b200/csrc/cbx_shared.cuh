@@ -510,7 +510,7 @@ __device__ __forceinline__ void encode_attacker_by_warp(const Tile& t, const Tar
     if (!(skip & 1)) {
     if (lane < 8) st_out(o.scalars + e * 8 + lane, (int32_t)t.g(e, STG_SCALARS + lane));
 #pragma unroll
-    for (int w = lane; w < 4 * LEAK; w += 32) st_out(o.leaked + e * 4 * LEAK + w, w < 4 * L->LEAKS ? (int32_t)t.g(e, L->g_leaked + w) : 0);
+    for (int w = lane; w < 4 * LEAK; w += 32) st_out(o.leaked + e * 4 * LEAK + w, w < 4 * L->LEAKS ? (int32_t)leak_field(t.g(e, L->g_leaked + (w >> 2)), w & 3) : 0);
 #pragma unroll
     for (int w = lane; w < 2 * NC; w += 32) {
       const int c = w >> 1;
@@ -616,7 +616,7 @@ __device__ __forceinline__ void encode_attacker(const Tile& t, const Target& o, 
   if (ENC == 2) { encode_attacker_by_warp<DimsToyCtf>(t, o, n_valid, enc_mask, wid, nw); return; }
   if (ENC == 3) { encode_attacker_by_warp<DimsChain10>(t, o, n_valid, enc_mask, wid, nw); return; }
   write_i32(o.scalars, 8, FastDiv(0u, 3u), n_valid, enc_mask, [&](int e, int wi) { return t.g(e, STG_SCALARS + wi); });
-  write_i32(o.leaked, 4 * L->LEAK, K.d_leaked, n_valid, enc_mask, [&](int e, int wi) { return wi < 4 * L->LEAKS ? t.g(e, L->g_leaked + wi) : 0u; });
+  write_i32(o.leaked, 4 * L->LEAK, K.d_leaked, n_valid, enc_mask, [&](int e, int wi) { return wi < 4 * L->LEAKS ? leak_field(t.g(e, L->g_leaked + (wi >> 2)), wi & 3) : 0u; });
   write_i32(o.cachem, 2 * L->C, K.d_cachem, n_valid, enc_mask, [&](int e, int wi) -> uint32_t {
     int c = wi >> 1;
     if (t.d(e, D_KIND) == OBS_BLANK || c >= (int)t.d(e, D_NC)) return 0u;

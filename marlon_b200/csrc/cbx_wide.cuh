@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(CBX_WIDE_WARPS * 32, 1) cbx_wide_kernel(const 
         uint4* so = reinterpret_cast<uint4*>(tm.scalars + (size_t)lane * 8);
         so[0] = make_uint4(c.g(STG_SCALARS + 0), c.g(STG_SCALARS + 1), c.g(STG_SCALARS + 2), c.g(STG_SCALARS + 3));
         so[1] = make_uint4(c.g(STG_SCALARS + 4), c.g(STG_SCALARS + 5), c.g(STG_SCALARS + 6), c.g(STG_SCALARS + 7));
-        for (int k = 0; k < L.LEAKS; ++k) nleak += c.g(L.g_leaked + 4 * k) != 0;  // slots fill in order (ENV:890-907)
+        for (int k = 0; k < L.LEAKS; ++k) nleak += c.g(L.g_leaked + k) != 0;  // slots fill in order (ENV:890-907)
       }
       // leaked_credentials [LEAK][4]: almost always all zero; a used slot is read from the staging words as it is
       for (int e = 0; e < n_valid; ++e) {
@@ -201,8 +201,8 @@ __global__ void __launch_bounds__(CBX_WIDE_WARPS * 32, 1) cbx_wide_kernel(const 
         emit_row(tm.leaked + (size_t)e * wpe_leak, 0, wpe_leak, wpe_leak, lane, [&](int w0) {
           const int slot = w0 >> 2;
           if (slot >= nl) return make_uint4(0u, 0u, 0u, 0u);
-          const uint32_t* q = sg + (L.g_leaked + 4 * slot) * CBX_TILE + e;
-          return make_uint4(q[0], q[CBX_TILE], q[2 * CBX_TILE], q[3 * CBX_TILE]);
+          const uint32_t q = sg[(L.g_leaked + slot) * CBX_TILE + e];
+          return make_uint4(leak_field(q, 0), leak_field(q, 1), leak_field(q, 2), leak_field(q, 3));
         });
       }
       // credential_cache_matrix [C][2] = (target discovery index, port) per cached credential: 16 bits per entry
