@@ -36,6 +36,8 @@ WORKLOADS = {
     "toyctf_scan": "CyberBattleToyCtf-v0 (N=12,C=10) CyberBattleEnv step with the built-in ScanAndReimageCompromisedMachines(0.6, 2, 5) "
                    "defender (configs[2] to the letter: notebook_withdefender.py:57-63 parameters, SLA 0.80, Philox detection draws, "
                    "auto-reset as under the SB3 VecEnv adapter)",
+    "chain100_scan": "CyberBattleChain-v0 size=100 (N=102,C=102) CyberBattleEnv step with the built-in ScanAndReimageCompromisedMachines(0.6, 2, 5) "
+                     "defender (config 4's other variant: SLA 0.80, Philox detection draws, auto-reset; factored masks)",
     "toyctf_live": "CyberBattleToyCtf-v0 (N=12,C=10) MARLon attacker+defender pair step with the LIVE LearningDefender binding (SURVEY 8f row 4: "
                    "the defender re-images / blocks / allows on the environment the attacker plays in; firewall rule lists are per-env state)",
     "random16": "CyberBattleRandom-v0, 16 generated 65-node networks (seeds 0-15) side by side in one batch (config 5: padded layout, "
@@ -53,6 +55,14 @@ def workload_config(mask_mode=0, workload="toyctf"):
             throws_on_invalid_actions=False, attacker_goal=config.AttackerGoal(own_atleast=6),
             defender_agent=config.ScanAndReimageCompromisedMachines(0.6, 2, 5), defender_constraint=config.DefenderConstraint(0.80),
             auto_reset=True, mask_mode=mask_mode, seed=2026)
+        return comp, cfg
+    if workload == "chain100_scan":
+        comp = scenario.compile_scenario(scenarios.chain_environment(100))
+        cfg = config.make_config(
+            _abi.MODE_CYBERBATTLE, maximum_node_count=102, maximum_total_credentials=102, maximum_discoverable_credentials_per_action=5,
+            throws_on_invalid_actions=False, attacker_goal=config.AttackerGoal(own_atleast_percent=1.0),
+            defender_agent=config.ScanAndReimageCompromisedMachines(0.6, 2, 5), defender_constraint=config.DefenderConstraint(0.80),
+            auto_reset=True, mask_mode=1, seed=2026)
         return comp, cfg
     if workload == "random16":
         from marlon_b200 import random_network

@@ -14,6 +14,10 @@ for w in chain100 random16; do
   timeout 200 python bench.py --workload $w --envs-per-gpu 131072 --steps 200 --warmup 5 --no-cpu-baseline --no-e2e > gpurun_out/bench_$w.log 2> gpurun_out/bench_$w.err; echo "rc=$?"
   python scripts/bench_line.py $w < gpurun_out/bench_$w.log | head -1
 done
+for w in chain100_scan; do
+  timeout 200 python bench.py --workload $w --envs-per-gpu 131072 --steps 200 --warmup 5 --no-cpu-baseline --no-e2e > gpurun_out/bench_$w.log 2> gpurun_out/bench_$w.err; python scripts/bench_line.py $w < gpurun_out/bench_$w.log | head -1
+done
+timeout 200 python bench.py --workload toyctf_live --no-cpu-baseline --no-e2e > gpurun_out/bench_toyctf_live.log 2> gpurun_out/bench_toyctf_live.err; python scripts/bench_line.py toyctf_live < gpurun_out/bench_toyctf_live.log | head -1
 timeout 200 python bench.py --workload toyctf_scan --no-cpu-baseline --no-e2e > gpurun_out/bench_toyctf_scan.log 2> gpurun_out/bench_toyctf_scan.err; python scripts/bench_line.py toyctf_scan < gpurun_out/bench_toyctf_scan.log | head -1
 timeout 300 python bench.py --no-cpu-baseline --no-e2e --envs-per-gpu 1048576 --steps 100 > gpurun_out/bench_1m.log 2> gpurun_out/bench_1m.err; python scripts/bench_line.py 1m < gpurun_out/bench_1m.log | head -1
 echo "== ncu launch list (default workload)"
