@@ -1,6 +1,6 @@
 """Build the CUDA library in-tree: ``marlon_b200/libcbx.so`` (sm_100a only, -lineinfo for ncu source pages).
 
-The four translation units (API, fused kernel + sampler + GAE, pipelined kernel, warp-per-tile kernel) compile in parallel
+The five translation units (API, fused kernel + sampler + GAE, pipelined kernel for each defender binding, warp-per-tile kernel) compile in parallel
 to ``build/*.o`` and are linked into one shared library.  ``-DCBX_EXPERIMENTS`` (``build_variant``) adds the section-skip
 timing switches and the plain-copy (non-TMA) staging variants; the release library has neither.
 """
@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libcbx.so")
 OBJ = os.path.join(HERE, "build")
-SOURCES = ["cbx_kernels.cu", "cbx_pipe.cu", "cbx_wide.cu", "cbx_api.cu"]
+SOURCES = ["cbx_kernels.cu", "cbx_pipe.cu", "cbx_pipe_live.cu", "cbx_wide.cu", "cbx_api.cu"]
 HEADERS = ["cbx_layout.h", "cbx_device.cuh", "cbx_shared.cuh", "cbx_pipe.cuh", "cbx_wide.cuh", os.path.join("..", "..", "include", "cbx.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--extended-lambda",
               "-Xcompiler", "-fPIC", "-diag-suppress", "177"]

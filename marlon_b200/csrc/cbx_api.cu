@@ -17,7 +17,7 @@ extern "C" {
 cudaError_t cbx_launch_step(const cbx_params* p, int op, int grid, int smem_bytes, int use_tma, cudaStream_t stream);
 cudaError_t cbx_launch_sample(const cbx_params* p, int32_t* att, int32_t* def, uint64_t seed, uint32_t step, cudaStream_t stream);
 cudaError_t cbx_kernel_attrs(int smem_bytes, int use_tma, int fast, int* blocks_per_sm);
-cudaError_t cbx_pipe_attrs(int enc, int smem_bytes);
+cudaError_t cbx_pipe_attrs(int enc, int smem_bytes, int live);
 cudaError_t cbx_launch_pipe(const cbx_params* p, int op, int grid, cudaStream_t stream);
 cudaError_t cbx_launch_gae(const float* rewards, const float* values, const uint8_t* episode_starts, const float* last_values,
                            const uint8_t* last_dones, float gamma, float lam, int T, int64_t n, float* advantages, float* returns,
@@ -573,7 +573,7 @@ static int create_impl(const cbx_scenario* const* scns, int n_scn, const int64_t
       bool ok = false;
       if (ewl || ewe) ok = plan_pipe(b->p, ewl ? atoi(ewl) : 4, ewe ? atoi(ewe) : 8, &Q);
       for (int k = 0; k < 4 && !ok && !(ewl || ewe); ++k) ok = plan_pipe(b->p, cand[k][0], cand[k][1], &Q);
-      if (ok && cbx_pipe_attrs(b->p.enc.warp_env, Q.total_bytes) == cudaSuccess) {
+      if (ok && cbx_pipe_attrs(b->p.enc.warp_env, Q.total_bytes, live ? 1 : 0) == cudaSuccess) {
         Q.enabled = 1;
         { const char* lt = getenv("CBX_PIPE_LOGIC_TMA"); Q.logic_tma = !(lt && lt[0] == '0'); }
         int per_sm = ect ? atoi(ect) : 1;

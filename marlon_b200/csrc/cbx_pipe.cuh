@@ -83,7 +83,11 @@ __device__ __forceinline__ void build_field_images(const Ctx& c, const uint32_t*
   for (int k = 0; k < 8; ++k) o[k] = (int32_t)c.g(STG_SCALARS + k);
   o = im.leak + e * 4 * LEAK;
 #pragma unroll 4
-  for (int k = 0; k < 4 * LEAK; ++k) o[k] = k < 4 * L->LEAKS ? (int32_t)leak_field(c.g(L->g_leaked + (k >> 2)), k & 3) : 0;
+  for (int k = 0; k < LEAK; ++k) {  // one packed staging word per slot -> the row's four words
+    const uint32_t q = k < L->LEAKS ? c.g(L->g_leaked + k) : 0u;
+    o[4 * k + 0] = (int32_t)leak_field(q, 0); o[4 * k + 1] = (int32_t)leak_field(q, 1);
+    o[4 * k + 2] = (int32_t)leak_field(q, 2); o[4 * k + 3] = (int32_t)leak_field(q, 3);
+  }
   o = im.cachem + e * 2 * NC;
 #pragma unroll 2
   for (int k = 0; k < NC; ++k) {
@@ -256,7 +260,10 @@ __device__ __forceinline__ void copy_field_rows(int32_t* dst, const int32_t* img
   }
 }
 
-template <int ENC>
+// LIVE: the live defender binding (per-env firewall rule lists).  A compile-time switch, not a test of cbx_params.fwx_words:
+// with Ctx::fx a constant nullptr the stale-binding instantiation carries none of the live branches of the game logic (as a
+// run-time pointer they cost the logic warps 12 % at 1 048 576 envs per launch, where the state does not stay in L2).
+template <int ENC, bool LIVE>
 __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant__ cbx_params p, const int op) {
   typedef typename DimsOf<ENC>::T D;
   extern __shared__ __align__(128) uint32_t smem[];
@@ -284,7 +291,7 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
   uint8_t* s_zero = reinterpret_cast<uint8_t*>(smem + Q.zero);
   uint8_t* s_defst = reinterpret_cast<uint8_t*>(smem + Q.def_static);
   const uint32_t* s_init = s_tb + p.table_words;
-  const uint32_t* s_fx = p.fwx_words ? s_init + ((L.S + 3) & ~3) : nullptr;  // live defender binding: firewall extension tables
+  const uint32_t* s_fx = LIVE ? s_init + ((L.S + 3) & ~3) : nullptr;  // live defender binding: firewall extension tables
   const uint32_t table_bytes = (uint32_t)(p.table_words + ((L.S + 3) & ~3) + p.fwx_words) * 4u;
   const int nthreads = (int)blockDim.x;  // logic + encoder warps (+ the publisher warp when launches overlap)
   constexpr uint32_t kRowBytes = CBX_TILE * 4u;
@@ -296,7 +303,7 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
   // dynamic tile order: this launch's OWN ticket counter (a fresh slot of a ring the host re-zeroes in halves: any number of
   // launches may be in flight at once when the grid is smaller than the machine, so no counter is shared or reset in-kernel)
   int* const tickets = p.tickets;
-  const bool fw_rows = s_fx != nullptr && def_encode && Q.i_fwin >= 0;  // live binding: per-env firewall rows, laid out by the logic warps
+  const bool fw_rows = LIVE && def_encode && Q.i_fwin >= 0;  // live binding: per-env firewall rows, laid out by the logic warps
   const bool keep_state = p.l2_hints & 1, stream_masks = p.l2_hints & 2, stream_rest = p.l2_hints & 4, keep_tables = p.l2_hints & 8;
   const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
 
@@ -754,6 +761,47 @@ __global__ void __launch_bounds__(512, 1) cbx_pipe_kernel(const __grid_constant_
   // stream order for whatever follows the NEXT launch: a grid that ends implies the grid before it has ended (it has, long
   // ago -- its tiles were consumed above -- so this never waits in practice)
   if (overlap) asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+
+// launch helpers, one set per binding (cbx_pipe.cu: stale, cbx_pipe_live.cu: live -- two translation units compile in parallel)
+template <bool LIVE>
+static cudaError_t pipe_attrs_t(int enc, int smem_bytes) {
+  switch (enc) {
+    case 3: return cudaFuncSetAttribute(cbx_pipe_kernel<3, LIVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    case 2: return cudaFuncSetAttribute(cbx_pipe_kernel<2, LIVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    default: return cudaFuncSetAttribute(cbx_pipe_kernel<1, LIVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  }
+}
+template <bool LIVE>
+static cudaError_t launch_pipe_t(const cbx_params* p, int op, int grid, cudaStream_t stream) {
+  // overlapped launches: one more warp, the publisher of the per-tile completion counters
+  const int threads = (p->pipe.wl + p->pipe.we + (p->overlap ? 1 : 0)) * 32;
+  if (p->overlap) {
+    // programmatic dependent launch: this grid's CTAs may start while the previous launch of the stream is still draining;
+    // the kernel orders its accesses tile by tile through cbx_params.tile_done
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = (size_t)p->pipe.total_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    switch (p->enc.warp_env) {
+      case 3: return cudaLaunchKernelEx(&cfg, cbx_pipe_kernel<3, LIVE>, *p, op);
+      case 2: return cudaLaunchKernelEx(&cfg, cbx_pipe_kernel<2, LIVE>, *p, op);
+      default: return cudaLaunchKernelEx(&cfg, cbx_pipe_kernel<1, LIVE>, *p, op);
+    }
+  }
+  switch (p->enc.warp_env) {
+    case 3: cbx_pipe_kernel<3, LIVE><<<grid, threads, p->pipe.total_bytes, stream>>>(*p, op); break;
+    case 2: cbx_pipe_kernel<2, LIVE><<<grid, threads, p->pipe.total_bytes, stream>>>(*p, op); break;
+    default: cbx_pipe_kernel<1, LIVE><<<grid, threads, p->pipe.total_bytes, stream>>>(*p, op); break;
+  }
+  return cudaGetLastError();
 }
 
 }  // namespace cbx
