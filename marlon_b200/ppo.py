@@ -66,6 +66,9 @@ class MultiDiscretePolicy(nn.Module):
             off += n
         self.register_buffer("_index", index.reshape(-1), persistent=False)
         self.register_buffer("_valid", valid, persistent=False)
+        # one head much larger than the rest (generated networks: 192 credentials next to 3 action kinds) would make the padded
+        # tensor several times the logits: such spaces are evaluated head by head instead
+        self._padded = A * K <= 2 * sum(self.nvec)
 
     @classmethod
     def for_space(cls, observation: Dict[str, torch.Tensor], nvec, feature_keys, hidden: int = 64) -> "MultiDiscretePolicy":
@@ -80,8 +83,30 @@ class MultiDiscretePolicy(nn.Module):
         logits = self.pi(h).index_select(1, self._index).reshape(-1, A, K).masked_fill(~self._valid, float("-inf"))
         return torch.log_softmax(logits, dim=2), self.vf(h).squeeze(1)
 
+    def _per_head(self, obs, actions=None):
+        """The same distribution head by head (no padding): -> (actions [n, A], values, log_prob, entropy)."""
+        x = obs if torch.is_tensor(obs) else flatten_observation(obs, self.feature_keys)
+        h = self.body(x)
+        logits, values = self.pi(h), self.vf(h).squeeze(1)
+        picked, lps, ents, off = [], 0.0, 0.0, 0
+        for a, n in enumerate(self.nvec):
+            lp = torch.log_softmax(logits[:, off:off + n], dim=1)
+            off += n
+            if actions is None:
+                u = torch.rand_like(lp).clamp_(1e-20, 1.0)
+                act = torch.argmax(lp - torch.log(-torch.log(u)), dim=1)
+            else:
+                act = actions[:, a].long()
+            picked.append(act)
+            lps = lps + lp.gather(1, act.unsqueeze(1)).squeeze(1)
+            ents = ents - (torch.exp(lp) * lp).sum(1)
+        return torch.stack(picked, dim=1), values, lps, ents
+
     def forward(self, obs, action_masks=None):
         """-> (actions int32 [n, A], values [n], log_probs [n]); the call signature ``rollout.collect_rollouts`` expects."""
+        if not self._padded:
+            actions, values, lp, _ = self._per_head(obs)
+            return actions.to(torch.int32), values, lp
         logp, values = self._log_probs(obs)
         u = torch.rand_like(logp).clamp_(1e-20, 1.0)
         actions = torch.argmax(logp - torch.log(-torch.log(u)), dim=2)  # Gumbel-max: a sample of each head's categorical
@@ -89,6 +114,9 @@ class MultiDiscretePolicy(nn.Module):
 
     def evaluate_actions(self, obs, actions):
         """-> (values, log_prob, entropy) of `actions` under the current policy (SB3 ``ActorCriticPolicy.evaluate_actions``)."""
+        if not self._padded:
+            _, values, lp, ent = self._per_head(obs, actions)
+            return values, lp, ent
         logp, values = self._log_probs(obs)
         chosen = logp.gather(2, actions.long().unsqueeze(2)).squeeze(2).sum(1)
         safe = logp.masked_fill(~self._valid, 0.0)  # not where(valid, p * logp, 0): 0 * -inf poisons the gradient

@@ -57,6 +57,22 @@ def test_rollout_buffer_get_covers_every_sample_once_in_sb3_order():
     assert whole.actions.shape[0] == T * n
 
 
+def test_skewed_action_space_is_evaluated_head_by_head_with_the_same_distribution():
+    """One head much larger than the others (generated networks: 192 credentials next to 3 action kinds): the padded batch of
+    heads would be several times the logits, so the policy evaluates head by head -- same log-probabilities and entropies."""
+    torch.manual_seed(0)
+    pol = ppo.MultiDiscretePolicy(50, [3, 72, 5, 72, 72, 9, 72, 72, 7, 192], ["x"])
+    assert not pol._padded
+    x = torch.randn(64, 50)
+    actions, values, lp = pol(x)
+    assert actions.dtype == torch.int32 and all(int(actions[:, a].max()) < n for a, n in enumerate(pol.nvec))
+    v1, lp1, ent1 = pol.evaluate_actions(x, actions)
+    assert torch.allclose(lp, lp1, atol=1e-5) and torch.allclose(values, v1)
+    pol._padded = True  # the padded evaluation of the same heads
+    v2, lp2, ent2 = pol.evaluate_actions(x, actions)
+    assert torch.allclose(lp1, lp2, atol=1e-5) and torch.allclose(ent1, ent2, atol=1e-4) and torch.allclose(v1, v2)
+
+
 @pytest.mark.gpu
 def test_collect_rollouts_and_ppo_update_on_device():
     from marlon_b200.rollout import collect_rollouts
