@@ -106,6 +106,13 @@ __global__ void __launch_bounds__(CBX_WIDE_WARPS * 32, 1) cbx_wide_kernel(const 
     if (lane == 0) x = gw + atomicAdd(p.tile_counter, 1);
     return __shfl_sync(kFull, x, 0);
   };
+  __shared__ __align__(8) uint64_t s_abar[CBX_WIDE_WARPS];  // one mbarrier per warp: the tile's action block
+  uint32_t aphase = 0;
+  if (lane == 0) {
+    mbar_init(&s_abar[warp], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
   for (int tile = (int)blockIdx.x * nw + warp; tile < p.n_tiles; tile = next_tile(tile)) {
     const int64_t e0 = (int64_t)tile * CBX_TILE;
     const int n_valid = (int)min((int64_t)CBX_TILE, p.n_envs - e0);
@@ -117,7 +124,25 @@ __global__ void __launch_bounds__(CBX_WIDE_WARPS * 32, 1) cbx_wide_kernel(const 
     for (int r = lane; r < L.S; r += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(gst + (size_t)r * CBX_TILE));
     auto load_actions = [&]() {
       if (reset_only) return;
-      if (p.att_actions && (who_att || !marlon))
+      const bool la = p.att_actions && (who_att || !marlon);
+      // a full tile's int32 actions are one contiguous 16-byte aligned block per agent: two bulk copies on the warp's mbarrier
+      // (22 dependent load -> shared-store pairs took 9 us per tile; the image area was last used through the generic proxy)
+      const bool bulk = !p.act_i16 && n_valid == CBX_TILE && (la || def_on) &&
+                        ((((uintptr_t)p.att_actions) | ((uintptr_t)p.def_actions)) & 15u) == 0;
+      if (bulk) {
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          const uint32_t att_bytes = la ? (uint32_t)(CBX_TILE * AW * 4) : 0u, def_bytes = def_on ? (uint32_t)(CBX_TILE * 12 * 4) : 0u;
+          mbar_expect_tx(&s_abar[warp], att_bytes + def_bytes);
+          if (att_bytes) tma_load_1d(act, p.att_actions + e0 * AW, att_bytes, &s_abar[warp]);
+          if (def_bytes) tma_load_1d(act + CBX_TILE * 10, p.def_actions + e0 * 12, def_bytes, &s_abar[warp]);
+        }
+        mbar_wait(&s_abar[warp], aphase);
+        aphase ^= 1u;
+        return;
+      }
+      if (la)
         for (int q = lane; q < n_valid * AW; q += 32) act[q] = load_act(p.att_actions, e0 * AW + q, p.act_i16);
       if (def_on)
         for (int q = lane; q < n_valid * 12; q += 32) act[CBX_TILE * 10 + q] = load_act(p.def_actions, e0 * 12 + q, p.act_i16);
