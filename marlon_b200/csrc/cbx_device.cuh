@@ -51,6 +51,14 @@ struct StepOut {
   int terminated, outcome, error, oob;
 };
 
+// Independent state loads issued together by the loops that walk a per-node array: 4 where the state is read in place from
+// global memory (cbx_wide.cu defines CBX_STATE_IN_PLACE), 1 where the state tile is in shared memory.
+#ifdef CBX_STATE_IN_PLACE
+constexpr int kLoadBatch = 4;
+#else
+constexpr int kLoadBatch = 1;
+#endif
+
 // One leaked-credential slot of the staging area (ENV:890-907: the observation row [1, cache index, target discovery index,
 // port]) in one word: bit 0 used | cache index << 1 (15 bits) | target discovery index << 16 (8) | port << 24 (8);
 // cbx_batch_create rejects bounds that do not fit.  leak_field(word, k) is element k of the row.
@@ -313,20 +321,30 @@ struct Ctx {
   __device__ int tick(int o_cd, int o_notrun /* -1 for the shadow copy */) const {
     int down = 0;
     const int words = (L->n + 3) >> 2;
-    for (int q = 0; q < words; ++q) {
-      uint32_t x = w(o_cd + q);
-      if (!x) continue;
+    // kLoadBatch words are loaded before the arithmetic: with the state in place (cbx_wide_kernel) every load is an L2 round
+    // trip, and issued one per iteration they took 10 us per tick at 26 words (+5 % env-steps/s with four in flight); with
+    // the state tile in shared memory the plain loop is the shorter code
+    for (int q0 = 0; q0 < words; q0 += kLoadBatch) {
+      uint32_t xs[kLoadBatch];
 #pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        uint32_t c = (x >> (8 * b)) & 0xFFu;
-        if (c) {
-          c -= 1;
-          x = (x & ~(0xFFu << (8 * b))) | (c << (8 * b));
-          if (c) down++;
-          else if (o_notrun >= 0) clrbit(o_notrun, q * 4 + b);
+      for (int j = 0; j < kLoadBatch; ++j) xs[j] = q0 + j < words ? w(o_cd + q0 + j) : 0u;
+#pragma unroll
+      for (int j = 0; j < kLoadBatch; ++j) {
+        uint32_t x = xs[j];
+        if (!x) continue;
+        const int q = q0 + j;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          uint32_t c = (x >> (8 * b)) & 0xFFu;
+          if (c) {
+            c -= 1;
+            x = (x & ~(0xFFu << (8 * b))) | (c << (8 * b));
+            if (c) down++;
+            else if (o_notrun >= 0) clrbit(o_notrun, q * 4 + b);
+          }
         }
+        w(o_cd + q) = x;
       }
-      w(o_cd + q) = x;
     }
     return down;
   }
@@ -391,9 +409,21 @@ struct Ctx {
     w(L->o_avail) &= fx ? ~0xFFFFu : ~0xFFu;
   }
   __device__ void snapshot_for_obs() const {
-    for (int k = 0; k < L->Wn; ++k) g(L->g_inst + k) = w(L->o_installed + k);
     const int pw = (L->n + 15) >> 4;
-    for (int k = 0; k < pw; ++k) g(L->g_priv + k) = w(L->o_priv + k);
+    for (int k0 = 0; k0 < L->Wn + pw; k0 += kLoadBatch) {  // loads kLoadBatch at a time, then the staging stores
+      uint32_t v[kLoadBatch];
+#pragma unroll
+      for (int j = 0; j < kLoadBatch; ++j) {
+        const int k = k0 + j;
+        v[j] = k < L->Wn ? w(L->o_installed + k) : k < L->Wn + pw ? w(L->o_priv + k - L->Wn) : 0u;
+      }
+#pragma unroll
+      for (int j = 0; j < kLoadBatch; ++j) {
+        const int k = k0 + j;
+        if (k < L->Wn) g(L->g_inst + k) = v[j];
+        else if (k < L->Wn + pw) g(L->g_priv + k - L->Wn) = v[j];
+      }
+    }
   }
   __device__ void stage_reset_obs() const {  // blank observation + masks/properties of the fresh state (ENV:1197-1200)
     for (int k = 0; k < 8; ++k) g(STG_SCALARS + k) = 0;

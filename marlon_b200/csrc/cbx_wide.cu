@@ -1,4 +1,5 @@
 // cbx_wide.cu -- translation unit of the warp-per-tile step kernel for large per-env state (cbx_wide.cuh) and its launch helpers.
+#define CBX_STATE_IN_PLACE 1  // cbx_device.cuh: loops over per-node state arrays keep several loads in flight
 #include "cbx_shared.cuh"
 #include "cbx_wide.cuh"
 
